@@ -1,0 +1,117 @@
+/*
+ * slode_b200 -- C ABI of the B200-native latent-ODE solve (sm_100a).
+ *
+ * Drop-in boundary for the ONE hot path of paidamoyo/structured_latent_ODEs: the batched
+ * integration of the latent ODE and its reverse-mode gradient.  The reference has no FFI of its
+ * own (it is pure Python); the boundary it crosses is the third-party call
+ *
+ *     torchdiffeq.odeint_adjoint(func=, y0=, t=, method=)   models/blackbox_ode.py:41-42
+ *     torchdiffeq.odeint(func=, y0=, t=, method=)           models/blackbox_ode.py:44-45
+ *
+ * with func = OdeFunc(z, Dynamics) (models/blackbox_ode.py:50-61, 64-109).  Each entry point
+ * below replaces one leg of that call for one right-hand side.  The Python host
+ * (structured_latent_odes_b200/torchdiffeq_api.py) binds these symbols with ctypes inside a
+ * torch.autograd.Function; INTEGRATION.md shows the two-line change on the reference side.
+ *
+ * Conventions (all entry points)
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never frees
+ *     or retains it; outputs are caller-allocated;
+ *   - all arrays are float32; `stream` is a cudaStream_t passed as void*; work is enqueued
+ *     asynchronously on it and the call returns immediately;
+ *   - return value 0 = ok, otherwise an SLODE_E* code; slode_last_error() gives the message of
+ *     the last failure on the calling thread;
+ *   - thread-safe; calls on different streams of one device are serialised on the device
+ *     (they share one packed-weight buffer in constant memory, ordered by an event).
+ *
+ * The blackbox right-hand side (Dynamics.forward, models/blackbox_ode.py:97-109):
+ *     x = [t, z];  h = relu(W1 x + b1);  f = sigmoid(Wg h + bg) - sigmoid(Wd h + bd) * state
+ * enters as   h_j(t) = relu(w1t[j] * t + c[b][j])   with
+ *     w1t = W1[:, 0]            (the column that multiplies t, :72,:101)
+ *     c   = z @ W1[:, 1:]^T + b1   (B,H)  -- time-invariant per trajectory, a plain GEMM done by
+ *                                            the host with cuBLAS (torch.addmm)
+ * Wg/Wd are dyanamics_growth.weight / dyanmics_degradation.weight, torch Linear layout (S,H).
+ */
+#ifndef SLODE_B200_H
+#define SLODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define SLODE_OK 0
+#define SLODE_EINVAL 1      /* bad argument (null pointer, negative size, unknown method/mode) */
+#define SLODE_EUNSUPPORTED 2 /* (H,S) / option combination not compiled in: no generic fallback */
+#define SLODE_ECUDA 3       /* a CUDA runtime call failed; see slode_last_error() */
+
+/* torchdiffeq `method=` strings the reference can pass (config.solver, data/x/config_x.py) */
+#define SLODE_METHOD_EULER 0
+#define SLODE_METHOD_MIDPOINT 1
+#define SLODE_METHOD_RK4 2      /* torchdiffeq's rk4 == 3/8 rule (rk4_alt_step_func) */
+#define SLODE_METHOD_DOPRI5 3
+
+/* backward modes */
+#define SLODE_BWD_DISCRETE 0 /* exact gradient of the unrolled solver == torchdiffeq.odeint + autograd
+                                (adjoint_solver=False, models/blackbox_ode.py:44-45) */
+#define SLODE_BWD_TDE_ADJOINT 1 /* torchdiffeq.odeint_adjoint semantics (adjoint_solver=True, :41-42):
+                                   continuous adjoint re-discretised with the same method, state reset
+                                   to the stored forward value at every output time */
+
+/* slode_query(what) */
+#define SLODE_Q_VERSION 0
+#define SLODE_Q_SM_ARCH 1        /* 100 */
+#define SLODE_Q_MAX_HIDDEN 2     /* largest H compiled for the register-resident kernels */
+#define SLODE_Q_MAX_STATE 3      /* largest S */
+#define SLODE_Q_N_SHAPES 4       /* number of compiled (H,S) pairs */
+#define SLODE_Q_SHAPE_BASE 100   /* 100+2i -> H of pair i, 101+2i -> S of pair i */
+#define SLODE_Q_FWD_LAUNCHES 10  /* kernels launched by the last fwd call on this thread */
+#define SLODE_Q_BWD_LAUNCHES 11
+
+int slode_query(int what);
+const char* slode_last_error(void);
+
+/* 1 if kernels for this (H,S) pair exist, else 0 */
+int slode_mlp_supported(int H, int S);
+
+/*
+ * Forward fixed-grid solve; replaces torchdiffeq.odeint(func=OdeFunc, y0, t, method) for
+ * method in {euler, midpoint, rk4} with grid == t (models/blackbox_ode.py:44-45).
+ *   t    (T)    strictly monotone output times == solver grid
+ *   c    (B,H)  row-major, see above;   y0 (B,S) row-major
+ *   sol  out: element (i,b,s) at sol[i*sol_stride_t + b*sol_stride_b + s]; sol[0] = y0.
+ *        (T,B,S)-contiguous (torchdiffeq's layout) is stride_t=B*S, stride_b=S;
+ *        (B,T,S)-contiguous (what solve_ODE's permute hands the decoder) is stride_t=S, stride_b=T*S.
+ */
+int slode_mlp_fixed_fwd(int method, int64_t B, int T, int H, int S,
+                        const float* t, const float* c, const float* y0,
+                        const float* w1t, const float* Wg, const float* bg,
+                        const float* Wd, const float* bd,
+                        float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                        void* stream);
+
+/*
+ * Reverse-mode gradient of slode_mlp_fixed_fwd (one reverse sweep over the stored grid states;
+ * stages are recomputed from sol[i], nothing else is checkpointed).
+ *   grad_sol  upstream dL/dsol, same indexing convention as sol (own strides)
+ *   grad_y0   out (B,S);   grad_c  out (B,H)  (host turns it into dz, dW1[:,1:], db1 with cuBLAS)
+ *   grad_w    in/out, ACCUMULATED into (caller zero-fills): flat
+ *             [ dw1t (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) ]
+ * mode SLODE_BWD_DISCRETE    : exact discrete adjoint (parity with odeint + autograd);
+ * mode SLODE_BWD_TDE_ADJOINT : odeint_adjoint emulation (grad_c then only feeds dW1/db1: the
+ *                              reference drops dz through the dynamics in this mode).
+ */
+int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
+                        const float* t, const float* c,
+                        const float* w1t, const float* Wg, const float* bg,
+                        const float* Wd, const float* bd,
+                        const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                        const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
+                        float* grad_y0, float* grad_c, float* grad_w,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLODE_B200_H */

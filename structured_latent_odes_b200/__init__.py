@@ -1,0 +1,15 @@
+"""structured_latent_odes_b200 -- B200-native (sm_100a) latent-ODE solve for SLODE.
+
+Public surface (mirrors the reference's hot path):
+
+    odeint, odeint_adjoint        torchdiffeq-shaped calls (models/blackbox_ode.py:40-45)
+    OdeModel, OdeFunc, Dynamics   module mirrors (models/blackbox_ode.py)
+    install_as_torchdiffeq        make `import torchdiffeq` in unmodified reference code resolve here
+
+All compute goes through ``csrc/libslode_b200.so`` (C ABI in ``include/slode_b200.h``); there is no
+CPU or eager fallback.
+"""
+from .torchdiffeq_api import odeint, odeint_adjoint, install_as_torchdiffeq, is_blackbox_func  # noqa: F401
+from .blackbox_ode import OdeModel, OdeFunc, Dynamics  # noqa: F401
+
+__version__ = "0.1.0"

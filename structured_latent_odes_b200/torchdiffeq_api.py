@@ -1,0 +1,236 @@
+"""``torchdiffeq``-shaped entry points backed by the sm_100a kernels.
+
+The reference crosses exactly one boundary on its hot path (``models/blackbox_ode.py:40-45``)::
+
+    sol = torchdiffeq.odeint_adjoint(func=d_states_d_t, y0=init_state, t=self.times, method=self.solver)
+    sol = torchdiffeq.odeint(func=d_states_d_t, y0=init_state, t=self.times, method=self.solver)
+
+``odeint`` / ``odeint_adjoint`` below keep that signature and the ``(len(t), *y0.shape)`` return
+layout.  They are not generic solvers: ``func`` must be one of the right-hand sides this package has
+a fused kernel for (the reference's ``OdeFunc`` over ``Dynamics``, or ``CvsMechanistic``); anything
+else raises ``NotImplementedError`` -- there is deliberately no eager / CPU fallback.
+
+Gradient semantics
+  * ``odeint``          -> exact discrete adjoint of the unrolled solver (what autograd through
+                           ``torchdiffeq.odeint`` gives, ``adjoint_solver=False``).
+  * ``odeint_adjoint``  -> torchdiffeq's continuous adjoint re-discretised with the same method and
+                           restarted from the stored forward state at every output time; gradients
+                           go to ``y0`` and ``func.parameters()`` only -- ``OdeFunc.constants`` (z) is
+                           a plain tensor and gets none through the dynamics.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _cabi
+
+__all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_func"]
+
+FIXED_METHODS = ("euler", "midpoint", "rk4")
+
+
+# ----------------------------------------------------------------------------------------------
+# func recognition
+# ----------------------------------------------------------------------------------------------
+def is_blackbox_func(func) -> bool:
+    """True for the reference's ``OdeFunc`` (``models/blackbox_ode.py:50-61``) or our mirror of it."""
+    dyn = getattr(func, "dynamics", None)
+    return (
+        dyn is not None
+        and isinstance(getattr(dyn, "dynamics_hidden", None), nn.Linear)
+        and isinstance(getattr(dyn, "dyanamics_growth", None), nn.Linear)
+        and isinstance(getattr(dyn, "dyanmics_degradation", None), nn.Linear)
+        and torch.is_tensor(getattr(func, "constants", None))
+    )
+
+
+def _check_blackbox(func):
+    dyn = func.dynamics
+    prod = getattr(dyn, "prod", None)
+    if isinstance(prod, nn.Sequential) and len(prod) > 1 and not isinstance(prod[1], nn.ReLU):
+        raise NotImplementedError(
+            f"hidden activation {type(prod[1]).__name__}: the fused kernels implement the ReLU hidden layer "
+            "that OdeModel always builds (models/blackbox_ode.py:26-27)")
+    z = func.constants
+    hid, gro, deg = dyn.dynamics_hidden, dyn.dyanamics_growth, dyn.dyanmics_degradation
+    if z.ndim != 2 or hid.in_features != z.shape[1] + 1:
+        raise ValueError(f"constants {tuple(z.shape)} do not match dynamics_hidden.in_features={hid.in_features}")
+    if gro.in_features != hid.out_features or deg.in_features != hid.out_features or gro.out_features != deg.out_features:
+        raise ValueError("inconsistent Dynamics layer sizes")
+    if hid.bias is None or gro.bias is None or deg.bias is None:
+        raise NotImplementedError("Dynamics layers without bias")
+    return z, hid, gro, deg
+
+
+def _check_common(y0, t, method, options, event_fn):
+    if event_fn is not None:
+        raise NotImplementedError("event_fn is not used by the reference and is not supported")
+    if not torch.is_tensor(y0):
+        raise NotImplementedError("tuple states are not supported (the reference passes one (B,S) tensor)")
+    if method is None:
+        method = "dopri5"  # torchdiffeq's default
+    if method not in _cabi.METHODS:
+        raise ValueError(f"Invalid method {method!r}; supported: {sorted(_cabi.METHODS)}")
+    if not y0.is_cuda:
+        raise RuntimeError("structured_latent_odes_b200 runs on CUDA tensors only (no CPU fallback); "
+                           f"got y0 on {y0.device}")
+    if y0.dtype != torch.float32:
+        raise TypeError(f"y0 must be float32, got {y0.dtype}")
+    if y0.ndim != 2:
+        raise ValueError(f"y0 must be (B, S), got {tuple(y0.shape)}")
+    if not torch.is_tensor(t) or t.ndim != 1 or t.numel() < 1:
+        raise ValueError("t must be a one-dimensional tensor")
+    if not t.is_floating_point():
+        raise TypeError("t must be floating point")
+    t = t.detach().to(device=y0.device, dtype=torch.float32).contiguous()
+    if t.numel() > 1:
+        d = t[1:] - t[:-1]
+        if not (bool((d > 0).all()) or bool((d < 0).all())):
+            raise ValueError("t must be strictly increasing or decreasing")
+    if method in FIXED_METHODS and options:
+        raise NotImplementedError(f"options={options!r} for fixed-grid solvers (the reference passes none: "
+                                  "the solver grid is t itself)")
+    return t, method
+
+
+# ----------------------------------------------------------------------------------------------
+# blackbox MLP dynamics, fixed grid
+# ----------------------------------------------------------------------------------------------
+def _ptr(x):
+    return x.data_ptr() if x is not None else None
+
+
+def _dense_tbs_strides(x):
+    """(stride_t, stride_b) of a (T,B,S) tensor usable by the kernels, or None if it must be copied."""
+    st, sb, ss = x.stride()
+    T, B, S = x.shape
+    if S > 1 and ss != 1:
+        return None
+    if (T > 1 and st <= 0) or (B > 1 and sb <= 0):
+        return None
+    return st, sb
+
+
+class _MlpFixedSolve(torch.autograd.Function):
+    """sol = solve(y0, c, weights, t); one forward kernel, one reverse-sweep kernel."""
+
+    @staticmethod
+    def forward(ctx, y0, c, w1t, Wg, bg, Wd, bd, t, method_id, mode, layout):
+        B, S = y0.shape
+        H = c.shape[1]
+        T = t.numel()
+        y0c, cc = y0.contiguous(), c.contiguous()
+        w = [x.detach().contiguous() for x in (w1t, Wg, bg, Wd, bd)]
+        if layout == "bts":  # (B,T,S)-contiguous storage, returned as a (T,B,S) view
+            store = torch.empty((B, T, S), device=y0.device, dtype=torch.float32)
+            sol = store.permute(1, 0, 2)
+        else:
+            sol = torch.empty((T, B, S), device=y0.device, dtype=torch.float32)
+        st, sb = sol.stride(0), sol.stride(1)
+        with torch.cuda.device(y0.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _cabi.lib().slode_mlp_fixed_fwd(method_id, B, T, H, S, _ptr(t), _ptr(cc), _ptr(y0c),
+                                                 *[_ptr(x) for x in w], _ptr(sol), st, sb, stream)
+        _cabi.check(rc, "slode_mlp_fixed_fwd")
+        ctx.save_for_backward(cc, *w, t, sol)
+        ctx.method_id, ctx.mode = method_id, mode
+        return sol
+
+    @staticmethod
+    def backward(ctx, grad_sol):
+        cc, w1t, Wg, bg, Wd, bd, t, sol = ctx.saved_tensors
+        T, B, S = sol.shape
+        H = cc.shape[1]
+        strides = _dense_tbs_strides(grad_sol)
+        if strides is None or grad_sol.dtype != torch.float32:
+            grad_sol = grad_sol.to(torch.float32).contiguous()
+            strides = (grad_sol.stride(0), grad_sol.stride(1))
+        grad_y0 = torch.empty((B, S), device=sol.device, dtype=torch.float32)
+        grad_c = torch.empty((B, H), device=sol.device, dtype=torch.float32)
+        grad_w = torch.zeros(H + 2 * (S * H + S), device=sol.device, dtype=torch.float32)
+        with torch.cuda.device(sol.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _cabi.lib().slode_mlp_fixed_bwd(
+                ctx.method_id, ctx.mode, B, T, H, S, _ptr(t), _ptr(cc), _ptr(w1t), _ptr(Wg), _ptr(bg), _ptr(Wd),
+                _ptr(bd), _ptr(sol), sol.stride(0), sol.stride(1), _ptr(grad_sol), strides[0], strides[1],
+                _ptr(grad_y0), _ptr(grad_c), _ptr(grad_w), stream)
+        _cabi.check(rc, "slode_mlp_fixed_bwd")
+        o = 0
+        gw1t = grad_w[o:o + H]; o += H
+        gWg = grad_w[o:o + S * H].view(S, H); o += S * H
+        gbg = grad_w[o:o + S]; o += S
+        gWd = grad_w[o:o + S * H].view(S, H); o += S * H
+        gbd = grad_w[o:o + S]
+        return grad_y0, grad_c, gw1t, gWg, gbg, gWd, gbd, None, None, None, None
+
+
+def _solve_blackbox(func, y0, t, method, mode, layout):
+    z, hid, gro, deg = _check_blackbox(func)
+    B, S = y0.shape
+    if z.shape[0] != B:
+        raise ValueError(f"constants batch {z.shape[0]} != y0 batch {B}")
+    if gro.out_features != S:
+        raise ValueError(f"y0 state dim {S} != Dynamics n_outputs {gro.out_features}")
+    H = hid.out_features
+    if not _cabi.lib().slode_mlp_supported(H, S):
+        raise NotImplementedError(
+            f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled kernel; available (H,S): "
+            f"{_cabi.supported_shapes()}. There is no generic fallback.")
+    if z.device != y0.device or hid.weight.device != y0.device:
+        raise RuntimeError("func tensors and y0 must live on the same CUDA device")
+    W1 = hid.weight
+    if mode == _cabi.BWD_TDE_ADJOINT:
+        z = z.detach()  # odeint_adjoint: constants are not in adjoint_params
+    # time-invariant part of the hidden pre-activation: a plain (B,L)x(L,H) GEMM -> cuBLAS
+    c = torch.addmm(hid.bias, z.to(torch.float32), W1[:, 1:].t())
+    return _MlpFixedSolve.apply(y0, c, W1[:, 0], gro.weight, gro.bias, deg.weight, deg.bias, t,
+                                _cabi.METHODS[method], mode, layout)
+
+
+# ----------------------------------------------------------------------------------------------
+# public API
+# ----------------------------------------------------------------------------------------------
+def _solve(func, y0, t, rtol, atol, method, options, event_fn, mode, layout):
+    t, method = _check_common(y0, t, method, options, event_fn)
+    if layout not in ("tbs", "bts"):
+        raise ValueError("layout must be 'tbs' (torchdiffeq's) or 'bts'")
+    if is_blackbox_func(func):
+        if method == "dopri5":
+            raise NotImplementedError("dopri5 for the blackbox dynamics is not built yet")
+        return _solve_blackbox(func, y0, t, method, mode, layout)
+    raise NotImplementedError(
+        f"func of type {type(func).__name__} has no fused kernel; supported: OdeFunc over Dynamics "
+        "(models/blackbox_ode.py). There is no generic fallback solver.")
+
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, layout="tbs"):
+    """Drop-in for ``torchdiffeq.odeint`` on the reference's hot path; returns ``(len(t), B, S)``.
+
+    ``layout="bts"`` stores the result (B,T,S)-contiguous (still returned as a (T,B,S) view) so that the
+    ``sol.permute(1, 0, 2)`` in ``OdeModel.solve_ODE`` hands the decoder a contiguous tensor.
+    """
+    return _solve(func, y0, t, rtol, atol, method, options, event_fn, _cabi.BWD_DISCRETE, layout)
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
+                   adjoint_rtol=None, adjoint_atol=None, adjoint_method=None, adjoint_options=None,
+                   adjoint_params=None, layout="tbs"):
+    """Drop-in for ``torchdiffeq.odeint_adjoint`` as the reference calls it (same-method adjoint)."""
+    if not isinstance(func, nn.Module):
+        raise ValueError("func must be an instance of nn.Module to specify the adjoint parameters")
+    if adjoint_method not in (None, method) or adjoint_options is not None \
+            or adjoint_rtol not in (None, rtol) or adjoint_atol not in (None, atol):
+        raise NotImplementedError("separate adjoint solver settings are never set by the reference")
+    if adjoint_params is not None:
+        want = {id(p) for p in func.parameters()}
+        if {id(p) for p in adjoint_params} != want:
+            raise NotImplementedError("adjoint_params other than tuple(func.parameters())")
+    return _solve(func, y0, t, rtol, atol, method, options, event_fn, _cabi.BWD_TDE_ADJOINT, layout)
+
+
+def install_as_torchdiffeq():
+    """Register this module as ``sys.modules['torchdiffeq']`` so that the reference's
+    ``import torchdiffeq`` (``models/blackbox_ode.py:3``) resolves to the B200 path unchanged."""
+    import sys
+    sys.modules["torchdiffeq"] = sys.modules[__name__]
