@@ -6,57 +6,252 @@
 //     D_k(t)  = sigmoid(bd_k + sum_j Wd_kj h_j(t))          "degradation"
 //     f(t,x)  = A(t) - D(t) * x                              (linear in the state, elementwise)
 //
-// Mapping: one thread = one trajectory for the whole time loop.  State, Butcher stages and the
-// time-invariant hidden pre-activations c[H] live in registers; the weights are warp-uniform and
-// are read as constant-bank operands of the FFMAs (c_pack, filled per call by pack_kernel), so an
-// RHS evaluation is H FFMA + H FMNMX + 2*S*H FFMA + 2S (EX2, RCP) with no load instructions.
+// Mapping: one thread = one trajectory for the whole time loop; state, Butcher stages and the
+// time-invariant hidden pre-activations c[H] stay in registers.
+//
+// FP32 pipe (measured on B200, profiles/r01/fp32_pipes_microbench.jsonl): a 3-register FFMA
+// sustains 84 FMA/clk/SM, FFMA with a uniform-register operand 118, and the packed FFMA2
+// (fma.rn.f32x2) with a uniform-register operand 127 = the full 128-lane peak, even with one
+// LDCU.128 per four FFMA2.  sm_100a has no constant-bank operand form: warp-uniform weights reach
+// the FMA pipe through uniform registers (LDCU).  The kernels are therefore built on FFMA2 with
+//     pair of OUTPUTS (o, o+1)  +=  (W[j][o], W[j][o+1]) (uniform pair)  *  h_j (broadcast .F32)
+// so one trajectory per thread still fills both halves of every FMA.  Head outputs are ordered so
+// that pairs line up with pairs of state components:
+//     o = 4q+{0,1}: growth of states 2q,2q+1   o = 4q+{2,3}: degradation of states 2q,2q+1
+//     S odd: the last pair is (growth_{S-1}, degradation_{S-1})
+// and all per-state arithmetic (stages, adjoints) runs on the same pair layout (Vec<S>).
 // rk4 (3/8 rule) re-uses the evaluation at t1 as the next step's evaluation at t0 (same float).
 //
 // Backward: reverse sweep over the stored grid states sol[i]; stages are recomputed.  Because the
-// hidden layer sees only (t, z), the cotangents of the head pre-activations delta_k(e) at the
+// hidden layer sees only (t, z), the cotangents of the head pre-activations delta_o(e) at the
 // evaluation times t_e determine every hidden-layer gradient through prefix sums
-//     P_k = sum_e delta_k(e),   Q_k = sum_e delta_k(e) t_e
+//     P_o = sum_e delta_o(e),   Q_o = sum_e delta_o(e) t_e
 // taken over the evaluations where unit j is active.  The sweep keeps running P,Q (2*2S registers)
 // and, whenever a unit's relu gate flips between consecutive evaluations (at most once per unit
 // for monotone t, but the summation-by-parts below is valid for any number of flips), adds
 // +-snapshot contributions:
-//     dc_j   += s * sum_k W_kj P_k              (per trajectory -> grad_c)
-//     dw1t_j += s * sum_k W_kj Q_k              (block accumulator)
-//     dW_kj  += s * (w1t_j Q_k + c_j P_k)       (block accumulator, = sum_e delta_k h_j)
+//     dc_j   += s * sum_o W_oj P_o              (per trajectory -> grad_c)
+//     dw1t_j += s * sum_o W_oj Q_o              (block accumulator)
+//     dW_oj  += s * (w1t_j Q_o + c_j P_o)       (block accumulator, = sum_e delta_o h_j)
 // with s=+1 when the unit turns off, -1 when it turns on, and +1 for every unit still active when
 // the sweep ends.  This replaces the two dense 2S*H products per evaluation of a textbook backward.
 #include <algorithm>
+#include <type_traits>
 
 #include "slode_common.cuh"
 
 namespace slode {
 
-constexpr int kPackMax = 8192;
-__constant__ float c_pack[kPackMax];
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f2;
 
-template <int H, int S>
-struct Pack {  // layout of c_pack for one (H,S)
-  static constexpr int W1T = 0;
-  static constexpr int WG = H;
-  static constexpr int BG = WG + S * H;
-  static constexpr int WD = BG + S;
-  static constexpr int BD = WD + S * H;
-  static constexpr int N = BD + S;
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 bc(float v) { return pk(v, v); }
+__device__ __forceinline__ void unpk(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float lo_of(f2 v) { float a, b; unpk(v, a, b); return a; }
+__device__ __forceinline__ float hi_of(f2 v) { float a, b; unpk(v, a, b); return b; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// S per-state values stored as S/2 pairs (+ one scalar when S is odd)
+template <int S>
+struct Vec {
+  static constexpr int NP = S / 2;
+  static constexpr bool TAIL = (S & 1) != 0;
+  f2 p[NP > 0 ? NP : 1];
+  float t;
 };
 
-// Packs the caller's weights into the staging buffer: head weights/biases pre-scaled by -log2(e) so
-// that sigmoid(u) = rcp(1 + ex2(v)).
+#define VEC_FOR_PAIRS for (int q = 0; q < Vec<S>::NP; ++q)
+
+template <int S> __device__ __forceinline__ Vec<S> vbc(float s) {
+  Vec<S> r;
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = bc(s);
+  r.t = s;
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vadd(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = add2(a.p[q], b.p[q]);
+  r.t = Vec<S>::TAIL ? a.t + b.t : 0.0f;
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vsub(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = sub2(a.p[q], b.p[q]);
+  r.t = Vec<S>::TAIL ? a.t - b.t : 0.0f;
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vmul(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = mul2(a.p[q], b.p[q]);
+  r.t = Vec<S>::TAIL ? a.t * b.t : 0.0f;
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vscale(const Vec<S>& a, float s) {
+  Vec<S> r;
+  const f2 ss = bc(s);
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = mul2(a.p[q], ss);
+  r.t = Vec<S>::TAIL ? a.t * s : 0.0f;
+  return r;
+}
+// s*a + c  (scalar s)
+template <int S> __device__ __forceinline__ Vec<S> vaxpy(float s, const Vec<S>& a, const Vec<S>& c) {
+  Vec<S> r;
+  const f2 ss = bc(s);
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = fma2(ss, a.p[q], c.p[q]);
+  r.t = Vec<S>::TAIL ? fmaf(s, a.t, c.t) : 0.0f;
+  return r;
+}
+// c - a*b
+template <int S> __device__ __forceinline__ Vec<S> vnfma(const Vec<S>& a, const Vec<S>& b, const Vec<S>& c) {
+  Vec<S> r;
+  const f2 m1 = bc(-1.0f);
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = fma2(mul2(a.p[q], m1), b.p[q], c.p[q]);
+  r.t = Vec<S>::TAIL ? fmaf(-a.t, b.t, c.t) : 0.0f;
+  return r;
+}
+// -(a*b)
+template <int S> __device__ __forceinline__ Vec<S> vnmul(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+  const f2 m1 = bc(-1.0f);
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = mul2(mul2(a.p[q], m1), b.p[q]);
+  r.t = Vec<S>::TAIL ? -a.t * b.t : 0.0f;
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vload(const float* p) {
+  Vec<S> r;
+  float v[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) v[s] = ld_stream(p + s);
+#pragma unroll
+  VEC_FOR_PAIRS r.p[q] = pk(v[2 * q], v[2 * q + 1]);
+  r.t = Vec<S>::TAIL ? v[S - 1] : 0.0f;
+  return r;
+}
+template <int S> __device__ __forceinline__ void vstore(float* p, const Vec<S>& a) {
+#pragma unroll
+  VEC_FOR_PAIRS {
+    float lo, hi;
+    unpk(a.p[q], lo, hi);
+    p[2 * q] = lo;
+    p[2 * q + 1] = hi;
+  }
+  if (Vec<S>::TAIL) p[S - 1] = a.t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed weights in constant memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kPackMax = 8192;
+}  // namespace slode
+// C linkage: the loads below name the symbol from inline PTX.
+extern "C" {
+__constant__ __align__(16) float slode_c_pack[slode::kPackMax];
+}
+namespace slode {
+
+// Weight loads.  Left alone, both NVVM and ptxas hoist the (loop-invariant) constant loads out of
+// the time loop into ~300 registers and spill them.  Every evaluation therefore reads through an
+// offset `wb` that is advanced by a kernel ARGUMENT which is always 0: uniform and loop-carried,
+// but not provably invariant, so the loads stay inside the evaluation as uniform-register loads
+// LDCU c[3][UR + imm] feeding the UR operand of FFMA2.
+typedef int wbase_t;
+// offset for evaluation number k of time-loop iteration i
+__device__ __forceinline__ wbase_t weight_base(int i, int k, unsigned wzero) { return (4 * i + k) * (int)wzero; }
+template <int OFF_FLOATS>
+__device__ __forceinline__ void ldc_pair2(wbase_t wb, f2& a, f2& b) {
+  static_assert(OFF_FLOATS % 4 == 0, "16-byte aligned");
+  const float4 v = *reinterpret_cast<const float4*>(&slode_c_pack[wb * 4 + OFF_FLOATS]);
+  a = pk(v.x, v.y);
+  b = pk(v.z, v.w);
+}
+template <int OFF_FLOATS>
+__device__ __forceinline__ void ldc_pair1(wbase_t wb, f2& a) {
+  static_assert(OFF_FLOATS % 2 == 0, "8-byte aligned");
+  const float2 v = *reinterpret_cast<const float2*>(&slode_c_pack[wb * 4 + OFF_FLOATS]);
+  a = pk(v.x, v.y);
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// head-output order used everywhere on the device (see file comment)
+__host__ __device__ constexpr int out_is_degr(int o, int S) {
+  return (o >= 4 * (S / 2)) ? (o & 1) : ((o >> 1) & 1);
+}
+__host__ __device__ constexpr int out_state(int o, int S) {
+  return (o >= 4 * (S / 2)) ? (S - 1) : (2 * (o >> 2) + (o & 1));
+}
+
+template <int H, int S>
+struct Pack {
+  static constexpr int K2 = 2 * S;
+  static constexpr int HP = (H + 3) / 4 * 4;   // every region starts 16-byte aligned
+  static constexpr int KP = (K2 + 3) / 4 * 4;
+  static constexpr int W1T = 0;                // [j]     time column of the hidden layer
+  static constexpr int BH = HP;                // [o]     head biases, pre-scaled by -log2(e)
+  static constexpr int WH = HP + KP;           // [j][o]  head weights, pre-scaled by -log2(e)
+  static constexpr int N = WH + H * K2;
+};
+
 __global__ void pack_kernel(int H, int S, const float* __restrict__ w1t, const float* __restrict__ Wg,
                             const float* __restrict__ bg, const float* __restrict__ Wd,
                             const float* __restrict__ bd, float* __restrict__ out) {
-  const int WG = H, BG = WG + S * H, WD = BG + S, BD = WD + S * H, N = BD + S;
+  const int K2 = 2 * S, HP = (H + 3) / 4 * 4, KP = (K2 + 3) / 4 * 4, BH = HP, WH = HP + KP, N = WH + H * K2;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    float v;
-    if (i < WG) v = w1t[i];
-    else if (i < BG) v = kNegLog2e * Wg[i - WG];
-    else if (i < WD) v = kNegLog2e * bg[i - BG];
-    else if (i < BD) v = kNegLog2e * Wd[i - WD];
-    else v = kNegLog2e * bd[i - BD];
+    float v = 0.0f;
+    if (i < HP) {
+      if (i < H) v = w1t[i];
+    } else if (i < WH) {
+      const int o = i - BH;
+      if (o < K2) {
+        const int s = out_state(o, S);
+        v = kNegLog2e * (out_is_degr(o, S) ? bd[s] : bg[s]);
+      }
+    } else {
+      const int j = (i - WH) / K2, o = (i - WH) % K2, s = out_state(o, S);
+      v = kNegLog2e * (out_is_degr(o, S) ? Wd[s * H + j] : Wg[s * H + j]);
+    }
     out[i] = v;
   }
 }
@@ -66,23 +261,57 @@ struct MaskWords {
   static constexpr int NW = (H + 31) / 32;
 };
 
-// One RHS evaluation: A[S], D[S] at time t (and, if MASK, the relu gate bits).
-// Gate word w covers units [32w, 32w+n_w); unit j sits at bit (n_w - 1 - (j - 32w)).
+// Result of one RHS evaluation in pair layout: sig[2q] = (A_2q, A_2q+1), sig[2q+1] = (D_2q, D_2q+1),
+// S odd: sig[S-1] = (A_{S-1}, D_{S-1}).
+template <int S>
+struct Sig {
+  f2 v[S];
+  __device__ __forceinline__ Vec<S> A() const {
+    Vec<S> r;
+#pragma unroll
+    VEC_FOR_PAIRS r.p[q] = v[2 * q];
+    r.t = Vec<S>::TAIL ? lo_of(v[S - 1]) : 0.0f;
+    return r;
+  }
+  __device__ __forceinline__ Vec<S> D() const {
+    Vec<S> r;
+#pragma unroll
+    VEC_FOR_PAIRS r.p[q] = v[2 * q + 1];
+    r.t = Vec<S>::TAIL ? hi_of(v[S - 1]) : 0.0f;
+    return r;
+  }
+};
+
+// One RHS evaluation at time t.  c2[jp] = (c_2jp, c_2jp+1).  Gate word w covers units
+// [32w, 32w+n_w); unit j sits at bit (n_w - 1 - (j - 32w)).
 template <int H, int S, bool MASK>
-__device__ __forceinline__ void mlp_eval(float t, const float (&c)[H], float (&A)[S], float (&D)[S],
+__device__ __forceinline__ void mlp_eval(wbase_t wb, float t, const f2 (&c2)[(H + 1) / 2], Sig<S>& out,
                                          uint32_t (&gate)[MaskWords<H>::NW]) {
   using P = Pack<H, S>;
   constexpr int NW = MaskWords<H>::NW;
-  float h[H];
+  constexpr int K2 = 2 * S;
+  float h[(H + 3) / 4 * 4];
   uint32_t neg[NW];
 #pragma unroll
   for (int w = 0; w < NW; ++w) neg[w] = 0u;
+  const f2 tt = bc(t);
+  // hidden layer: two unit pairs per 16-byte uniform load
+  static_for<0, (H + 3) / 4>([&](auto I) {
+    constexpr int qq = decltype(I)::value;
+    f2 w0, w1;
+    ldc_pair2<P::W1T + 4 * qq>(wb, w0, w1);
+    float p[4];
+    unpk(fma2(w0, tt, c2[2 * qq]), p[0], p[1]);
+    if constexpr (2 * qq + 1 < (H + 1) / 2) unpk(fma2(w1, tt, c2[2 * qq + 1]), p[2], p[3]);
 #pragma unroll
-  for (int j = 0; j < H; ++j) {
-    const float p = fmaf(c_pack[P::W1T + j], t, c[j]);
-    if (MASK) neg[j / 32] = __funnelshift_l(__float_as_uint(p), neg[j / 32], 1);
-    h[j] = fmaxf(p, 0.0f);
-  }
+    for (int r = 0; r < 4; ++r) {
+      const int j = 4 * qq + r;
+      if (j < H) {
+        if (MASK) neg[j / 32] = __funnelshift_l(__float_as_uint(p[r]), neg[j / 32], 1);
+        h[j] = fmaxf(p[r], 0.0f);
+      }
+    }
+  });
   if (MASK) {
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
@@ -91,103 +320,119 @@ __device__ __forceinline__ void mlp_eval(float t, const float (&c)[H], float (&A
       gate[w] = (~neg[w]) & low;
     }
   }
+  f2 acc[(S + 1) / 2 * 2];
+  static_for<0, (S + 1) / 2>([&](auto I) {
+    constexpr int q = decltype(I)::value;
+    ldc_pair2<P::BH + 4 * q>(wb, acc[2 * q], acc[2 * q + 1]);
+  });
+  // heads: flat pair index pi = j*S + op; two pairs per 16-byte uniform load
+  constexpr int NPAIR = H * S;
+  static_for<0, NPAIR / 2>([&](auto I) {
+    constexpr int q = decltype(I)::value;
+    constexpr int pa = 2 * q, pb = 2 * q + 1;
+    f2 wa, wb2;
+    ldc_pair2<P::WH + 4 * q>(wb, wa, wb2);
+    acc[pa % S] = fma2(bc(h[pa / S]), wa, acc[pa % S]);
+    acc[pb % S] = fma2(bc(h[pb / S]), wb2, acc[pb % S]);
+  });
+  if constexpr (NPAIR % 2 == 1) {
+    constexpr int pa = NPAIR - 1;
+    f2 wa;
+    ldc_pair1<P::WH + 2 * pa>(wb, wa);
+    acc[pa % S] = fma2(bc(h[pa / S]), wa, acc[pa % S]);
+  }
+  const f2 one = bc(1.0f);
 #pragma unroll
-  for (int k = 0; k < S; ++k) {
-    float ua = c_pack[P::BG + k];
-    float ud = c_pack[P::BD + k];
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-      ua = fmaf(c_pack[P::WG + k * H + j], h[j], ua);
-      ud = fmaf(c_pack[P::WD + k * H + j], h[j], ud);
-    }
-    A[k] = sigmoid_from_scaled(ua);
-    D[k] = sigmoid_from_scaled(ud);
+  for (int op = 0; op < S; ++op) {
+    float v0, v1;
+    unpk(acc[op], v0, v1);
+    const f2 e = add2(pk(ex2_approx(v0), ex2_approx(v1)), one);
+    unpk(e, v0, v1);
+    out.v[op] = pk(rcp_approx(v0), rcp_approx(v1));
   }
 }
 
 // Scheduling fence: the RHS evaluations of one step do not depend on each other (the MLP sees only
 // t), so ptxas would interleave all of them and blow the register budget.  Making the next
-// evaluation's time nominally depend on the previous evaluation's last outputs serialises them.
-__device__ __forceinline__ float after(float t, float dep0, float dep1) {
-  asm volatile("" : "+f"(t) : "f"(dep0), "f"(dep1));
+// evaluation's time nominally depend on the previous evaluation's outputs serialises them.
+template <int S>
+__device__ __forceinline__ float after(float t, const Sig<S>& dep) {
+  asm volatile("" : "+f"(t) : "l"(dep.v[S - 1]), "l"(dep.v[0]));
   return t;
 }
 
-// f = A - D*x with the reference's two roundings (xa - xd * state, blackbox_ode.py:108)
-__device__ __forceinline__ float rhs(float A, float D, float x) { return __fsub_rn(A, __fmul_rn(D, x)); }
+// f = A - D*x
+template <int S>
+__device__ __forceinline__ Vec<S> rhs(const Sig<S>& e, const Vec<S>& x) { return vnfma<S>(e.D(), x, e.A()); }
 
+#ifndef SLODE_FWD_MINB
+#define SLODE_FWD_MINB 4
+#endif
 constexpr int kBlock = 128;
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int H, int S, int METHOD>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, SLODE_FWD_MINB)
 mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
-                     const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb) {
+                     const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb,
+                     unsigned wzero) {
   uint32_t nogate[MaskWords<H>::NW];
-  for (int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x; b < B; b += (int64_t)gridDim.x * kBlock) {
-    float c[H], x[S];
+  // Uniform control flow: every thread of the block runs the same tile and time loops (tail
+  // threads redo trajectory B-1 with their stores predicated off), so the loop counters and the
+  // weight base stay in uniform registers.
+  const int64_t ntiles = (B + kBlock - 1) / kBlock;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t b_raw = tile * kBlock + threadIdx.x;
+    const bool valid = b_raw < B;
+    const int64_t b = valid ? b_raw : B - 1;
+    f2 c2[(H + 1) / 2];
 #pragma unroll
-    for (int j = 0; j < H; ++j) c[j] = ld_stream(cin + b * H + j);
-    float* out = sol + b * sb;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      x[s] = ld_stream(y0 + b * S + s);
-      out[s] = x[s];
+    for (int jp = 0; jp < (H + 1) / 2; ++jp) {
+      const float c0 = ld_stream(cin + b * H + 2 * jp);
+      const float c1 = (2 * jp + 1 < H) ? ld_stream(cin + b * H + 2 * jp + 1) : 0.0f;
+      c2[jp] = pk(c0, c1);
     }
+    float* out = sol + b * sb;
+    Vec<S> x = vload<S>(y0 + b * S);
+    if (valid) vstore<S>(out, x);
     float t0 = __ldg(tgrid);
-    float A0[S], D0[S];
-    if (METHOD == SLODE_METHOD_RK4) mlp_eval<H, S, false>(t0, c, A0, D0, nogate);
+    Sig<S> e0;  // rk4: evaluation at the current grid time, carried over from the previous step
+    if (METHOD == SLODE_METHOD_RK4) mlp_eval<H, S, false>(weight_base(T, 0, wzero), t0, c2, e0, nogate);
 
 #pragma unroll 1
     for (int i = 0; i + 1 < T; ++i) {
       const float t1 = __ldg(tgrid + i + 1);
-      const float dt = __fsub_rn(t1, t0);
-      float A[S], D[S];
+      const float dt = t1 - t0;
       if (METHOD == SLODE_METHOD_EULER) {
-        mlp_eval<H, S, false>(t0, c, A, D, nogate);
-#pragma unroll
-        for (int s = 0; s < S; ++s) x[s] = __fadd_rn(x[s], __fmul_rn(dt, rhs(A[s], D[s], x[s])));
+        Sig<S> e;
+        mlp_eval<H, S, false>(weight_base(i, 0, wzero), t0, c2, e, nogate);
+        x = vaxpy<S>(dt, rhs<S>(e, x), x);
       } else if (METHOD == SLODE_METHOD_MIDPOINT) {
-        const float half_dt = __fmul_rn(0.5f, dt);
-        float ym[S];
-        mlp_eval<H, S, false>(t0, c, A, D, nogate);
-#pragma unroll
-        for (int s = 0; s < S; ++s) ym[s] = __fadd_rn(x[s], __fmul_rn(rhs(A[s], D[s], x[s]), half_dt));
-        mlp_eval<H, S, false>(after(__fadd_rn(t0, half_dt), A[S - 1], D[S - 1]), c, A, D, nogate);
-#pragma unroll
-        for (int s = 0; s < S; ++s) x[s] = __fadd_rn(x[s], __fmul_rn(dt, rhs(A[s], D[s], ym[s])));
+        const float half_dt = 0.5f * dt;
+        Sig<S> e, em;
+        mlp_eval<H, S, false>(weight_base(i, 1, wzero), t0, c2, e, nogate);
+        const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(e, x), x);
+        mlp_eval<H, S, false>(weight_base(i, 2, wzero), after<S>(t0 + half_dt, e), c2, em, nogate);
+        x = vaxpy<S>(dt, rhs<S>(em, ym), x);
       } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func)
-        float k1[S], k2[S], k3[S], y[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          k1[s] = rhs(A0[s], D0[s], x[s]);
-          y[s] = __fadd_rn(x[s], __fmul_rn(__fmul_rn(dt, k1[s]), kOneThird));
-        }
-        mlp_eval<H, S, false>(after(__fadd_rn(t0, __fmul_rn(dt, kOneThird)), A0[S - 1], D0[S - 1]), c, A, D, nogate);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          k2[s] = rhs(A[s], D[s], y[s]);
-          y[s] = __fadd_rn(x[s], __fmul_rn(dt, __fsub_rn(k2[s], __fmul_rn(k1[s], kOneThird))));
-        }
-        mlp_eval<H, S, false>(after(__fadd_rn(t0, __fmul_rn(dt, kTwoThirds)), A[S - 1], D[S - 1]), c, A, D, nogate);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          k3[s] = rhs(A[s], D[s], y[s]);
-          y[s] = __fadd_rn(x[s], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[s], k2[s]), k3[s])));
-        }
-        mlp_eval<H, S, false>(after(t1, A[S - 1], D[S - 1]), c, A0, D0, nogate);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const float k4 = rhs(A0[s], D0[s], y[s]);
-          const float sum = __fadd_rn(__fadd_rn(k1[s], __fmul_rn(3.0f, __fadd_rn(k2[s], k3[s]))), k4);
-          x[s] = __fadd_rn(x[s], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
-        }
+        Sig<S> e;
+        const Vec<S> k1 = rhs<S>(e0, x);
+        Vec<S> y = vaxpy<S>(dt * kOneThird, k1, x);
+        mlp_eval<H, S, false>(weight_base(i, 3, wzero), after<S>(t0 + dt * kOneThird, e0), c2, e, nogate);
+        const Vec<S> k2 = rhs<S>(e, y);
+        y = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
+        mlp_eval<H, S, false>(weight_base(i, 0, wzero), after<S>(t0 + dt * kTwoThirds, e), c2, e, nogate);
+        const Vec<S> k3 = rhs<S>(e, y);
+        y = vaxpy<S>(dt, vadd<S>(vsub<S>(k1, k2), k3), x);
+        mlp_eval<H, S, false>(weight_base(i, 1, wzero), after<S>(t1, e), c2, e0, nogate);
+        const Vec<S> k4 = rhs<S>(e0, y);
+        const Vec<S> sum = vadd<S>(vaxpy<S>(3.0f, vadd<S>(k2, k3), k1), k4);
+        x = vaxpy<S>(dt * 0.125f, sum, x);
       }
       out += st;
-#pragma unroll
-      for (int s = 0; s < S; ++s) out[s] = x[s];
+      if (valid) vstore<S>(out, x);
       t0 = t1;
     }
   }
@@ -199,44 +444,46 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
 template <int H, int S>
 struct BwdSmem {
   static constexpr int K2 = 2 * S;
-  static constexpr int KP = (K2 + 3) / 4 * 4;  // head index padded for 16-byte rows
-  float c[H][kBlock];    // per-thread copy of c for dynamic unit index
-  float gc[H][kBlock];   // per-thread dL/dc accumulators
-  float W[H][KP];        // original head weights, [unit][growth 0..S-1 | degradation S..2S-1]
+  float c[H][kBlock];     // per-thread copy of c for dynamic unit index
+  float gc[H][kBlock];    // per-thread dL/dc accumulators
+  float2 W[H][S];         // original (unscaled) head weights, [unit][output pair] in device output order
   float w1t[H];
-  float G[K2][H];        // block accumulators: dWg rows then dWd rows
+  float G[K2][H];         // block accumulators, [output (device order)][unit]
   float gw1t[H];
   float gb[K2];
 };
 
 template <int H, int S>
 struct Sweep {
-  static constexpr int K2 = 2 * S;
   static constexpr int NW = MaskWords<H>::NW;
-  float P[K2], Q[K2];
+  f2 P[S], Q[S];  // pair layout == Sig layout
   uint32_t prev[NW];
 
   __device__ __forceinline__ void init(const uint32_t (&gate)[NW]) {
 #pragma unroll
-    for (int k = 0; k < K2; ++k) P[k] = Q[k] = 0.0f;
+    for (int k = 0; k < S; ++k) P[k] = Q[k] = 0ull;
 #pragma unroll
     for (int w = 0; w < NW; ++w) prev[w] = gate[w];
   }
 
   __device__ __forceinline__ void snapshot(BwdSmem<H, S>& sm, int j, float sign) {
     const int tid = threadIdx.x;
-    const float wj = sm.w1t[j];
-    const float cj = sm.c[j][tid];
-    float s1 = 0.0f, s2 = 0.0f;
+    const f2 wj = bc(sign * sm.w1t[j]);
+    const f2 cj = bc(sign * sm.c[j][tid]);
+    f2 s1 = 0ull, s2 = 0ull;
 #pragma unroll
-    for (int k = 0; k < K2; ++k) {
-      const float W = sm.W[j][k];
-      s1 = fmaf(W, P[k], s1);
-      s2 = fmaf(W, Q[k], s2);
-      atomicAdd(&sm.G[k][j], sign * fmaf(wj, Q[k], cj * P[k]));
+    for (int op = 0; op < S; ++op) {
+      const float2 w = sm.W[j][op];
+      const f2 W = pk(w.x, w.y);
+      s1 = fma2(W, P[op], s1);
+      s2 = fma2(W, Q[op], s2);
+      float g0, g1;
+      unpk(fma2(wj, Q[op], mul2(cj, P[op])), g0, g1);
+      atomicAdd(&sm.G[2 * op][j], g0);
+      atomicAdd(&sm.G[2 * op + 1][j], g1);
     }
-    sm.gc[j][tid] += sign * s1;
-    atomicAdd(&sm.gw1t[j], sign * s2);
+    sm.gc[j][tid] += sign * (lo_of(s1) + hi_of(s1));
+    atomicAdd(&sm.gw1t[j], sign * (lo_of(s2) + hi_of(s2)));
   }
 
   // gate flips between the previous contributing evaluation and this one
@@ -255,14 +502,25 @@ struct Sweep {
     }
   }
 
-  // add the cotangents of the head pre-activations of one evaluation at time te
-  __device__ __forceinline__ void add(float te, const float (&dg)[S], const float (&dd)[S]) {
+  // add the cotangents of the head pre-activations of one evaluation at time te:
+  //   f = A - D*y with upstream gf:  d(pre_A) = gf*A(1-A),  d(pre_D) = -gf*y*D(1-D)
+  __device__ __forceinline__ void add(float te, const Vec<S>& gf, const Vec<S>& y, const Sig<S>& e) {
+    const Vec<S> one = vbc<S>(1.0f);
+    const Vec<S> A = e.A(), D = e.D();
+    const Vec<S> dg = vmul<S>(gf, vmul<S>(A, vsub<S>(one, A)));
+    const Vec<S> dd = vmul<S>(vmul<S>(gf, y), vmul<S>(D, vsub<S>(D, one)));
+    const f2 tt = bc(te);
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      P[s] += dg[s];
-      Q[s] = fmaf(dg[s], te, Q[s]);
-      P[S + s] += dd[s];
-      Q[S + s] = fmaf(dd[s], te, Q[S + s]);
+    VEC_FOR_PAIRS {
+      P[2 * q] = add2(P[2 * q], dg.p[q]);
+      Q[2 * q] = fma2(dg.p[q], tt, Q[2 * q]);
+      P[2 * q + 1] = add2(P[2 * q + 1], dd.p[q]);
+      Q[2 * q + 1] = fma2(dd.p[q], tt, Q[2 * q + 1]);
+    }
+    if (Vec<S>::TAIL) {
+      const f2 d = pk(dg.t, dd.t);
+      P[S - 1] = add2(P[S - 1], d);
+      Q[S - 1] = fma2(d, tt, Q[S - 1]);
     }
   }
 
@@ -278,20 +536,21 @@ struct Sweep {
       }
     }
 #pragma unroll
-    for (int k = 0; k < K2; ++k) atomicAdd(&sm.gb[k], P[k]);
+    for (int op = 0; op < S; ++op) {
+      float p0, p1;
+      unpk(P[op], p0, p1);
+      atomicAdd(&sm.gb[2 * op], p0);
+      atomicAdd(&sm.gb[2 * op + 1], p1);
+    }
   }
 };
 
-// cotangents wrt the pre-sigmoid head outputs for one stage:
-//   f = A - D*y, upstream gf  ->  dA = gf, dD = -gf*y;  d(pre) = d(.) * s(1-s)
-template <int S>
-__device__ __forceinline__ void stage_deltas(const float (&gf)[S], const float (&y)[S], const float (&A)[S],
-                                             const float (&D)[S], float (&dg)[S], float (&dd)[S]) {
+template <int H, int S>
+__device__ __forceinline__ void load_c2(const BwdSmem<H, S>& sm, f2 (&c2)[(H + 1) / 2]) {
+  const int tid = threadIdx.x;
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    dg[s] = gf[s] * A[s] * (1.0f - A[s]);
-    dd[s] = -gf[s] * y[s] * D[s] * (1.0f - D[s]);
-  }
+  for (int jp = 0; jp < (H + 1) / 2; ++jp)
+    c2[jp] = pk(sm.c[2 * jp][tid], (2 * jp + 1 < H) ? sm.c[2 * jp + 1][tid] : 0.0f);
 }
 
 template <int H, int S, int METHOD, int MODE>
@@ -300,19 +559,17 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
                      const float* __restrict__ w1t, const float* __restrict__ Wg, const float* __restrict__ Wd,
                      const float* __restrict__ sol, int64_t st, int64_t sb,
                      const float* __restrict__ gsol, int64_t gst, int64_t gsb,
-                     float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w) {
+                     float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,
+                     unsigned wzero) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem<H, S>& sm = *reinterpret_cast<BwdSmem<H, S>*>(smem_raw);
   constexpr int K2 = 2 * S;
   constexpr int NW = MaskWords<H>::NW;
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < H * BwdSmem<H, S>::KP; i += kBlock) {
-    const int j = i / BwdSmem<H, S>::KP, k = i % BwdSmem<H, S>::KP;
-    float v = 0.0f;
-    if (k < S) v = Wg[k * H + j];
-    else if (k < K2) v = Wd[(k - S) * H + j];
-    sm.W[j][k] = v;
+  for (int i = tid; i < H * K2; i += kBlock) {
+    const int j = i / K2, o = i % K2, s = out_state(o, S);
+    (&sm.W[0][0].x)[i] = out_is_degr(o, S) ? Wd[s * H + j] : Wg[s * H + j];
   }
   for (int i = tid; i < H; i += kBlock) {
     sm.w1t[i] = w1t[i];
@@ -324,260 +581,195 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
 
   const int64_t ntiles = (B + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t b = tile * kBlock + tid;
-    if (b < B) {
-      float c[H];
+    const int64_t b_raw = tile * kBlock + tid;
+    const bool valid = b_raw < B;  // tail threads redo trajectory B-1 with zero cotangents
+    const int64_t b = valid ? b_raw : B - 1;
+    {
 #pragma unroll
       for (int j = 0; j < H; ++j) {
-        c[j] = ld_stream(cin + b * H + j);
-        sm.c[j][tid] = c[j];
+        sm.c[j][tid] = ld_stream(cin + b * H + j);
         sm.gc[j][tid] = 0.0f;
       }
+      f2 c2[(H + 1) / 2];
+      load_c2<H, S>(sm, c2);
       const float* xs = sol + b * sb;
       const float* gs = gsol + b * gsb;
-      float lam[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) lam[s] = ld_stream(gs + (int64_t)(T - 1) * gst + s);
+      const float live = valid ? 1.0f : 0.0f;
+      Vec<S> lam = vscale<S>(vload<S>(gs + (int64_t)(T - 1) * gst), live);
 
       Sweep<H, S> sw;
       float t1 = __ldg(tgrid + T - 1);
-      float Ac[S], Dc[S];  // evaluation carried across intervals (rk4: at the shared grid time)
-      uint32_t gc_[NW], g1[NW], g2[NW], g3[NW];
+      Sig<S> ec;  // evaluation carried across intervals (rk4: at the shared grid time)
+      uint32_t g0[NW], g1[NW], g2[NW], g3[NW];
       bool started = false;
       if (METHOD == SLODE_METHOD_RK4) {
-        mlp_eval<H, S, true>(t1, c, Ac, Dc, gc_);
-        sw.init(gc_);
+        mlp_eval<H, S, true>(weight_base(T, 0, wzero), t1, c2, ec, g0);
+        sw.init(g0);
         started = true;
       }
 
 #pragma unroll 1
       for (int i = T - 2; i >= 0; --i) {
         const float t0 = __ldg(tgrid + i);
-        float x[S], gnext[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          x[s] = ld_stream(xs + (int64_t)i * st + s);
-          gnext[s] = ld_stream(gs + (int64_t)i * gst + s);
-        }
-        float dg[S], dd[S];
+        const Vec<S> x = vload<S>(xs + (int64_t)i * st);
+        const Vec<S> gnext = vscale<S>(vload<S>(gs + (int64_t)i * gst), live);
 
         if (MODE == SLODE_BWD_DISCRETE) {
-          const float dt = __fsub_rn(t1, t0);
+          const float dt = t1 - t0;
           if (METHOD == SLODE_METHOD_EULER) {
-            float A[S], D[S], gk[S];
-            mlp_eval<H, S, true>(t0, c, A, D, g1);
-#pragma unroll
-            for (int s = 0; s < S; ++s) gk[s] = dt * lam[s];
-            stage_deltas<S>(gk, x, A, D, dg, dd);
+            Sig<S> e;
+            mlp_eval<H, S, true>(weight_base(i, 2, wzero), t0, c2, e, g1);
+            const Vec<S> gk = vscale<S>(lam, dt);
             if (!started) { sw.init(g1); started = true; } else sw.events(sm, g1);
-            sw.add(t0, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) lam[s] = fmaf(-gk[s], D[s], lam[s]) + gnext[s];
+            sw.add(t0, gk, x, e);
+            lam = vadd<S>(vnfma<S>(gk, e.D(), lam), gnext);
           } else if (METHOD == SLODE_METHOD_MIDPOINT) {
-            const float half_dt = __fmul_rn(0.5f, dt);
-            const float tm = __fadd_rn(t0, half_dt);
-            float A1[S], D1[S], A2[S], D2[S], ym[S], gk[S];
-            mlp_eval<H, S, true>(t0, c, A1, D1, g1);
-            mlp_eval<H, S, true>(after(tm, A1[S - 1], D1[S - 1]), c, A2, D2, g2);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              ym[s] = __fadd_rn(x[s], __fmul_rn(rhs(A1[s], D1[s], x[s]), half_dt));
-              gk[s] = dt * lam[s];  // dL/dk2
-            }
-            stage_deltas<S>(gk, ym, A2, D2, dg, dd);
+            const float half_dt = 0.5f * dt;
+            const float tm = t0 + half_dt;
+            Sig<S> e1, e2;
+            mlp_eval<H, S, true>(weight_base(i, 3, wzero), t0, c2, e1, g1);
+            mlp_eval<H, S, true>(weight_base(i, 0, wzero), after<S>(tm, e1), c2, e2, g2);
+            const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(e1, x), x);
+            Vec<S> gk = vscale<S>(lam, dt);  // dL/dk2
             if (!started) { sw.init(g2); started = true; } else sw.events(sm, g2);
-            sw.add(tm, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float gy = -gk[s] * D2[s];  // dL/dy_mid
-              lam[s] += gy;
-              gk[s] = half_dt * gy;  // dL/dk1
-            }
-            stage_deltas<S>(gk, x, A1, D1, dg, dd);
+            sw.add(tm, gk, ym, e2);
+            const Vec<S> gy = vnmul<S>(gk, e2.D());  // dL/dy_mid
+            lam = vadd<S>(lam, gy);
+            gk = vscale<S>(gy, half_dt);  // dL/dk1
             sw.events(sm, g1);
-            sw.add(t0, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) lam[s] = fmaf(-gk[s], D1[s], lam[s]) + gnext[s];
+            sw.add(t0, gk, x, e1);
+            lam = vadd<S>(vnfma<S>(gk, e1.D(), lam), gnext);
           } else {  // rk4 3/8
-            const float ta = __fadd_rn(t0, __fmul_rn(dt, kOneThird));
-            const float tb = __fadd_rn(t0, __fmul_rn(dt, kTwoThirds));
-            float A1[S], D1[S], A2[S], D2[S], A3[S], D3[S];
-            mlp_eval<H, S, true>(t0, c, A1, D1, g1);
-            mlp_eval<H, S, true>(after(ta, A1[S - 1], D1[S - 1]), c, A2, D2, g2);
-            mlp_eval<H, S, true>(after(tb, A2[S - 1], D2[S - 1]), c, A3, D3, g3);
-            float y2[S], y3[S], y4[S], gk1[S], gk2[S], gk3[S], gk4[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float k1 = rhs(A1[s], D1[s], x[s]);
-              y2[s] = __fadd_rn(x[s], __fmul_rn(__fmul_rn(dt, k1), kOneThird));
-              const float k2 = rhs(A2[s], D2[s], y2[s]);
-              y3[s] = __fadd_rn(x[s], __fmul_rn(dt, __fsub_rn(k2, __fmul_rn(k1, kOneThird))));
-              const float k3 = rhs(A3[s], D3[s], y3[s]);
-              y4[s] = __fadd_rn(x[s], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1, k2), k3)));
-              const float w = 0.125f * dt * lam[s];
-              gk1[s] = w;
-              gk2[s] = 3.0f * w;
-              gk3[s] = 3.0f * w;
-              gk4[s] = w;
-            }
+            const float ta = t0 + dt * kOneThird;
+            const float tb = t0 + dt * kTwoThirds;
             const float dt3 = dt * kOneThird;
-            // stage 4 (time t1, carried evaluation)
-            stage_deltas<S>(gk4, y4, Ac, Dc, dg, dd);
-            sw.add(t1, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float gy = -gk4[s] * Dc[s];
-              lam[s] += gy;
-              gk1[s] = fmaf(dt, gy, gk1[s]);
-              gk2[s] = fmaf(-dt, gy, gk2[s]);
-              gk3[s] = fmaf(dt, gy, gk3[s]);
-            }
+            Sig<S> e1, e2, e3;
+            mlp_eval<H, S, true>(weight_base(i, 1, wzero), t0, c2, e1, g1);
+            mlp_eval<H, S, true>(weight_base(i, 2, wzero), after<S>(ta, e1), c2, e2, g2);
+            mlp_eval<H, S, true>(weight_base(i, 3, wzero), after<S>(tb, e2), c2, e3, g3);
+            const Vec<S> k1 = rhs<S>(e1, x);
+            const Vec<S> y2 = vaxpy<S>(dt3, k1, x);
+            const Vec<S> k2 = rhs<S>(e2, y2);
+            const Vec<S> y3 = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
+            const Vec<S> k3 = rhs<S>(e3, y3);
+            const Vec<S> y4 = vaxpy<S>(dt, vadd<S>(vsub<S>(k1, k2), k3), x);
+            const Vec<S> w = vscale<S>(lam, 0.125f * dt);
+            Vec<S> gk1 = w, gk2 = vscale<S>(w, 3.0f), gk3 = gk2;
+            // stage 4 (time t1, carried evaluation): gk4 = w
+            sw.add(t1, w, y4, ec);
+            Vec<S> gy = vnmul<S>(w, ec.D());
+            lam = vadd<S>(lam, gy);
+            gk1 = vaxpy<S>(dt, gy, gk1);
+            gk2 = vaxpy<S>(-dt, gy, gk2);
+            gk3 = vaxpy<S>(dt, gy, gk3);
             // stage 3
-            stage_deltas<S>(gk3, y3, A3, D3, dg, dd);
             sw.events(sm, g3);
-            sw.add(tb, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float gy = -gk3[s] * D3[s];
-              lam[s] += gy;
-              gk2[s] = fmaf(dt, gy, gk2[s]);
-              gk1[s] = fmaf(-dt3, gy, gk1[s]);
-            }
+            sw.add(tb, gk3, y3, e3);
+            gy = vnmul<S>(gk3, e3.D());
+            lam = vadd<S>(lam, gy);
+            gk2 = vaxpy<S>(dt, gy, gk2);
+            gk1 = vaxpy<S>(-dt3, gy, gk1);
             // stage 2
-            stage_deltas<S>(gk2, y2, A2, D2, dg, dd);
             sw.events(sm, g2);
-            sw.add(ta, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float gy = -gk2[s] * D2[s];
-              lam[s] += gy;
-              gk1[s] = fmaf(dt3, gy, gk1[s]);
-            }
+            sw.add(ta, gk2, y2, e2);
+            gy = vnmul<S>(gk2, e2.D());
+            lam = vadd<S>(lam, gy);
+            gk1 = vaxpy<S>(dt3, gy, gk1);
             // stage 1 (time t0; becomes the carried evaluation of the next interval)
-            stage_deltas<S>(gk1, x, A1, D1, dg, dd);
             sw.events(sm, g1);
-            sw.add(t0, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              lam[s] = fmaf(-gk1[s], D1[s], lam[s]) + gnext[s];
-              Ac[s] = A1[s];
-              Dc[s] = D1[s];
-            }
+            sw.add(t0, gk1, x, e1);
+            lam = vadd<S>(vnfma<S>(gk1, e1.D(), lam), gnext);
+            ec = e1;
           }
         } else {
           // torchdiffeq.odeint_adjoint emulation: one step of the same method on the augmented
           // system [y, a, a_theta] from t1 down to t0, y restarted from the stored sol[i+1].
           // In reversed time s=-t the step is ds = t1 - t0 > 0 with
           //   Ky = D*y - A,  Ka = -a*D,  a_theta += w_m * a_m^T df/dtheta(t_m, y_m).
-          const float ds = __fsub_rn(t1, t0);
-          float y[S];
-#pragma unroll
-          for (int s = 0; s < S; ++s) y[s] = ld_stream(xs + (int64_t)(i + 1) * st + s);
+          const float ds = t1 - t0;
+          const Vec<S> y = vload<S>(xs + (int64_t)(i + 1) * st);
+          const Vec<S> zero = vbc<S>(0.0f);
           if (METHOD == SLODE_METHOD_EULER) {
-            float A[S], D[S], v[S];
-            mlp_eval<H, S, true>(t1, c, A, D, g1);
-#pragma unroll
-            for (int s = 0; s < S; ++s) v[s] = ds * lam[s];
-            stage_deltas<S>(v, y, A, D, dg, dd);
+            Sig<S> e;
+            mlp_eval<H, S, true>(weight_base(i, 0, wzero), t1, c2, e, g1);
+            const Vec<S> v = vscale<S>(lam, ds);
             if (!started) { sw.init(g1); started = true; } else sw.events(sm, g1);
-            sw.add(t1, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) lam[s] = fmaf(-ds * lam[s], D[s], lam[s]) + gnext[s];
+            sw.add(t1, v, y, e);
+            lam = vadd<S>(vnfma<S>(v, e.D(), lam), gnext);
           } else if (METHOD == SLODE_METHOD_MIDPOINT) {
-            const float half = __fmul_rn(0.5f, ds);
-            const float tm = __fsub_rn(t1, half);
-            float A1[S], D1[S], A2[S], D2[S], ym[S], am[S], v[S];
-            mlp_eval<H, S, false>(t1, c, A1, D1, g1);
-            mlp_eval<H, S, true>(after(tm, A1[S - 1], D1[S - 1]), c, A2, D2, g2);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              ym[s] = fmaf(fmaf(D1[s], y[s], -A1[s]), half, y[s]);
-              am[s] = fmaf(-lam[s] * D1[s], half, lam[s]);
-              v[s] = ds * am[s];
-            }
-            stage_deltas<S>(v, ym, A2, D2, dg, dd);
+            const float half = 0.5f * ds;
+            const float tm = t1 - half;
+            Sig<S> e1, e2;
+            mlp_eval<H, S, false>(weight_base(i, 1, wzero), t1, c2, e1, g1);
+            mlp_eval<H, S, true>(weight_base(i, 2, wzero), after<S>(tm, e1), c2, e2, g2);
+            const Vec<S> ky1 = vsub<S>(zero, rhs<S>(e1, y));  // D1*y - A1
+            const Vec<S> ka1 = vnmul<S>(lam, e1.D());         // -a*D1
+            const Vec<S> ym = vaxpy<S>(half, ky1, y);
+            const Vec<S> am = vaxpy<S>(half, ka1, lam);
+            const Vec<S> v = vscale<S>(am, ds);
             if (!started) { sw.init(g2); started = true; } else sw.events(sm, g2);
-            sw.add(tm, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) lam[s] = fmaf(-v[s], D2[s], lam[s]) + gnext[s];
+            sw.add(tm, v, ym, e2);
+            lam = vadd<S>(vnfma<S>(v, e2.D(), lam), gnext);
           } else {  // rk4 3/8 on the augmented system
-            const float ta = __fsub_rn(t1, __fmul_rn(ds, kOneThird));
-            const float tb = __fsub_rn(t1, __fmul_rn(ds, kTwoThirds));
+            const float ta = t1 - ds * kOneThird;
+            const float tb = t1 - ds * kTwoThirds;
             const float w8 = 0.125f * ds;
-            float A[S], D[S], v[S], ym[S], am[S];
-            float ky1[S], ka1[S], ky2[S], ka2[S], ky3[S], ka3[S], asum[S];
+            Sig<S> e;
             // stage 1 at t1 (carried evaluation)
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              ky1[s] = fmaf(Dc[s], y[s], -Ac[s]);
-              ka1[s] = -lam[s] * Dc[s];
-              v[s] = w8 * lam[s];
-            }
-            stage_deltas<S>(v, y, Ac, Dc, dg, dd);
-            sw.add(t1, dg, dd);
+            const Vec<S> ky1 = vsub<S>(zero, rhs<S>(ec, y));
+            const Vec<S> ka1 = vnmul<S>(lam, ec.D());
+            sw.add(t1, vscale<S>(lam, w8), y, ec);
             // stage 2
-            mlp_eval<H, S, true>(ta, c, A, D, g1);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              ym[s] = fmaf(ds * ky1[s], kOneThird, y[s]);
-              am[s] = fmaf(ds * ka1[s], kOneThird, lam[s]);
-              ky2[s] = fmaf(D[s], ym[s], -A[s]);
-              ka2[s] = -am[s] * D[s];
-              v[s] = 3.0f * w8 * am[s];
-            }
-            stage_deltas<S>(v, ym, A, D, dg, dd);
+            mlp_eval<H, S, true>(weight_base(i, 3, wzero), after<S>(ta, ec), c2, e, g1);
+            Vec<S> ym = vaxpy<S>(ds * kOneThird, ky1, y);
+            Vec<S> am = vaxpy<S>(ds * kOneThird, ka1, lam);
+            const Vec<S> ky2 = vsub<S>(zero, rhs<S>(e, ym));
+            const Vec<S> ka2 = vnmul<S>(am, e.D());
             sw.events(sm, g1);
-            sw.add(ta, dg, dd);
+            sw.add(ta, vscale<S>(am, 3.0f * w8), ym, e);
             // stage 3
-            mlp_eval<H, S, true>(after(tb, A[S - 1], D[S - 1]), c, A, D, g1);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              ym[s] = fmaf(ds, ky2[s] - ky1[s] * kOneThird, y[s]);
-              am[s] = fmaf(ds, ka2[s] - ka1[s] * kOneThird, lam[s]);
-              ky3[s] = fmaf(D[s], ym[s], -A[s]);
-              ka3[s] = -am[s] * D[s];
-              v[s] = 3.0f * w8 * am[s];
-            }
-            stage_deltas<S>(v, ym, A, D, dg, dd);
+            mlp_eval<H, S, true>(weight_base(i, 0, wzero), after<S>(tb, e), c2, e, g1);
+            ym = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ky1, ky2), y);
+            am = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ka1, ka2), lam);
+            const Vec<S> ky3 = vsub<S>(zero, rhs<S>(e, ym));
+            const Vec<S> ka3 = vnmul<S>(am, e.D());
             sw.events(sm, g1);
-            sw.add(tb, dg, dd);
+            sw.add(tb, vscale<S>(am, 3.0f * w8), ym, e);
             // stage 4 at t0 (becomes the carried evaluation)
-            mlp_eval<H, S, true>(after(t0, A[S - 1], D[S - 1]), c, Ac, Dc, g1);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              ym[s] = fmaf(ds, (ky1[s] - ky2[s]) + ky3[s], y[s]);
-              am[s] = fmaf(ds, (ka1[s] - ka2[s]) + ka3[s], lam[s]);
-              asum[s] = (ka1[s] + 3.0f * (ka2[s] + ka3[s])) - am[s] * Dc[s];
-              v[s] = w8 * am[s];
-            }
-            stage_deltas<S>(v, ym, Ac, Dc, dg, dd);
+            mlp_eval<H, S, true>(weight_base(i, 1, wzero), after<S>(t0, e), c2, ec, g1);
+            ym = vaxpy<S>(ds, vadd<S>(vsub<S>(ky1, ky2), ky3), y);
+            am = vaxpy<S>(ds, vadd<S>(vsub<S>(ka1, ka2), ka3), lam);
+            const Vec<S> ka4 = vnmul<S>(am, ec.D());
             sw.events(sm, g1);
-            sw.add(t0, dg, dd);
-#pragma unroll
-            for (int s = 0; s < S; ++s) lam[s] = fmaf(asum[s] * ds, 0.125f, lam[s]) + gnext[s];
+            sw.add(t0, vscale<S>(am, w8), ym, ec);
+            const Vec<S> asum = vadd<S>(vaxpy<S>(3.0f, vadd<S>(ka2, ka3), ka1), ka4);
+            lam = vadd<S>(vaxpy<S>(w8, asum, lam), gnext);
           }
         }
         t1 = t0;
       }
 
       if (started) sw.finish(sm);
+      if (valid) {
+        vstore<S>(grad_y0 + b * S, lam);
 #pragma unroll
-      for (int s = 0; s < S; ++s) grad_y0[b * S + s] = lam[s];
-#pragma unroll
-      for (int j = 0; j < H; ++j) grad_c[b * H + j] = sm.gc[j][tid];
+        for (int j = 0; j < H; ++j) grad_c[b * H + j] = sm.gc[j][tid];
+      }
     }
   }
 
   __syncthreads();
-  using P = Pack<H, S>;
-  for (int i = tid; i < H; i += kBlock) atomicAdd(grad_w + P::W1T + i, sm.gw1t[i]);
-  for (int i = tid; i < S * H; i += kBlock) {
-    atomicAdd(grad_w + P::WG + i, (&sm.G[0][0])[i]);
-    atomicAdd(grad_w + P::WD + i, (&sm.G[S][0])[i]);
+  // flush block accumulators: grad_w = [ dw1t (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) ]
+  for (int i = tid; i < H; i += kBlock) atomicAdd(grad_w + i, sm.gw1t[i]);
+  for (int i = tid; i < K2 * H; i += kBlock) {
+    const int o = i / H, j = i % H, s = out_state(o, S);
+    const int base = out_is_degr(o, S) ? (H + S * H + S) : H;
+    atomicAdd(grad_w + base + s * H + j, sm.G[o][j]);
   }
-  if (tid < S) {
-    atomicAdd(grad_w + P::BG + tid, sm.gb[tid]);
-    atomicAdd(grad_w + P::BD + tid, sm.gb[S + tid]);
+  if (tid < K2) {
+    const int s = out_state(tid, S);
+    const int base = out_is_degr(tid, S) ? (H + S * H + S + S * H) : (H + S * H);
+    atomicAdd(grad_w + base + s, sm.gb[tid]);
   }
 }
 
@@ -588,7 +780,12 @@ struct Shape {
   int H, S;
 };
 // (25,5): CVS / challenge configs; (25,8): proc config; the rest serve tests and the width sweep.
+#ifdef SLODE_ONLY_25_5
+#define SLODE_SHAPES(X) X(25, 5)
+#else
 #define SLODE_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5)
+#endif
+
 
 static const Shape kShapes[] = {
 #define X(h, s) {h, s},
@@ -599,14 +796,14 @@ constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
 static int upload_pack(PackGuard& g, int H, int S, const float* w1t, const float* Wg, const float* bg,
                        const float* Wd, const float* bd) {
-  const int n = H + 2 * (S * H + S);
+  const int n = (H + 3) / 4 * 4 + (2 * S + 3) / 4 * 4 + H * 2 * S;
   if (n > kPackMax) {
     set_error("packed weights (%d floats) exceed the constant buffer", n);
     return SLODE_EUNSUPPORTED;
   }
   pack_kernel<<<1, 256, 0, g.stream>>>(H, S, w1t, Wg, bg, Wd, bd, g.staging);
   SLODE_CUDA_TRY(cudaGetLastError());
-  SLODE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_pack, g.staging, sizeof(float) * n, 0, cudaMemcpyDeviceToDevice, g.stream));
+  SLODE_CUDA_TRY(cudaMemcpyToSymbolAsync(slode_c_pack, g.staging, sizeof(float) * n, 0, cudaMemcpyDeviceToDevice, g.stream));
   return SLODE_OK;
 }
 
@@ -615,7 +812,7 @@ static int launch_fwd(int64_t B, int T, const float* t, const float* c, const fl
                       int64_t sb, cudaStream_t stream, int sms) {
   const int64_t tiles = (B + kBlock - 1) / kBlock;
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * 64);
-  mlp_fixed_fwd_kernel<H, S, METHOD><<<grid, kBlock, 0, stream>>>(B, T, t, c, y0, sol, st, sb);
+  mlp_fixed_fwd_kernel<H, S, METHOD><<<grid, kBlock, 0, stream>>>(B, T, t, c, y0, sol, st, sb, 0u);
   SLODE_CUDA_TRY(cudaGetLastError());
   return SLODE_OK;
 }
@@ -635,7 +832,7 @@ static int launch_bwd(int64_t B, int T, const float* t, const float* c, const fl
   }
   const int64_t tiles = (B + kBlock - 1) / kBlock;
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * blocks_per_sm);
-  kern<<<grid, kBlock, smem, stream>>>(B, T, t, c, w1t, Wg, Wd, sol, st, sb, gsol, gst, gsb, gy0, gc, gw);
+  kern<<<grid, kBlock, smem, stream>>>(B, T, t, c, w1t, Wg, Wd, sol, st, sb, gsol, gst, gsb, gy0, gc, gw, 0u);
   SLODE_CUDA_TRY(cudaGetLastError());
   return SLODE_OK;
 }
