@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the SLODE latent-ODE hot path on B200 (contract: see the task statement / DESIGN.md section 5).
+
+    python bench.py --gpus 1 --steps K --warmup W                      # this repo's sm_100a path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W     # reference algorithm on the host cores
+
+Workload (BASELINE.json configs[1], blackbox variant, SURVEY.md section 8d "Config 2"):
+    2^20 trajectories per GPU x 100 output times, fp32, rk4 (torchdiffeq's 3/8 rule), L=15 H=25 S=5,
+    forward solve + reverse sweep (exact discrete adjoint == torchdiffeq.odeint + autograd).
+metric = ODE trajectory-steps/s (fwd+bwd); one trajectory-step = one trajectory advanced across one output interval.
+
+One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM.  ``e2e``: the same solve through the public
+API with the step's inputs (latents z and observations y) in pinned HOST memory, copied in inside the timed
+region, and the loss + flat parameter gradients read back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "ode_trajectory_steps_per_s_fwd_bwd"
+UNIT = "trajectory-steps/s"
+L, H, S, O, T = 15, 25, 5, 3, 100
+# fp32 FMA-pipe peak: 148 SMs x 128 lanes x 2 flop x 1.965 GHz; the FFMA2 micro-benchmark in
+# profiles/r01/fp32_pipes_microbench.jsonl measures 74.0 TFLOP/s (127.2 of 128 FMA/clk/SM) on this pool's B200.
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def algorithmic_flops(method: str, T: int, H: int, S: int):
+    """(forward, backward) fp32 flop per TRAJECTORY of the work the path needs:
+    hidden layer with the time-invariant part hoisted (2H per MLP evaluation), both heads (4HS), the sigmoid's add
+    (2S), f = A - D x per stage (2S), the Butcher combinations; MLP evaluations per step: euler 1, midpoint 2,
+    rk4 3 (+1 per solve: the 3/8 rule's last stage time is the next step's first).  Backward = stage recompute +
+    the adjoint recurrences + the prefix-sum weight-gradient bookkeeping."""
+    steps = T - 1
+    stages = {"euler": 1, "midpoint": 2, "rk4": 4}[method]
+    evals = {"euler": steps, "midpoint": 2 * steps, "rk4": 3 * steps + 1}[method]
+    mlp = 2 * H + 4 * H * S + 2 * S
+    combine = {"euler": 2 * S, "midpoint": 4 * S, "rk4": 16 * S}[method]
+    fwd = evals * mlp + steps * (stages * 2 * S + combine)
+    # per stage: cotangents of the head pre-activations (10S), P/Q prefix sums (8S), adjoint update (6S);
+    # per hidden unit: two snapshots (gate flip + end of sweep) of 2 * (4*2S + 3*2S) flop.
+    bwd = fwd + steps * stages * 24 * S + H * 2 * (14 * 2 * S)
+    return float(fwd), float(bwd)
+
+
+def algorithmic_bytes(T: int, H: int, S: int):
+    """(forward, backward) HBM bytes per trajectory: fwd reads c (H) + y0 (S), writes sol (T*S);
+    bwd reads sol + grad_sol + c, writes grad_y0 + grad_c."""
+    return 4.0 * (H + S + T * S), 4.0 * (2 * T * S + H + S + H)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, period=0.05):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop_flag = threading.Event()
+        self.period = period
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop_flag.set()
+        if self.nv is not None:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s), "power_w_max": round(max(self.power), 1) if self.power else None}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------
+def seeded_port_model(method, adjoint):
+    """CPU legs only (cpu_baseline / --impl reference): the oracle port of the reference classes with
+    reference-architecture weights under torch.manual_seed(12) (config_cvs.py:28)."""
+    from oracle import slode_port
+    torch.manual_seed(12)
+    times = torch.arange(0.0, T, 1.0)
+    return slode_port.OdeModel(times, S, L, H, adjoint, method)
+
+
+def cpu_reference_step(model, heads_w, z, y):
+    """One fwd+bwd of the reference algorithm on the host: x0 net, torchdiffeq-style solve, q50 head, MSE, backward."""
+    model.zero_grad()
+    sol = model.solve_ODE(z)
+    loss = ((sol @ heads_w.t()) - y).square().mean()
+    loss.backward()
+    return float(loss.detach())
+
+
+def time_cpu_reference(method, adjoint, B, reps, warmup=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = seeded_port_model(method, adjoint)
+    g = torch.Generator().manual_seed(12)
+    z = torch.randn(B, L, generator=g)
+    y = torch.rand(B, T, O, generator=g)
+    Wq = torch.randn(O, S, generator=g) * 0.3
+    for _ in range(warmup):
+        cpu_reference_step(model, Wq, z, y)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(model, Wq, z, y)
+        times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def run_reference_arm(args):
+    """The reference's own algorithm (oracle port of models/blackbox_ode.py + torchdiffeq restatement; the real
+    package cannot be installed: torchdiffeq / pyro are absent and there is no network) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.ref_batch
+    times, cores = time_cpu_reference(args.method, args.adjoint, B, args.steps, warmup=max(1, min(args.warmup, 2)))
+    total = sum(times)
+    value = B * (T - 1) * len(times) / total
+    sample = f"{B} of 2^20 trajectories per step, T={T}, {args.method}, fwd+bwd, {len(times)} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, B_per_gpu=B, n=1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, B_per_gpu, n):
+    return {"workload": "configs[1] blackbox: 2^20 trajectories/GPU x 100 obs times, fp32 rk4(3/8) fwd+bwd",
+            "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L,
+            "ode_hidden_dim": H, "ode_state_dim": S, "solver": args.method,
+            "gradient": "odeint_adjoint emulation" if args.adjoint else "discrete adjoint (odeint + autograd parity)",
+            "parallelism": f"trajectory-sharded x{n}, one flat all-reduce of parameter gradients",
+            "l2": "inputs larger than L2 (sol / grad_sol are 2.1 GB each per GPU vs 126 MB L2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="trajectories per GPU")
+    ap.add_argument("--method", default="rk4", choices=["euler", "midpoint", "rk4"])
+    ap.add_argument("--adjoint", action="store_true", help="odeint_adjoint gradient semantics instead of discrete")
+    ap.add_argument("--ref-batch", type=int, default=8192, help="trajectories per CPU step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    import structured_latent_odes_b200 as slode
+    from structured_latent_odes_b200 import _cabi, sharding
+    from structured_latent_odes_b200.torchdiffeq_api import KernelTimer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()
+
+    B = args.batch
+    torch.manual_seed(12)  # reference seed (config_cvs.py:28); identical weights on every rank
+    model = slode.OdeModel()
+    model.init_with_params(times=torch.arange(0.0, T, 1.0, device=dev), ode_state_dim=S, latent_dim=L,
+                           ode_hidden_dim=H, adjoint_solver=args.adjoint, solver=args.method, device=dev)
+    model = model.to(dev)
+    params = [p for k, p in model.named_parameters()]
+    reducer = sharding.FlatGradReducer(params)
+
+    g = torch.Generator(device=dev).manual_seed(12 + rank)
+    z = torch.randn(B, L, device=dev, generator=g)
+    G = torch.randn(T, B, S, device=dev, generator=g).permute(1, 0, 2)  # upstream dL/dsol, resident
+    launches = [0]
+    lib = _cabi.lib()
+
+    def step_resident():
+        model.zero_grad(set_to_none=True)
+        sol = model.solve_ODE(z)
+        launches[0] += lib.slode_query(_cabi.Q_FWD_LAUNCHES)
+        sol.backward(G)
+        launches[0] += lib.slode_query(_cabi.Q_BWD_LAUNCHES)
+        reducer.reduce()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks, KernelTimer() as kt:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        ktimes = kt.summary()
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    value = world * B * (T - 1) * args.steps / (ms_total * 1e-3)
+    n_launches = launches[0]
+
+    # ---- end to end: pinned host inputs -> loss + gradients back on the host --------------------------------
+    gc = torch.Generator().manual_seed(100 + rank)
+    z_host = torch.randn(B, L, generator=gc).pin_memory()
+    y_host = torch.rand(B, T, O, generator=gc).pin_memory()
+    Wq = (torch.randn(O, S, generator=torch.Generator().manual_seed(7)) * 0.3).to(dev)
+    nchunk = max(1, args.e2e_chunks)
+    bounds = [sharding.shard_bounds(B, i, nchunk) for i in range(nchunk)]
+    copy_stream = torch.cuda.Stream()
+    out_host = torch.empty(1 + reducer.numel, dtype=torch.float32).pin_memory()
+    zbuf = [torch.empty(bounds[0][1] - bounds[0][0], L, device=dev) for _ in range(2)]
+    ybuf = [torch.empty(bounds[0][1] - bounds[0][0], T, O, device=dev) for _ in range(2)]
+
+    def step_e2e():
+        """Chunked, double-buffered: chunk k+1 is copied on the copy stream while chunk k is solved."""
+        model.zero_grad(set_to_none=True)
+        main = torch.cuda.current_stream()
+        loss_acc = torch.zeros((), device=dev)
+        ready = [None, None]
+        free = [None, None]
+
+        def issue(i):
+            lo, hi = bounds[i]
+            s = i & 1
+            with torch.cuda.stream(copy_stream):
+                if free[s] is not None:
+                    copy_stream.wait_event(free[s])
+                zbuf[s][: hi - lo].copy_(z_host[lo:hi], non_blocking=True)
+                ybuf[s][: hi - lo].copy_(y_host[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            ready[s] = ev
+
+        issue(0)
+        for i in range(nchunk):
+            lo, hi = bounds[i]
+            s = i & 1
+            if i + 1 < nchunk:
+                issue(i + 1)
+            main.wait_event(ready[s])
+            zc, yc = zbuf[s][: hi - lo], ybuf[s][: hi - lo]
+            sol = model.solve_ODE(zc)
+            loss = ((sol @ Wq.t()) - yc).square().sum() / (B * T * O)
+            loss.backward()
+            loss_acc += loss.detach()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            free[s] = ev
+        flat = reducer.reduce()
+        out_host[:1].copy_(loss_acc.reshape(1), non_blocking=True)
+        out_host[1:].copy_(flat, non_blocking=True)
+        main.synchronize()  # the caller reads the loss: the step ends when it is on the host
+
+    for _ in range(3):
+        step_e2e()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    sync_all()
+    t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * (T - 1) * args.steps / (float(t_e2e.item()) * 1e-3)
+    h2d = z_host.numel() * 4 + y_host.numel() * 4
+    d2h = out_host.numel() * 4
+
+    if rank == 0:
+        ff, fb = algorithmic_flops(args.method, T, H, S)
+        bf, bb = algorithmic_bytes(T, H, S)
+        fwd_ms = sum(ktimes["fwd"]) / max(len(ktimes["fwd"]), 1)
+        bwd_ms = sum(ktimes["bwd"]) / max(len(ktimes["bwd"]), 1)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"bwd_{args.method}_{int(args.adjoint)}")
+        except Exception:
+            pass
+        achieved_b = B * fb / (bwd_ms * 1e-3) / 1e12
+        achieved_f = B * ff / (fwd_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, B, world),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t_e2e.item()) / args.steps,
+                    "what": f"pinned z (B,{L}) + observations (B,{T},{O}) -> solve -> q50 head + MSE -> backward -> "
+                            f"loss + {reducer.numel} parameter gradients on the host; {nchunk} double-buffered chunks"},
+            "gpu_launches": n_launches,
+            "roofline": {"bound": "fp32", "kernel": "mlp_fixed_bwd_kernel (reverse sweep, dominant)",
+                         "achieved": achieved_b, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved_b / FP32_PEAK_TFLOPS, "traffic": traffic,
+                         "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz; FFMA2 micro-benchmark measured 74.0 "
+                                        "(profiles/r01/fp32_pipes_microbench.jsonl); MEASURED_PEAKS.json has no fp32 entry",
+                         "algorithmic_flop_per_launch": B * fb, "ms_per_launch": bwd_ms,
+                         "hbm": {"achieved": B * bb / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": B * bb / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "measured" if peaks else "fallback"}},
+            "roofline_fwd": {"bound": "fp32", "kernel": "mlp_fixed_fwd_kernel", "achieved": achieved_f,
+                             "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_f / FP32_PEAK_TFLOPS,
+                             "algorithmic_flop_per_launch": B * ff, "ms_per_launch": fwd_ms,
+                             "hbm": {"achieved": B * bf / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": B * bf / (fwd_ms * 1e-3) / 1e9 / hbm_peak}},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            reps = 3
+            times, cores = time_cpu_reference(args.method, args.adjoint, args.ref_batch, reps)
+            v = args.ref_batch * (T - 1) * reps / sum(times)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.ref_batch} of 2^20 trajectories, T={T}, {args.method}, fwd+bwd "
+                                              f"(x0 net, solve, q50 head + MSE, backward), best-effort all host threads, "
+                                              f"{reps} reps after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

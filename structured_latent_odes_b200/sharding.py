@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing for the latent-ODE solve: shard trajectories, reduce parameter gradients once.
+
+Trajectories are independent (``Dynamics.forward`` has no cross-trajectory term,
+``models/blackbox_ode.py:97-109``), so the batch axis shards with no forward communication.  The only
+exchange of a training step is the sum of the parameter gradients, done as ONE ``all_reduce`` over a
+single flat fp32 buffer (dynamics + initial-state net + whatever else the caller registers).  The
+reference has no distributed code at all; this is where ``training_*.py`` would gain it
+(``run_batch``, ``training_cvs.py:147-157``).
+
+One process per GPU; ``torch.distributed`` backend ``nccl`` on GPUs, ``gloo`` in the CPU tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_total: int, rank: int, world_size: int):
+    """Contiguous row range [lo, hi) of rank ``rank``; the first ``n_total % world_size`` ranks get one extra."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, rem = divmod(n_total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_rows(x: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
+    lo, hi = shard_bounds(x.shape[0], rank, world_size)
+    return x[lo:hi]
+
+
+class FlatGradReducer:
+    """Sum the ``.grad`` of a fixed parameter list across ranks with one collective.
+
+    The flat buffer is allocated once; ``reduce()`` packs, all-reduces (SUM) and unpacks in place.
+    Parameters whose ``.grad`` is ``None`` contribute zeros (every rank must issue the same collective).
+    """
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no parameters to reduce")
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        self.group = group
+
+    def reduce(self, average: bool = False):
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[o:o + n].zero_()
+            else:
+                self.flat[o:o + n].copy_(p.grad.reshape(-1))
+            o += n
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if average:
+                self.flat.div_(dist.get_world_size(self.group))
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = self.flat[o:o + n].view_as(p).clone()
+            else:
+                p.grad.copy_(self.flat[o:o + n].view_as(p))
+            o += n
+        return self.flat

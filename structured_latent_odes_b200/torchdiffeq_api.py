@@ -25,9 +25,52 @@ from torch import nn
 
 from . import _cabi
 
-__all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_func"]
+__all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_func", "KernelTimer"]
 
 FIXED_METHODS = ("euler", "midpoint", "rk4")
+
+
+class KernelTimer:
+    """Optional CUDA-event timing of the C-ABI calls (bench.py uses it for the roofline numbers).
+
+    ``with KernelTimer() as kt: ...`` records an event pair on the launching stream around every
+    forward / backward library call made inside the block; ``kt.summary()`` synchronises and returns
+    ``{"fwd": [ms...], "bwd": [ms...]}``.
+    """
+
+    active = None
+
+    def __init__(self):
+        self.events = {"fwd": [], "bwd": []}
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.events.items()}
+
+
+class _timed:
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __enter__(self):
+        kt = KernelTimer.active
+        if kt is not None:
+            self.pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.pair[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        kt = KernelTimer.active
+        if kt is not None:
+            self.pair[1].record()
+            kt.events[self.kind].append(self.pair)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -128,7 +171,7 @@ class _MlpFixedSolve(torch.autograd.Function):
         else:
             sol = torch.empty((T, B, S), device=y0.device, dtype=torch.float32)
         st, sb = sol.stride(0), sol.stride(1)
-        with torch.cuda.device(y0.device):
+        with torch.cuda.device(y0.device), _timed("fwd"):
             stream = torch.cuda.current_stream().cuda_stream
             rc = _cabi.lib().slode_mlp_fixed_fwd(method_id, B, T, H, S, _ptr(t), _ptr(cc), _ptr(y0c),
                                                  *[_ptr(x) for x in w], _ptr(sol), st, sb, stream)
@@ -149,7 +192,7 @@ class _MlpFixedSolve(torch.autograd.Function):
         grad_y0 = torch.empty((B, S), device=sol.device, dtype=torch.float32)
         grad_c = torch.empty((B, H), device=sol.device, dtype=torch.float32)
         grad_w = torch.zeros(H + 2 * (S * H + S), device=sol.device, dtype=torch.float32)
-        with torch.cuda.device(sol.device):
+        with torch.cuda.device(sol.device), _timed("bwd"):
             stream = torch.cuda.current_stream().cuda_stream
             rc = _cabi.lib().slode_mlp_fixed_bwd(
                 ctx.method_id, ctx.mode, B, T, H, S, _ptr(t), _ptr(cc), _ptr(w1t), _ptr(Wg), _ptr(bg), _ptr(Wd),

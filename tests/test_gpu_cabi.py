@@ -1,0 +1,38 @@
+"""Direct calls into the C ABI with raw device pointers (what a non-PyTorch host would do)."""
+import ctypes
+
+import pytest
+import torch
+
+import slode_testutil as U
+from structured_latent_odes_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_raw_pointer_call_matches_the_python_api():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    o = U.make_oracle("cvs", "rk4", False)
+    p = U.make_product(o)
+    B, T, L, H, S = 300, 86, 15, 25, 5
+    z = torch.randn(B, L, device="cuda")
+    want = p.solve_ODE(z).permute(1, 0, 2).contiguous()
+    d = p.dynamics
+    W1 = d.dynamics_hidden.weight.detach()
+    c = torch.addmm(d.dynamics_hidden.bias.detach(), z, W1[:, 1:].t()).contiguous()
+    y0 = p.initialize_state(z).detach().contiguous()
+    w1t = W1[:, 0].contiguous()
+    Wg, bg = d.dyanamics_growth.weight.detach().contiguous(), d.dyanamics_growth.bias.detach().contiguous()
+    Wd, bd = d.dyanmics_degradation.weight.detach().contiguous(), d.dyanmics_degradation.bias.detach().contiguous()
+    sol = torch.empty(T, B, S, device="cuda")
+    L_ = _cabi.lib()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    rc = L_.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, B, T, H, S, p.times.data_ptr(), c.data_ptr(), y0.data_ptr(),
+                                w1t.data_ptr(), Wg.data_ptr(), bg.data_ptr(), Wd.data_ptr(), bd.data_ptr(),
+                                sol.data_ptr(), B * S, S, ctypes.c_void_p(s.cuda_stream))
+    assert rc == 0, L_.slode_last_error()
+    s.synchronize()
+    assert torch.equal(sol, want)
+    assert L_.slode_query(_cabi.Q_FWD_LAUNCHES) >= 1
