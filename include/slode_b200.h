@@ -111,6 +111,37 @@ int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
                         float* grad_y0, float* grad_c, float* grad_w,
                         void* stream);
 
+/* element types of the CVS entry points */
+#define SLODE_F32 0
+#define SLODE_F64 1
+
+/*
+ * CVS mechanistic right-hand side (dx_dt, data/cvs/cvs_data.py:52-91), 4 states (Pa/100, Pv/10, S, SV/100),
+ * fixed-grid solve.  Replaces the reference's one-trajectory-at-a-time scipy LSODA loop
+ * (create_cvs_data, data/cvs/cvs_data.py:111-134) with a batched solve, and gives the RHS the odeint-style
+ * forward(t, state) module API of the latent ODE (north_star: "mechanistic RHS fused into the stage evaluation").
+ *   dtype      SLODE_F32 (odeint drop-in) or SLODE_F64 (data generator: the reference generates in float64);
+ *              every array below has that element type
+ *   substeps   solver steps per output interval (1 = torchdiffeq's "grid == t"; <= 16)
+ *   y0 (B,4), i_ext (B), r_tpr_mod (B): per-trajectory initial state and treatments (:24-26, :106-108)
+ *   theta (10) = [f_hr_max, f_hr_min, r_tpr_max, r_tpr_min, sv_mod, ca, cv, k_width, p_aset, tau] (:28-49)
+ *   sol / grad_sol indexing as in slode_mlp_fixed_fwd with S = 4
+ * Backward outputs: grad_y0 (B,4), grad_i_ext (B), grad_r_tpr_mod (B) written; grad_theta (10) ACCUMULATED
+ * (caller zero-fills).  Modes as for slode_mlp_fixed_bwd.
+ */
+int slode_cvs_fixed_fwd(int method, int dtype, int64_t B, int T, int substeps,
+                        const void* t, const void* y0, const void* i_ext, const void* r_tpr_mod,
+                        const void* theta,
+                        void* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                        void* stream);
+
+int slode_cvs_fixed_bwd(int method, int mode, int dtype, int64_t B, int T, int substeps,
+                        const void* t, const void* i_ext, const void* r_tpr_mod, const void* theta,
+                        const void* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                        const void* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
+                        void* grad_y0, void* grad_i_ext, void* grad_r_tpr_mod, void* grad_theta,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libslode_b200.so")
 METHOD_EULER, METHOD_MIDPOINT, METHOD_RK4, METHOD_DOPRI5 = 0, 1, 2, 3
 METHODS = {"euler": METHOD_EULER, "midpoint": METHOD_MIDPOINT, "rk4": METHOD_RK4, "dopri5": METHOD_DOPRI5}
 BWD_DISCRETE, BWD_TDE_ADJOINT = 0, 1
+F32, F64 = 0, 1
 Q_VERSION, Q_SM_ARCH, Q_MAX_HIDDEN, Q_MAX_STATE, Q_N_SHAPES = 0, 1, 2, 3, 4
 Q_FWD_LAUNCHES, Q_BWD_LAUNCHES, Q_SHAPE_BASE = 10, 11, 100
 
@@ -29,6 +30,9 @@ SIGNATURES = {
     "slode_mlp_fixed_fwd": (_i, [_i, _i64, _i, _i, _i] + [_p] * 8 + [_p, _i64, _i64, _p]),
     "slode_mlp_fixed_bwd": (_i, [_i, _i, _i64, _i, _i, _i] + [_p] * 7 + [_p, _i64, _i64, _p, _i64, _i64]
                             + [_p, _p, _p, _p]),
+    "slode_cvs_fixed_fwd": (_i, [_i, _i, _i64, _i, _i] + [_p] * 5 + [_p, _i64, _i64, _p]),
+    "slode_cvs_fixed_bwd": (_i, [_i, _i, _i, _i64, _i, _i] + [_p] * 4 + [_p, _i64, _i64, _p, _i64, _i64]
+                            + [_p] * 5),
 }
 
 _lib = None

@@ -106,7 +106,7 @@ def _check_blackbox(func):
     return z, hid, gro, deg
 
 
-def _check_common(y0, t, method, options, event_fn):
+def _check_common(func, y0, t, method, options, event_fn):
     if event_fn is not None:
         raise NotImplementedError("event_fn is not used by the reference and is not supported")
     if not torch.is_tensor(y0):
@@ -118,20 +118,22 @@ def _check_common(y0, t, method, options, event_fn):
     if not y0.is_cuda:
         raise RuntimeError("structured_latent_odes_b200 runs on CUDA tensors only (no CPU fallback); "
                            f"got y0 on {y0.device}")
-    if y0.dtype != torch.float32:
-        raise TypeError(f"y0 must be float32, got {y0.dtype}")
+    from .cvs_mechanistic import CvsMechanistic
+    is_cvs = isinstance(func, CvsMechanistic)
+    if y0.dtype != torch.float32 and not (is_cvs and y0.dtype == torch.float64):
+        raise TypeError(f"y0 must be float32 (float64 only for CvsMechanistic), got {y0.dtype}")
     if y0.ndim != 2:
         raise ValueError(f"y0 must be (B, S), got {tuple(y0.shape)}")
     if not torch.is_tensor(t) or t.ndim != 1 or t.numel() < 1:
         raise ValueError("t must be a one-dimensional tensor")
     if not t.is_floating_point():
         raise TypeError("t must be floating point")
-    t = t.detach().to(device=y0.device, dtype=torch.float32).contiguous()
+    t = t.detach().to(device=y0.device, dtype=y0.dtype).contiguous()
     if t.numel() > 1:
         d = t[1:] - t[:-1]
         if not (bool((d > 0).all()) or bool((d < 0).all())):
             raise ValueError("t must be strictly increasing or decreasing")
-    if method in FIXED_METHODS and options:
+    if method in FIXED_METHODS and options and not is_cvs:
         raise NotImplementedError(f"options={options!r} for fixed-grid solvers (the reference passes none: "
                                   "the solver grid is t itself)")
     return t, method
@@ -235,16 +237,21 @@ def _solve_blackbox(func, y0, t, method, mode, layout):
 # public API
 # ----------------------------------------------------------------------------------------------
 def _solve(func, y0, t, rtol, atol, method, options, event_fn, mode, layout):
-    t, method = _check_common(y0, t, method, options, event_fn)
+    t, method = _check_common(func, y0, t, method, options, event_fn)
     if layout not in ("tbs", "bts"):
         raise ValueError("layout must be 'tbs' (torchdiffeq's) or 'bts'")
+    from . import cvs_mechanistic as _cvs
+    if isinstance(func, _cvs.CvsMechanistic):
+        if method == "dopri5":
+            raise NotImplementedError("dopri5 for the CVS mechanistic dynamics: use rk4 with options={'step_size': h}")
+        return _cvs.solve_cvs(func, y0, t, method, mode, layout, options)
     if is_blackbox_func(func):
         if method == "dopri5":
             raise NotImplementedError("dopri5 for the blackbox dynamics is not built yet")
         return _solve_blackbox(func, y0, t, method, mode, layout)
     raise NotImplementedError(
         f"func of type {type(func).__name__} has no fused kernel; supported: OdeFunc over Dynamics "
-        "(models/blackbox_ode.py). There is no generic fallback solver.")
+        "(models/blackbox_ode.py) and CvsMechanistic (data/cvs/cvs_data.py dx_dt). There is no generic fallback solver.")
 
 
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, layout="tbs"):
