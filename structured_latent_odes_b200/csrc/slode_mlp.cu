@@ -185,26 +185,30 @@ __constant__ __align__(16) float slode_c_pack[slode::kPackMax];
 }
 namespace slode {
 
-// Weight loads.  Left alone, both NVVM and ptxas hoist the (loop-invariant) constant loads out of
-// the time loop into ~300 registers and spill them.  Every evaluation therefore reads through an
-// offset `wb` that is advanced by a kernel ARGUMENT which is always 0: uniform and loop-carried,
-// but not provably invariant, so the loads stay inside the evaluation as uniform-register loads
-// LDCU c[3][UR + imm] feeding the UR operand of FFMA2.
-typedef int wbase_t;
-// offset for evaluation number k of time-loop iteration i
-__device__ __forceinline__ wbase_t weight_base(int i, int k, unsigned wzero) { return (4 * i + k) * (int)wzero; }
+// Weight loads.  Left alone, both NVVM and ptxas hoist the (loop-invariant) constant loads out of the time loop
+// into ~300 registers and spill them.  The loads are therefore `asm volatile` with a STATIC address
+// (symbol + immediate): NVVM may not move or merge them, and ptxas keeps them inside the evaluation as 16-byte
+// uniform-register loads  LDCU.128 UR, c[3][imm]  -- one load per two FFMA2.  (A register-offset address
+// c[3][UR+imm] makes ptxas split every 16-byte load into two LDCU.64, one per FFMA2, and the kernel becomes
+// issue-bound: measured in profiles/r01.)  ptxas would still merge loads of the SAME address issued by different
+// evaluations of one time step into ordinary registers, so every evaluation site of a kernel reads its own copy
+// ("slot") of the packed weights: kSlots copies sit back to back in constant memory.
 template <int OFF_FLOATS>
-__device__ __forceinline__ void ldc_pair2(wbase_t wb, f2& a, f2& b) {
+__device__ __forceinline__ void ldc_pair2(f2& a, f2& b) {
   static_assert(OFF_FLOATS % 4 == 0, "16-byte aligned");
-  const float4 v = *reinterpret_cast<const float4*>(&slode_c_pack[wb * 4 + OFF_FLOATS]);
-  a = pk(v.x, v.y);
-  b = pk(v.z, v.w);
+  float x, y, z, w;
+  asm volatile("ld.const.v4.f32 {%0, %1, %2, %3}, [slode_c_pack+%4];"
+               : "=f"(x), "=f"(y), "=f"(z), "=f"(w)
+               : "n"(OFF_FLOATS * 4));
+  a = pk(x, y);
+  b = pk(z, w);
 }
 template <int OFF_FLOATS>
-__device__ __forceinline__ void ldc_pair1(wbase_t wb, f2& a) {
+__device__ __forceinline__ void ldc_pair1(f2& a) {
   static_assert(OFF_FLOATS % 2 == 0, "8-byte aligned");
-  const float2 v = *reinterpret_cast<const float2*>(&slode_c_pack[wb * 4 + OFF_FLOATS]);
-  a = pk(v.x, v.y);
+  float x, y;
+  asm volatile("ld.const.v2.f32 {%0, %1}, [slode_c_pack+%2];" : "=f"(x), "=f"(y) : "n"(OFF_FLOATS * 4));
+  a = pk(x, y);
 }
 
 template <int I, int N, class F>
@@ -223,6 +227,7 @@ __host__ __device__ constexpr int out_state(int o, int S) {
   return (o >= 4 * (S / 2)) ? (S - 1) : (2 * (o >> 2) + (o & 1));
 }
 
+constexpr int kSlots = 5;
 template <int H, int S>
 struct Pack {
   static constexpr int K2 = 2 * S;
@@ -231,16 +236,18 @@ struct Pack {
   static constexpr int W1T = 0;                // [j]     time column of the hidden layer
   static constexpr int BH = HP;                // [o]     head biases, pre-scaled by -log2(e)
   static constexpr int WH = HP + KP;           // [j][o]  head weights, pre-scaled by -log2(e)
-  static constexpr int N = WH + H * K2;
+  static constexpr int N = (WH + H * K2 + 3) / 4 * 4;  // one slot, 16-byte multiple
 };
 
 __global__ void pack_kernel(int H, int S, const float* __restrict__ w1t, const float* __restrict__ Wg,
                             const float* __restrict__ bg, const float* __restrict__ Wd,
                             const float* __restrict__ bd, float* __restrict__ out) {
-  const int K2 = 2 * S, HP = (H + 3) / 4 * 4, KP = (K2 + 3) / 4 * 4, BH = HP, WH = HP + KP, N = WH + H * K2;
+  const int K2 = 2 * S, HP = (H + 3) / 4 * 4, KP = (K2 + 3) / 4 * 4, BH = HP, WH = HP + KP,
+            N = (WH + H * K2 + 3) / 4 * 4;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     float v = 0.0f;
-    if (i < HP) {
+    if (i >= WH + H * K2) {
+    } else if (i < HP) {
       if (i < H) v = w1t[i];
     } else if (i < WH) {
       const int o = i - BH;
@@ -252,7 +259,7 @@ __global__ void pack_kernel(int H, int S, const float* __restrict__ w1t, const f
       const int j = (i - WH) / K2, o = (i - WH) % K2, s = out_state(o, S);
       v = kNegLog2e * (out_is_degr(o, S) ? Wd[s * H + j] : Wg[s * H + j]);
     }
-    out[i] = v;
+    for (int slot = 0; slot < kSlots; ++slot) out[slot * N + i] = v;
   }
 }
 
@@ -284,12 +291,12 @@ struct Sig {
 
 // One RHS evaluation at time t.  c2[jp] = (c_2jp, c_2jp+1).  Gate word w covers units
 // [32w, 32w+n_w); unit j sits at bit (n_w - 1 - (j - 32w)).
-template <int H, int S, bool MASK>
-__device__ __forceinline__ void mlp_eval(wbase_t wb, float t, const f2 (&c2)[(H + 1) / 2], Sig<S>& out,
+template <int H, int S, bool MASK, int SLOT>
+__device__ __forceinline__ void mlp_eval(float t, const f2 (&c2)[(H + 1) / 2], Sig<S>& out,
                                          uint32_t (&gate)[MaskWords<H>::NW]) {
   using P = Pack<H, S>;
   constexpr int NW = MaskWords<H>::NW;
-  constexpr int K2 = 2 * S;
+  constexpr int BASE = SLOT * P::N;
   float h[(H + 3) / 4 * 4];
   uint32_t neg[NW];
 #pragma unroll
@@ -299,7 +306,7 @@ __device__ __forceinline__ void mlp_eval(wbase_t wb, float t, const f2 (&c2)[(H 
   static_for<0, (H + 3) / 4>([&](auto I) {
     constexpr int qq = decltype(I)::value;
     f2 w0, w1;
-    ldc_pair2<P::W1T + 4 * qq>(wb, w0, w1);
+    ldc_pair2<BASE + P::W1T + 4 * qq>(w0, w1);
     float p[4];
     unpk(fma2(w0, tt, c2[2 * qq]), p[0], p[1]);
     if constexpr (2 * qq + 1 < (H + 1) / 2) unpk(fma2(w1, tt, c2[2 * qq + 1]), p[2], p[3]);
@@ -323,7 +330,7 @@ __device__ __forceinline__ void mlp_eval(wbase_t wb, float t, const f2 (&c2)[(H 
   f2 acc[(S + 1) / 2 * 2];
   static_for<0, (S + 1) / 2>([&](auto I) {
     constexpr int q = decltype(I)::value;
-    ldc_pair2<P::BH + 4 * q>(wb, acc[2 * q], acc[2 * q + 1]);
+    ldc_pair2<BASE + P::BH + 4 * q>(acc[2 * q], acc[2 * q + 1]);
   });
   // heads: flat pair index pi = j*S + op; two pairs per 16-byte uniform load
   constexpr int NPAIR = H * S;
@@ -331,14 +338,14 @@ __device__ __forceinline__ void mlp_eval(wbase_t wb, float t, const f2 (&c2)[(H 
     constexpr int q = decltype(I)::value;
     constexpr int pa = 2 * q, pb = 2 * q + 1;
     f2 wa, wb2;
-    ldc_pair2<P::WH + 4 * q>(wb, wa, wb2);
+    ldc_pair2<BASE + P::WH + 4 * q>(wa, wb2);
     acc[pa % S] = fma2(bc(h[pa / S]), wa, acc[pa % S]);
     acc[pb % S] = fma2(bc(h[pb / S]), wb2, acc[pb % S]);
   });
   if constexpr (NPAIR % 2 == 1) {
     constexpr int pa = NPAIR - 1;
     f2 wa;
-    ldc_pair1<P::WH + 2 * pa>(wb, wa);
+    ldc_pair1<BASE + P::WH + 2 * pa>(wa);
     acc[pa % S] = fma2(bc(h[pa / S]), wa, acc[pa % S]);
   }
   const f2 one = bc(1.0f);
@@ -399,7 +406,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     if (valid) vstore<S>(out, x);
     float t0 = __ldg(tgrid);
     Sig<S> e0;  // rk4: evaluation at the current grid time, carried over from the previous step
-    if (METHOD == SLODE_METHOD_RK4) mlp_eval<H, S, false>(weight_base(T, 0, wzero), t0, c2, e0, nogate);
+    if (METHOD == SLODE_METHOD_RK4) mlp_eval<H, S, false, 4>(t0, c2, e0, nogate);
 
 #pragma unroll 1
     for (int i = 0; i + 1 < T; ++i) {
@@ -407,26 +414,26 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       const float dt = t1 - t0;
       if (METHOD == SLODE_METHOD_EULER) {
         Sig<S> e;
-        mlp_eval<H, S, false>(weight_base(i, 0, wzero), t0, c2, e, nogate);
+        mlp_eval<H, S, false, 0>(t0, c2, e, nogate);
         x = vaxpy<S>(dt, rhs<S>(e, x), x);
       } else if (METHOD == SLODE_METHOD_MIDPOINT) {
         const float half_dt = 0.5f * dt;
         Sig<S> e, em;
-        mlp_eval<H, S, false>(weight_base(i, 1, wzero), t0, c2, e, nogate);
+        mlp_eval<H, S, false, 1>(t0, c2, e, nogate);
         const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(e, x), x);
-        mlp_eval<H, S, false>(weight_base(i, 2, wzero), after<S>(t0 + half_dt, e), c2, em, nogate);
+        mlp_eval<H, S, false, 2>(after<S>(t0 + half_dt, e), c2, em, nogate);
         x = vaxpy<S>(dt, rhs<S>(em, ym), x);
       } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func)
         Sig<S> e;
         const Vec<S> k1 = rhs<S>(e0, x);
         Vec<S> y = vaxpy<S>(dt * kOneThird, k1, x);
-        mlp_eval<H, S, false>(weight_base(i, 3, wzero), after<S>(t0 + dt * kOneThird, e0), c2, e, nogate);
+        mlp_eval<H, S, false, 3>(after<S>(t0 + dt * kOneThird, e0), c2, e, nogate);
         const Vec<S> k2 = rhs<S>(e, y);
         y = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
-        mlp_eval<H, S, false>(weight_base(i, 0, wzero), after<S>(t0 + dt * kTwoThirds, e), c2, e, nogate);
+        mlp_eval<H, S, false, 0>(after<S>(t0 + dt * kTwoThirds, e), c2, e, nogate);
         const Vec<S> k3 = rhs<S>(e, y);
         y = vaxpy<S>(dt, vadd<S>(vsub<S>(k1, k2), k3), x);
-        mlp_eval<H, S, false>(weight_base(i, 1, wzero), after<S>(t1, e), c2, e0, nogate);
+        mlp_eval<H, S, false, 1>(after<S>(t1, e), c2, e0, nogate);
         const Vec<S> k4 = rhs<S>(e0, y);
         const Vec<S> sum = vadd<S>(vaxpy<S>(3.0f, vadd<S>(k2, k3), k1), k4);
         x = vaxpy<S>(dt * 0.125f, sum, x);
@@ -603,7 +610,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       uint32_t g0[NW], g1[NW], g2[NW], g3[NW];
       bool started = false;
       if (METHOD == SLODE_METHOD_RK4) {
-        mlp_eval<H, S, true>(weight_base(T, 0, wzero), t1, c2, ec, g0);
+        mlp_eval<H, S, true, 4>(t1, c2, ec, g0);
         sw.init(g0);
         started = true;
       }
@@ -618,7 +625,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           const float dt = t1 - t0;
           if (METHOD == SLODE_METHOD_EULER) {
             Sig<S> e;
-            mlp_eval<H, S, true>(weight_base(i, 2, wzero), t0, c2, e, g1);
+            mlp_eval<H, S, true, 2>(t0, c2, e, g1);
             const Vec<S> gk = vscale<S>(lam, dt);
             if (!started) { sw.init(g1); started = true; } else sw.events(sm, g1);
             sw.add(t0, gk, x, e);
@@ -627,8 +634,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             const float half_dt = 0.5f * dt;
             const float tm = t0 + half_dt;
             Sig<S> e1, e2;
-            mlp_eval<H, S, true>(weight_base(i, 3, wzero), t0, c2, e1, g1);
-            mlp_eval<H, S, true>(weight_base(i, 0, wzero), after<S>(tm, e1), c2, e2, g2);
+            mlp_eval<H, S, true, 3>(t0, c2, e1, g1);
+            mlp_eval<H, S, true, 0>(after<S>(tm, e1), c2, e2, g2);
             const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(e1, x), x);
             Vec<S> gk = vscale<S>(lam, dt);  // dL/dk2
             if (!started) { sw.init(g2); started = true; } else sw.events(sm, g2);
@@ -644,9 +651,9 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             const float tb = t0 + dt * kTwoThirds;
             const float dt3 = dt * kOneThird;
             Sig<S> e1, e2, e3;
-            mlp_eval<H, S, true>(weight_base(i, 1, wzero), t0, c2, e1, g1);
-            mlp_eval<H, S, true>(weight_base(i, 2, wzero), after<S>(ta, e1), c2, e2, g2);
-            mlp_eval<H, S, true>(weight_base(i, 3, wzero), after<S>(tb, e2), c2, e3, g3);
+            mlp_eval<H, S, true, 1>(t0, c2, e1, g1);
+            mlp_eval<H, S, true, 2>(after<S>(ta, e1), c2, e2, g2);
+            mlp_eval<H, S, true, 3>(after<S>(tb, e2), c2, e3, g3);
             const Vec<S> k1 = rhs<S>(e1, x);
             const Vec<S> y2 = vaxpy<S>(dt3, k1, x);
             const Vec<S> k2 = rhs<S>(e2, y2);
@@ -691,7 +698,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           const Vec<S> zero = vbc<S>(0.0f);
           if (METHOD == SLODE_METHOD_EULER) {
             Sig<S> e;
-            mlp_eval<H, S, true>(weight_base(i, 0, wzero), t1, c2, e, g1);
+            mlp_eval<H, S, true, 0>(t1, c2, e, g1);
             const Vec<S> v = vscale<S>(lam, ds);
             if (!started) { sw.init(g1); started = true; } else sw.events(sm, g1);
             sw.add(t1, v, y, e);
@@ -700,8 +707,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             const float half = 0.5f * ds;
             const float tm = t1 - half;
             Sig<S> e1, e2;
-            mlp_eval<H, S, false>(weight_base(i, 1, wzero), t1, c2, e1, g1);
-            mlp_eval<H, S, true>(weight_base(i, 2, wzero), after<S>(tm, e1), c2, e2, g2);
+            mlp_eval<H, S, false, 1>(t1, c2, e1, g1);
+            mlp_eval<H, S, true, 2>(after<S>(tm, e1), c2, e2, g2);
             const Vec<S> ky1 = vsub<S>(zero, rhs<S>(e1, y));  // D1*y - A1
             const Vec<S> ka1 = vnmul<S>(lam, e1.D());         // -a*D1
             const Vec<S> ym = vaxpy<S>(half, ky1, y);
@@ -720,7 +727,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             const Vec<S> ka1 = vnmul<S>(lam, ec.D());
             sw.add(t1, vscale<S>(lam, w8), y, ec);
             // stage 2
-            mlp_eval<H, S, true>(weight_base(i, 3, wzero), after<S>(ta, ec), c2, e, g1);
+            mlp_eval<H, S, true, 3>(after<S>(ta, ec), c2, e, g1);
             Vec<S> ym = vaxpy<S>(ds * kOneThird, ky1, y);
             Vec<S> am = vaxpy<S>(ds * kOneThird, ka1, lam);
             const Vec<S> ky2 = vsub<S>(zero, rhs<S>(e, ym));
@@ -728,7 +735,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             sw.events(sm, g1);
             sw.add(ta, vscale<S>(am, 3.0f * w8), ym, e);
             // stage 3
-            mlp_eval<H, S, true>(weight_base(i, 0, wzero), after<S>(tb, e), c2, e, g1);
+            mlp_eval<H, S, true, 0>(after<S>(tb, e), c2, e, g1);
             ym = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ky1, ky2), y);
             am = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ka1, ka2), lam);
             const Vec<S> ky3 = vsub<S>(zero, rhs<S>(e, ym));
@@ -736,7 +743,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             sw.events(sm, g1);
             sw.add(tb, vscale<S>(am, 3.0f * w8), ym, e);
             // stage 4 at t0 (becomes the carried evaluation)
-            mlp_eval<H, S, true>(weight_base(i, 1, wzero), after<S>(t0, e), c2, ec, g1);
+            mlp_eval<H, S, true, 1>(after<S>(t0, e), c2, ec, g1);
             ym = vaxpy<S>(ds, vadd<S>(vsub<S>(ky1, ky2), ky3), y);
             am = vaxpy<S>(ds, vadd<S>(vsub<S>(ka1, ka2), ka3), lam);
             const Vec<S> ka4 = vnmul<S>(am, ec.D());
@@ -796,7 +803,7 @@ constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
 static int upload_pack(PackGuard& g, int H, int S, const float* w1t, const float* Wg, const float* bg,
                        const float* Wd, const float* bd) {
-  const int n = (H + 3) / 4 * 4 + (2 * S + 3) / 4 * 4 + H * 2 * S;
+  const int n = kSlots * (((H + 3) / 4 * 4 + (2 * S + 3) / 4 * 4 + H * 2 * S + 3) / 4 * 4);
   if (n > kPackMax) {
     set_error("packed weights (%d floats) exceed the constant buffer", n);
     return SLODE_EUNSUPPORTED;
