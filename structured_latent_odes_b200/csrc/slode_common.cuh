@@ -31,6 +31,10 @@ struct PackGuard {
   int sms;         // SM count of the current device
 };
 
+// Per-device scratch of the reverse sweep (flip records, see slode_mlp_kernels.cuh); grown on demand, owned by
+// the library, valid while the caller holds a PackGuard (which serialises the kernels that use it).
+float* flip_workspace(size_t bytes);
+
 // thread-local launch counters reported by slode_query
 extern thread_local int g_fwd_launches;
 extern thread_local int g_bwd_launches;

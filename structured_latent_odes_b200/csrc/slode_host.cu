@@ -31,6 +31,8 @@ struct DeviceState {
   int sms = 0;
   cudaEvent_t pack_done = nullptr;
   float* staging = nullptr;
+  float* flip_ws = nullptr;
+  size_t flip_bytes = 0;
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
@@ -48,6 +50,32 @@ DeviceState* current_device_state() {  // g_mu held
   return &d;
 }
 }  // namespace
+
+float* flip_workspace(size_t bytes) {  // g_mu is held by the caller's PackGuard
+  DeviceState* d = current_device_state();
+  if (!d) {
+    cuda_fail(cudaGetLastError(), "device state");
+    return nullptr;
+  }
+  if (bytes > d->flip_bytes) {
+    // kernels of earlier calls may still be using the old buffer: all of them are ordered before pack_done
+    if (d->flip_ws) {
+      if (cudaEventSynchronize(d->pack_done) != cudaSuccess || cudaFree(d->flip_ws) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "cudaFree(flip workspace)");
+        return nullptr;
+      }
+      d->flip_ws = nullptr;
+      d->flip_bytes = 0;
+    }
+    const cudaError_t e = cudaMalloc(&d->flip_ws, bytes);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "cudaMalloc(flip workspace)");
+      return nullptr;
+    }
+    d->flip_bytes = bytes;
+  }
+  return d->flip_ws;
+}
 
 PackGuard::PackGuard(cudaStream_t s) : status(0), stream(s), staging(nullptr), sms(148) {
   g_mu.lock();

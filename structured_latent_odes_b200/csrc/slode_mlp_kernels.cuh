@@ -1,0 +1,910 @@
+// Fixed-grid solve of the SLODE blackbox latent ODE and its reverse sweep, hand-written for sm_100a.
+//
+// Right-hand side (reference: Dynamics.forward, models/blackbox_ode.py:97-109):
+//     h_j(t)  = relu(w1t_j * t + c_j)                       c = z W1[:,1:]^T + b1  (per trajectory)
+//     A_k(t)  = sigmoid(bg_k + sum_j Wg_kj h_j(t))          "growth"
+//     D_k(t)  = sigmoid(bd_k + sum_j Wd_kj h_j(t))          "degradation"
+//     f(t,x)  = A(t) - D(t) * x                              (affine in the state, elementwise)
+//
+// Mapping: one thread = TWO trajectories for the whole time loop, packed in the two halves of a 64-bit
+// register pair; every arithmetic instruction of the kernel is a packed fp32x2 op (FFMA2 / FADD2 / FMUL2) over
+// that pair.  Weights are warp-uniform scalars streamed from constant memory into uniform registers (one
+// LDCU.128 = four weights) and enter the FMA as the broadcast operand:
+//     acc_o(traj0,traj1) += W_jo (UR, .F32 broadcast) * h_j(traj0,traj1)
+// Measured on B200 (profiles/r01/fp32_pipes_microbench.jsonl): this form sustains 127 of the 128 FMA/clk/SM
+// with one LDCU.128 per four FFMA2, where a 3-register FFMA reaches 84.  Per trajectory and MLP evaluation
+// (H=25, S=5): 137.5 FFMA2 + 39 LDCU.128 + 25 FMNMX + 20 MUFU + ~10 others  ->  FMA-pipe bound.
+//
+// rk4 (3/8 rule) re-uses the evaluation at t1 as the next step's evaluation at t0 (same float).
+//
+// Backward: reverse sweep over the stored grid states sol[i]; stages are recomputed.  Because the hidden layer
+// sees only (t, z), the cotangents delta_o(e) of the head pre-activations at the evaluation times t_e determine
+// every hidden-layer gradient through prefix sums
+//     P_o = sum_e delta_o(e),   Q_o = sum_e delta_o(e) t_e
+// taken over the evaluations where unit j is active.  The sweep keeps running P,Q and, whenever a unit's relu
+// gate flips between consecutive evaluations (once per unit for monotone t; the summation by parts is valid for
+// any number of flips), adds +-snapshot contributions
+//     dc_j   += s * sum_o W_oj P_o              (per trajectory -> grad_c)
+//     dw1t_j += s * sum_o W_oj Q_o              (block accumulator)
+//     dW_oj  += s * (w1t_j Q_o + c_j P_o)       (block accumulator, = sum_e delta_o h_j)
+// with s=+1 when the unit turns off, -1 when it turns on, and +1 for every unit still active when the sweep
+// ends.  This replaces the two dense 2S*H products per evaluation of a textbook backward by O(S) work.
+#pragma once
+
+#include <algorithm>
+#include <type_traits>
+
+#include "slode_common.cuh"
+#include "slode_mlp_api.h"
+
+#ifndef SLODE_PACK_SYM
+#error "define SLODE_PACK_SYM (the per-translation-unit constant symbol) before including slode_mlp_kernels.cuh"
+#endif
+#define SLODE_STR2(x) #x
+#define SLODE_STR(x) SLODE_STR2(x)
+
+namespace slode {
+
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic: lo = first trajectory of the thread, hi = second
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f2;
+
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 bc(float v) { return pk(v, v); }
+__device__ __forceinline__ void unpk(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+template <int HALF> __device__ __forceinline__ float half_of(f2 v) {
+  float a, b;
+  unpk(v, a, b);
+  return HALF ? b : a;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
+
+// S per-state values of the two trajectories
+template <int S>
+struct Vec {
+  f2 v[S];
+};
+#define SLODE_FOR_S for (int s = 0; s < S; ++s)
+
+template <int S> __device__ __forceinline__ Vec<S> vadd(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = add2(a.v[s], b.v[s]);
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vsub(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = sub2(a.v[s], b.v[s]);
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vmul(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = mul2(a.v[s], b.v[s]);
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vscale(const Vec<S>& a, float c) {
+  Vec<S> r;
+  const f2 cc = bc(c);
+#pragma unroll
+  SLODE_FOR_S r.v[s] = mul2(a.v[s], cc);
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vscale2(const Vec<S>& a, f2 cc) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = mul2(a.v[s], cc);
+  return r;
+}
+// c*a + b  (scalar c)
+template <int S> __device__ __forceinline__ Vec<S> vaxpy(float c, const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+  const f2 cc = bc(c);
+#pragma unroll
+  SLODE_FOR_S r.v[s] = fma2(cc, a.v[s], b.v[s]);
+  return r;
+}
+// c - a*b
+template <int S> __device__ __forceinline__ Vec<S> vnfma(const Vec<S>& a, const Vec<S>& b, const Vec<S>& c) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = fma2(neg2(a.v[s]), b.v[s], c.v[s]);
+  return r;
+}
+// -(a*b)
+template <int S> __device__ __forceinline__ Vec<S> vnmul(const Vec<S>& a, const Vec<S>& b) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = mul2(neg2(a.v[s]), b.v[s]);
+  return r;
+}
+template <int S> __device__ __forceinline__ Vec<S> vload2(const float* p0, const float* p1) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = pk(__ldg(p0 + s), __ldg(p1 + s));
+  return r;
+}
+template <int S> __device__ __forceinline__ void vstore2(float* p0, bool ok0, float* p1, bool ok1, const Vec<S>& a) {
+#pragma unroll
+  SLODE_FOR_S {
+    float lo, hi;
+    unpk(a.v[s], lo, hi);
+    if (ok0) p0[s] = lo;
+    if (ok1) p1[s] = hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed weights in constant memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kPackMax = 8192;   // floats (32 KB of the 64 KB constant bank), one buffer per compiled shape
+constexpr int kSlots = 5;        // copies of the packed weights, one per evaluation site of a kernel
+constexpr int kBlock = 128;      // threads per block = 256 trajectories per tile
+}  // namespace slode
+
+// C linkage: the loads below name the symbol from inline PTX.  One symbol per translation unit (= per compiled
+// (H,S) shape), named by SLODE_PACK_SYM.
+extern "C" {
+__constant__ __align__(16) float SLODE_PACK_SYM[slode::kPackMax];
+}
+namespace slode {
+
+// Weight loads are `asm volatile` with a STATIC address (symbol + immediate): NVVM may not move or merge them
+// and ptxas keeps them inside the evaluation as 16-byte uniform-register loads  LDCU.128 UR, c[3][imm].
+// (Left alone, both compilers hoist the loop-invariant loads out of the time loop into registers and spill; a
+// register-offset address c[3][UR+imm] makes ptxas split every 16-byte load into two LDCU.64.)  ptxas would
+// still merge loads of the SAME address issued by different evaluations of one time step into ordinary
+// registers, so every evaluation site of a kernel reads its own copy ("slot") of the packed weights.
+template <int OFF_FLOATS>
+__device__ __forceinline__ void ldc4(float* v) {
+  static_assert(OFF_FLOATS % 4 == 0, "16-byte aligned");
+  asm volatile("ld.const.v4.f32 {%0, %1, %2, %3}, [" SLODE_STR(SLODE_PACK_SYM) "+%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "n"(OFF_FLOATS * 4));
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// One slot: [ head biases (2S, padded to 4) | H unit records ], record j = [ w1t_j | W_j,0 .. W_j,2S-1 ] padded
+// to a multiple of 4 floats.  Head outputs o < S are growth, o >= S degradation; biases and head weights are
+// pre-scaled by -log2(e) so that sigmoid(u) = rcp(1 + ex2(v)).
+template <int H, int S>
+struct Pack {
+  static constexpr int K2 = 2 * S;
+  static constexpr int KP = (K2 + 3) / 4 * 4;
+  static constexpr int UNIT = (1 + K2 + 3) / 4 * 4;
+  static constexpr int N = KP + H * UNIT;
+};
+
+template <int H, int S>
+__global__ void pack_kernel(const float* __restrict__ w1t, const float* __restrict__ Wg, const float* __restrict__ bg,
+                            const float* __restrict__ Wd, const float* __restrict__ bd, float* __restrict__ out) {
+  using P = Pack<H, S>;
+  for (int i = threadIdx.x; i < P::N; i += blockDim.x) {
+    float v = 0.0f;
+    if (i < P::KP) {
+      if (i < P::K2) v = kNegLog2e * ((i < S) ? bg[i] : bd[i - S]);
+    } else {
+      const int j = (i - P::KP) / P::UNIT, r = (i - P::KP) % P::UNIT;
+      if (r == 0) {
+        v = w1t[j];
+      } else if (r <= P::K2) {
+        const int o = r - 1;
+        v = kNegLog2e * ((o < S) ? Wg[o * H + j] : Wd[(o - S) * H + j]);
+      }
+    }
+    for (int slot = 0; slot < kSlots; ++slot) out[slot * P::N + i] = v;
+  }
+}
+
+template <int H, int S>
+int upload_pack(const PackSrc& w, float* staging, cudaStream_t stream) {
+  using P = Pack<H, S>;
+  static_assert(kSlots * P::N <= kPackMax, "packed weights exceed the constant buffer");
+  pack_kernel<H, S><<<1, 256, 0, stream>>>(w.w1t, w.Wg, w.bg, w.Wd, w.bd, staging);
+  SLODE_CUDA_TRY(cudaGetLastError());
+  SLODE_CUDA_TRY(cudaMemcpyToSymbolAsync(SLODE_PACK_SYM, staging, sizeof(float) * kSlots * P::N, 0,
+                                         cudaMemcpyDeviceToDevice, stream));
+  return SLODE_OK;
+}
+
+template <int H>
+struct Gate {
+  static constexpr int NW = (H + 31) / 32;
+  uint32_t w[2][NW];  // [half][word]; unit j sits at bit (n_w - 1 - (j - 32 word)) of its word
+};
+
+// One RHS evaluation at time t for both trajectories.  cj(j) returns the pair (c_j of traj0, c_j of traj1).
+template <int H, int S, bool MASK, int SLOT, class CLoad>
+__device__ __forceinline__ void mlp_eval(float t, CLoad cj, Vec<S>& A, Vec<S>& D, Gate<H>& gate) {
+  using P = Pack<H, S>;
+  constexpr int K2 = 2 * S;
+  constexpr int BASE = SLOT * P::N;
+  constexpr int NW = Gate<H>::NW;
+  f2 acc[P::KP];
+  static_for<0, P::KP / 4>([&](auto I) {
+    constexpr int q = decltype(I)::value;
+    float b[4];
+    ldc4<BASE + 4 * q>(b);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[4 * q + r] = bc(b[r]);
+  });
+  uint32_t neg[2][NW];
+  if (MASK) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) neg[0][w] = neg[1][w] = 0u;
+  }
+  const f2 tt = bc(t);
+  static_for<0, H>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    float r[P::UNIT];
+    static_for<0, P::UNIT / 4>([&](auto Q) {
+      constexpr int q = decltype(Q)::value;
+      ldc4<BASE + P::KP + j * P::UNIT + 4 * q>(r + 4 * q);
+    });
+    float p0, p1;
+    unpk(fma2(bc(r[0]), tt, cj(j)), p0, p1);
+    if (MASK) {
+      neg[0][j / 32] = __funnelshift_l(__float_as_uint(p0), neg[0][j / 32], 1);
+      neg[1][j / 32] = __funnelshift_l(__float_as_uint(p1), neg[1][j / 32], 1);
+    }
+    const f2 h = pk(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f));
+#pragma unroll
+    for (int o = 0; o < K2; ++o) acc[o] = fma2(h, bc(r[1 + o]), acc[o]);
+  });
+  if (MASK) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
+      const uint32_t low = (nw == 32) ? 0xffffffffu : ((1u << nw) - 1u);
+      gate.w[0][w] = (~neg[0][w]) & low;
+      gate.w[1][w] = (~neg[1][w]) & low;
+    }
+  }
+  const f2 one = bc(1.0f);
+#pragma unroll
+  for (int o = 0; o < K2; ++o) {
+    float v0, v1;
+    unpk(acc[o], v0, v1);
+    const f2 e = add2(pk(ex2_approx(v0), ex2_approx(v1)), one);
+    unpk(e, v0, v1);
+    const f2 sg = pk(rcp_approx(v0), rcp_approx(v1));
+    if (o < S) A.v[o] = sg; else D.v[o - S] = sg;
+  }
+}
+
+// Scheduling fence: the RHS evaluations of one step do not depend on each other (the MLP sees only t), so ptxas
+// would interleave all of them and blow the register budget.  Making the next evaluation's time nominally
+// depend on the previous evaluation's outputs serialises them.
+template <int S>
+__device__ __forceinline__ float after(float t, const Vec<S>& a, const Vec<S>& d) {
+  asm volatile("" : "+f"(t) : "l"(a.v[0]), "l"(a.v[S - 1]), "l"(d.v[0]), "l"(d.v[S - 1]));
+  return t;
+}
+
+// f = A - D*x
+template <int S>
+__device__ __forceinline__ Vec<S> rhs(const Vec<S>& A, const Vec<S>& D, const Vec<S>& x) { return vnfma<S>(D, x, A); }
+
+#ifndef SLODE_FWD_MINB
+#define SLODE_FWD_MINB 4
+#endif
+#ifndef SLODE_BWD_MINB
+#define SLODE_BWD_MINB 3
+#endif
+
+// trajectory pair of a thread
+struct PairIdx {
+  int64_t b0, b1;
+  bool ok0, ok1;
+};
+__device__ __forceinline__ PairIdx pair_index(int64_t tile, int64_t B) {
+  const int64_t r = 2 * (tile * kBlock + threadIdx.x);
+  PairIdx p;
+  p.ok0 = r < B;
+  p.ok1 = r + 1 < B;
+  p.b0 = p.ok0 ? r : B - 1;      // tail threads redo trajectory B-1 with stores / cotangents masked off
+  p.b1 = p.ok1 ? r + 1 : B - 1;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int H, int S, int METHOD>
+__global__ void __launch_bounds__(kBlock, SLODE_FWD_MINB)
+mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
+                     const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb) {
+  Gate<H> nogate;
+  const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const PairIdx pi = pair_index(tile, B);
+    f2 c2[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) c2[j] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
+    auto cj = [&](int j) { return c2[j]; };
+    float* out0 = sol + pi.b0 * sb;
+    float* out1 = sol + pi.b1 * sb;
+    Vec<S> x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
+    vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
+    float t0 = __ldg(tgrid);
+    Vec<S> A, D, k1;
+    if (METHOD == SLODE_METHOD_RK4) {  // k1 of the first step; afterwards carried over from the step before
+      mlp_eval<H, S, false, 4>(t0, cj, A, D, nogate);
+      k1 = rhs<S>(A, D, x);
+    }
+
+#pragma unroll 1
+    for (int i = 0; i + 1 < T; ++i) {
+      const float t1 = __ldg(tgrid + i + 1);
+      const float dt = t1 - t0;
+      if (METHOD == SLODE_METHOD_EULER) {
+        mlp_eval<H, S, false, 0>(t0, cj, A, D, nogate);
+        x = vaxpy<S>(dt, rhs<S>(A, D, x), x);
+      } else if (METHOD == SLODE_METHOD_MIDPOINT) {
+        const float half_dt = 0.5f * dt;
+        mlp_eval<H, S, false, 1>(t0, cj, A, D, nogate);
+        const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A, D, x), x);
+        mlp_eval<H, S, false, 2>(after<S>(t0 + half_dt, A, D), cj, A, D, nogate);
+        x = vaxpy<S>(dt, rhs<S>(A, D, ym), x);
+      } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func)
+        Vec<S> y = vaxpy<S>(dt * kOneThird, k1, x);
+        mlp_eval<H, S, false, 3>(after<S>(t0 + dt * kOneThird, k1, y), cj, A, D, nogate);
+        const Vec<S> k2 = rhs<S>(A, D, y);
+        y = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
+        mlp_eval<H, S, false, 0>(after<S>(t0 + dt * kTwoThirds, A, D), cj, A, D, nogate);
+        const Vec<S> k3 = rhs<S>(A, D, y);
+        y = vaxpy<S>(dt, vadd<S>(vsub<S>(k1, k2), k3), x);
+        const Vec<S> part = vaxpy<S>(3.0f, vadd<S>(k2, k3), k1);
+        mlp_eval<H, S, false, 1>(after<S>(t1, A, D), cj, A, D, nogate);
+        const Vec<S> k4 = rhs<S>(A, D, y);
+        x = vaxpy<S>(dt * 0.125f, vadd<S>(part, k4), x);
+        k1 = rhs<S>(A, D, x);
+      }
+      out0 += st;
+      out1 += st;
+      vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
+      t0 = t1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <int H, int S>
+struct BwdSmem {
+  static constexpr int K2 = 2 * S;
+  f2 c[H][kBlock];           // c_j of the thread's two trajectories
+  f2 stash[5 * S][kBlock];   // rk4: [0,2S) / [2S,4S) double-buffered (A,D) at a grid time, [4S,5S) stage point Y2
+  float W[H][K2];            // original (unscaled) head weights, [unit][output]
+  float w1t[H];
+  float G[K2][H];            // block accumulators of dW, [output][unit]
+  float gw1t[H];
+  float gb[K2];
+};
+
+template <int H, int S>
+struct Sweep {
+  static constexpr int NW = Gate<H>::NW;
+  static constexpr int K2 = 2 * S;
+  static constexpr int REC = 2 * K2;              // floats per record: P[0..K2) then Q[0..K2) of one trajectory
+  static constexpr int REC_PER_THREAD = H * 2 * REC;  // [unit][half][REC]
+  f2 P[K2], Q[K2];
+  uint32_t prev[2][NW], first[2][NW];
+
+  __device__ __forceinline__ void init(const Gate<H>& g) {
+#pragma unroll
+    for (int o = 0; o < K2; ++o) P[o] = Q[o] = 0ull;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      prev[0][w] = first[0][w] = g.w[0][w];
+      prev[1][w] = first[1][w] = g.w[1][w];
+    }
+  }
+
+  // A relu gate of this trajectory flipped between the previous contributing evaluation and this one: record
+  // the prefix sums as they stand (before this evaluation is added) in the unit's slot of the thread's scratch.
+  // p_j(t) = w1t_j t + c_j is monotone in t, so each unit flips at most once per sweep.
+  template <int HALF>
+  __device__ __forceinline__ void events_half(float* __restrict__ rec, const Gate<H>& g) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      uint32_t diff = g.w[HALF][w] ^ prev[HALF][w];
+      const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
+      while (diff) {
+        const int q = __ffs(diff) - 1;
+        diff &= diff - 1;
+        const int j = 32 * w + (nw - 1 - q);
+        float4* dst = reinterpret_cast<float4*>(rec + (j * 2 + HALF) * REC);
+        float v[REC];
+#pragma unroll
+        for (int o = 0; o < K2; ++o) {
+          v[o] = half_of<HALF>(P[o]);
+          v[K2 + o] = half_of<HALF>(Q[o]);
+        }
+#pragma unroll
+        for (int k = 0; k < REC / 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+      prev[HALF][w] = g.w[HALF][w];
+    }
+  }
+  __device__ __forceinline__ void events(float* __restrict__ rec, const Gate<H>& g) {
+    events_half<0>(rec, g);
+    events_half<1>(rec, g);
+  }
+
+  // add the cotangents of the head pre-activations of one evaluation at time te:
+  //   f = A - D*y with upstream gf:  d(pre_A) = gf*A(1-A),  d(pre_D) = -gf*y*D(1-D)
+  __device__ __forceinline__ void add(float te, const Vec<S>& gf, const Vec<S>& y, const Vec<S>& A, const Vec<S>& D) {
+    const f2 tt = bc(te);
+#pragma unroll
+    SLODE_FOR_S {
+      const f2 dg = mul2(gf.v[s], fma2(neg2(A.v[s]), A.v[s], A.v[s]));                 // gf * (A - A^2)
+      const f2 dd = mul2(mul2(gf.v[s], y.v[s]), fma2(D.v[s], D.v[s], neg2(D.v[s])));   // gf*y * (D^2 - D)
+      P[s] = add2(P[s], dg);
+      Q[s] = fma2(dg, tt, Q[s]);
+      P[S + s] = add2(P[S + s], dd);
+      Q[S + s] = fma2(dd, tt, Q[S + s]);
+    }
+  }
+
+  // End of the sweep: for every hidden unit (uniform loop, all lanes busy) combine the recorded and the final
+  // prefix sums into the sums over the evaluations where the unit was active,
+  //     active throughout: final      turned off: record      turned on: final - record      never: 0
+  // and turn them into dc_j (per trajectory), dw1t_j and dW_oj (warp shuffle reduction, one shared atomic per
+  // warp and value).
+  __device__ __forceinline__ void finish(BwdSmem<H, S>& sm, const float* __restrict__ rec, float* gc0, float* gc1) {
+    const int tid = threadIdx.x;
+    const bool lane0 = (tid & 31) == 0;
+#pragma unroll 1
+    for (int j = 0; j < H; ++j) {
+      const int w = j >> 5;
+      const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
+      const int bit = nw - 1 - (j - 32 * w);
+      float arec[2], afin[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t fw = first[h][0], lw = prev[h][0];
+#pragma unroll
+        for (int ww = 1; ww < NW; ++ww) {
+          if (w == ww) { fw = first[h][ww]; lw = prev[h][ww]; }
+        }
+        const bool f = (fw >> bit) & 1u, l = (lw >> bit) & 1u;
+        arec[h] = (f == l) ? 0.0f : (f ? 1.0f : -1.0f);
+        afin[h] = l ? 1.0f : 0.0f;
+      }
+      const f2 ar = pk(arec[0], arec[1]), af = pk(afin[0], afin[1]);
+      const float4* r0 = reinterpret_cast<const float4*>(rec + (j * 2 + 0) * REC);
+      const float4* r1 = reinterpret_cast<const float4*>(rec + (j * 2 + 1) * REC);
+      float v0[REC], v1[REC];
+#pragma unroll
+      for (int k = 0; k < REC / 4; ++k) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (arec[0] != 0.0f) a = r0[k];
+        if (arec[1] != 0.0f) b = r1[k];
+        v0[4 * k] = a.x; v0[4 * k + 1] = a.y; v0[4 * k + 2] = a.z; v0[4 * k + 3] = a.w;
+        v1[4 * k] = b.x; v1[4 * k + 1] = b.y; v1[4 * k + 2] = b.z; v1[4 * k + 3] = b.w;
+      }
+      const f2 wj = bc(sm.w1t[j]);
+      const f2 cj = sm.c[j][tid];
+      f2 s1 = 0ull, s2 = 0ull;
+      float red[K2 + 1];
+#pragma unroll
+      for (int o = 0; o < K2; ++o) {
+        const f2 pe = fma2(ar, pk(v0[o], v1[o]), mul2(af, P[o]));
+        const f2 qe = fma2(ar, pk(v0[K2 + o], v1[K2 + o]), mul2(af, Q[o]));
+        const f2 wo = bc(sm.W[j][o]);
+        s1 = fma2(wo, pe, s1);
+        s2 = fma2(wo, qe, s2);
+        float lo, hi;
+        unpk(fma2(wj, qe, mul2(cj, pe)), lo, hi);
+        red[o] = lo + hi;
+      }
+      {
+        float lo, hi;
+        unpk(s1, lo, hi);
+        if (gc0) gc0[j] = lo;
+        if (gc1) gc1[j] = hi;
+        unpk(s2, lo, hi);
+        red[K2] = lo + hi;
+      }
+#pragma unroll
+      for (int k = 0; k <= K2; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
+      }
+      if (lane0) {
+#pragma unroll
+        for (int o = 0; o < K2; ++o) atomicAdd(&sm.G[o][j], red[o]);
+        atomicAdd(&sm.gw1t[j], red[K2]);
+      }
+    }
+    // head biases: total of the cotangents over all evaluations
+    float tot[K2];
+#pragma unroll
+    for (int o = 0; o < K2; ++o) {
+      float lo, hi;
+      unpk(P[o], lo, hi);
+      tot[o] = lo + hi;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) tot[o] += __shfl_xor_sync(0xffffffffu, tot[o], off);
+    }
+    if (lane0) {
+#pragma unroll
+      for (int o = 0; o < K2; ++o) atomicAdd(&sm.gb[o], tot[o]);
+    }
+  }
+};
+
+template <int S>
+__device__ __forceinline__ void stash_put(f2 (*st)[kBlock], int base, const Vec<S>& a) {
+#pragma unroll
+  SLODE_FOR_S st[base + s][threadIdx.x] = a.v[s];
+}
+template <int S>
+__device__ __forceinline__ Vec<S> stash_get(f2 (*st)[kBlock], int base) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = st[base + s][threadIdx.x];
+  return r;
+}
+
+template <int H, int S, int METHOD, int MODE>
+__global__ void __launch_bounds__(kBlock, SLODE_BWD_MINB)
+mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
+                     const float* __restrict__ w1t, const float* __restrict__ Wg, const float* __restrict__ Wd,
+                     const float* __restrict__ sol, int64_t st, int64_t sb,
+                     const float* __restrict__ gsol, int64_t gst, int64_t gsb,
+                     float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,
+                     float* __restrict__ flip_ws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem<H, S>& sm = *reinterpret_cast<BwdSmem<H, S>*>(smem_raw);
+  constexpr int K2 = 2 * S;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < H * K2; i += kBlock) {
+    const int j = i / K2, o = i % K2;
+    sm.W[j][o] = (o < S) ? Wg[o * H + j] : Wd[(o - S) * H + j];
+  }
+  for (int i = tid; i < H; i += kBlock) {
+    sm.w1t[i] = w1t[i];
+    sm.gw1t[i] = 0.0f;
+  }
+  for (int i = tid; i < K2 * H; i += kBlock) (&sm.G[0][0])[i] = 0.0f;
+  if (tid < K2) sm.gb[tid] = 0.0f;
+  __syncthreads();
+
+  const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const PairIdx pi = pair_index(tile, B);
+    // a masked-off half aliases trajectory B-1 (owned by another half): it must never touch grad_c
+    float* gc0 = pi.ok0 ? grad_c + pi.b0 * H : nullptr;
+    float* gc1 = pi.ok1 ? grad_c + pi.b1 * H : nullptr;
+    // this thread's flip-record slots (re-used tile after tile)
+    float* rec = flip_ws + ((size_t)blockIdx.x * kBlock + tid) * Sweep<H, S>::REC_PER_THREAD;
+#pragma unroll
+    for (int j = 0; j < H; ++j)
+      sm.c[j][tid] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
+    auto cj = [&](int j) { return sm.c[j][tid]; };
+    const float* xs0 = sol + pi.b0 * sb;
+    const float* xs1 = sol + pi.b1 * sb;
+    const float* gs0 = gsol + pi.b0 * gsb;
+    const float* gs1 = gsol + pi.b1 * gsb;
+    const f2 live = pk(pi.ok0 ? 1.0f : 0.0f, pi.ok1 ? 1.0f : 0.0f);
+    Vec<S> lam = vscale2<S>(vload2<S>(gs0 + (int64_t)(T - 1) * gst, gs1 + (int64_t)(T - 1) * gst), live);
+
+    Sweep<H, S> sw;
+    float t1 = __ldg(tgrid + T - 1);
+    Gate<H> g1, g2, g3;
+    bool started = false;
+    int cur = 0;  // rk4: which half of the (A,D) double buffer holds the evaluation at t1
+    if (METHOD == SLODE_METHOD_RK4) {
+      Vec<S> A, D;
+      mlp_eval<H, S, true, 4>(t1, cj, A, D, g1);
+      stash_put<S>(sm.stash, 0, A);
+      stash_put<S>(sm.stash, S, D);
+      sw.init(g1);
+      started = true;
+    }
+
+#pragma unroll 1
+    for (int i = T - 2; i >= 0; --i) {
+      const float t0 = __ldg(tgrid + i);
+      const Vec<S> x = vload2<S>(xs0 + (int64_t)i * st, xs1 + (int64_t)i * st);
+
+      if (MODE == SLODE_BWD_DISCRETE) {
+        const float dt = t1 - t0;
+        if (METHOD == SLODE_METHOD_EULER) {
+          Vec<S> A, D;
+          mlp_eval<H, S, true, 2>(t0, cj, A, D, g1);
+          const Vec<S> gk = vscale<S>(lam, dt);
+          if (!started) { sw.init(g1); started = true; } else sw.events(rec, g1);
+          sw.add(t0, gk, x, A, D);
+          lam = vnfma<S>(gk, D, lam);
+        } else if (METHOD == SLODE_METHOD_MIDPOINT) {
+          const float half_dt = 0.5f * dt;
+          const float tm = t0 + half_dt;
+          Vec<S> A1, D1, A2, D2;
+          mlp_eval<H, S, true, 3>(t0, cj, A1, D1, g1);
+          mlp_eval<H, S, true, 0>(after<S>(tm, A1, D1), cj, A2, D2, g2);
+          const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A1, D1, x), x);
+          Vec<S> gk = vscale<S>(lam, dt);  // dL/dk2
+          if (!started) { sw.init(g2); started = true; } else sw.events(rec, g2);
+          sw.add(tm, gk, ym, A2, D2);
+          const Vec<S> gy = vnmul<S>(gk, D2);  // dL/dy_mid
+          lam = vadd<S>(lam, gy);
+          gk = vscale<S>(gy, half_dt);  // dL/dk1
+          sw.events(rec, g1);
+          sw.add(t0, gk, x, A1, D1);
+          lam = vnfma<S>(gk, D1, lam);
+        } else {  // rk4 3/8
+          const float ta = t0 + dt * kOneThird;
+          const float tb = t0 + dt * kTwoThirds;
+          const float dt3 = dt * kOneThird;
+          const int nxt = cur ^ 1;
+          Vec<S> A, D, k1, k2, Y3, Y4;
+          {  // stage 1 at t0: (A,D) go to the double buffer (needed last here, first in the next interval)
+            mlp_eval<H, S, true, 1>(t0, cj, A, D, g1);
+            stash_put<S>(sm.stash, 2 * S * nxt, A);
+            stash_put<S>(sm.stash, 2 * S * nxt + S, D);
+            k1 = rhs<S>(A, D, x);
+          }
+          Vec<S> A2, D2, A3, D3;
+          {
+            const Vec<S> Y2 = vaxpy<S>(dt3, k1, x);
+            stash_put<S>(sm.stash, 4 * S, Y2);
+            mlp_eval<H, S, true, 2>(after<S>(ta, A, D), cj, A2, D2, g2);
+            k2 = rhs<S>(A2, D2, Y2);
+          }
+          Y3 = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
+          mlp_eval<H, S, true, 3>(after<S>(tb, A2, D2), cj, A3, D3, g3);
+          {
+            const Vec<S> k3 = rhs<S>(A3, D3, Y3);
+            Y4 = vaxpy<S>(dt, vadd<S>(vsub<S>(k1, k2), k3), x);
+          }
+          const Vec<S> w = vscale<S>(lam, 0.125f * dt);
+          Vec<S> gk1, gk2, gk3, gy;
+          {  // stage 4 (time t1, evaluation carried in the double buffer): gk4 = w
+            const Vec<S> Ac = stash_get<S>(sm.stash, 2 * S * cur), Dc = stash_get<S>(sm.stash, 2 * S * cur + S);
+            sw.add(t1, w, Y4, Ac, Dc);
+            gy = vnmul<S>(w, Dc);
+          }
+          lam = vadd<S>(lam, gy);
+          gk1 = vaxpy<S>(dt, gy, w);
+          gk2 = vaxpy<S>(-dt, gy, vscale<S>(w, 3.0f));
+          gk3 = vaxpy<S>(dt, gy, vscale<S>(w, 3.0f));
+          // stage 3
+          sw.events(rec, g3);
+          sw.add(tb, gk3, Y3, A3, D3);
+          gy = vnmul<S>(gk3, D3);
+          lam = vadd<S>(lam, gy);
+          gk2 = vaxpy<S>(dt, gy, gk2);
+          gk1 = vaxpy<S>(-dt3, gy, gk1);
+          // stage 2
+          sw.events(rec, g2);
+          sw.add(ta, gk2, stash_get<S>(sm.stash, 4 * S), A2, D2);
+          gy = vnmul<S>(gk2, D2);
+          lam = vadd<S>(lam, gy);
+          gk1 = vaxpy<S>(dt3, gy, gk1);
+          // stage 1 (time t0; its evaluation is the carried one of the next interval)
+          sw.events(rec, g1);
+          {
+            const Vec<S> A1 = stash_get<S>(sm.stash, 2 * S * nxt), D1 = stash_get<S>(sm.stash, 2 * S * nxt + S);
+            sw.add(t0, gk1, x, A1, D1);
+            lam = vnfma<S>(gk1, D1, lam);
+          }
+          cur = nxt;
+        }
+      } else {
+        // torchdiffeq.odeint_adjoint emulation: one step of the same method on the augmented system
+        // [y, a, a_theta] from t1 down to t0, y restarted from the stored sol[i+1].  In reversed time s=-t the
+        // step is ds = t1 - t0 > 0 with  Ky = D*y - A,  Ka = -a*D,  a_theta += w_m * a_m^T df/dtheta(t_m, y_m).
+        const float ds = t1 - t0;
+        const Vec<S> y = vload2<S>(xs0 + (int64_t)(i + 1) * st, xs1 + (int64_t)(i + 1) * st);
+        if (METHOD == SLODE_METHOD_EULER) {
+          Vec<S> A, D;
+          mlp_eval<H, S, true, 0>(t1, cj, A, D, g1);
+          const Vec<S> v = vscale<S>(lam, ds);
+          if (!started) { sw.init(g1); started = true; } else sw.events(rec, g1);
+          sw.add(t1, v, y, A, D);
+          lam = vnfma<S>(v, D, lam);
+        } else if (METHOD == SLODE_METHOD_MIDPOINT) {
+          const float half = 0.5f * ds;
+          const float tm = t1 - half;
+          Vec<S> A1, D1, A2, D2;
+          mlp_eval<H, S, false, 1>(t1, cj, A1, D1, g1);
+          mlp_eval<H, S, true, 2>(after<S>(tm, A1, D1), cj, A2, D2, g2);
+          const Vec<S> ym = vaxpy<S>(-half, rhs<S>(A1, D1, y), y);   // y + half*(D1*y - A1)
+          const Vec<S> am = vaxpy<S>(-half, vmul<S>(lam, D1), lam);  // a + half*(-a*D1)
+          const Vec<S> v = vscale<S>(am, ds);
+          if (!started) { sw.init(g2); started = true; } else sw.events(rec, g2);
+          sw.add(tm, v, ym, A2, D2);
+          lam = vnfma<S>(v, D2, lam);
+        } else {  // rk4 3/8 on the augmented system; Ky = -f, Ka = -a*D
+          const float ta = t1 - ds * kOneThird;
+          const float tb = t1 - ds * kTwoThirds;
+          const float w8 = 0.125f * ds;
+          const int nxt = cur ^ 1;
+          Vec<S> A, D;
+          const Vec<S> Ac = stash_get<S>(sm.stash, 2 * S * cur), Dc = stash_get<S>(sm.stash, 2 * S * cur + S);
+          // stage 1 at t1 (carried evaluation)
+          const Vec<S> ky1 = vsub<S>(vmul<S>(Dc, y), Ac);
+          const Vec<S> ka1 = vnmul<S>(lam, Dc);
+          sw.add(t1, vscale<S>(lam, w8), y, Ac, Dc);
+          // stage 2
+          mlp_eval<H, S, true, 3>(after<S>(ta, ky1, ka1), cj, A, D, g1);
+          Vec<S> ym = vaxpy<S>(ds * kOneThird, ky1, y);
+          Vec<S> am = vaxpy<S>(ds * kOneThird, ka1, lam);
+          const Vec<S> ky2 = vsub<S>(vmul<S>(D, ym), A);
+          const Vec<S> ka2 = vnmul<S>(am, D);
+          sw.events(rec, g1);
+          sw.add(ta, vscale<S>(am, 3.0f * w8), ym, A, D);
+          // stage 3
+          mlp_eval<H, S, true, 0>(after<S>(tb, A, D), cj, A, D, g1);
+          ym = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ky1, ky2), y);
+          am = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ka1, ka2), lam);
+          const Vec<S> ky3 = vsub<S>(vmul<S>(D, ym), A);
+          const Vec<S> ka3 = vnmul<S>(am, D);
+          sw.events(rec, g1);
+          sw.add(tb, vscale<S>(am, 3.0f * w8), ym, A, D);
+          // stage 4 at t0 (becomes the carried evaluation)
+          mlp_eval<H, S, true, 1>(after<S>(t0, A, D), cj, A, D, g1);
+          stash_put<S>(sm.stash, 2 * S * nxt, A);
+          stash_put<S>(sm.stash, 2 * S * nxt + S, D);
+          ym = vaxpy<S>(ds, vadd<S>(vsub<S>(ky1, ky2), ky3), y);
+          am = vaxpy<S>(ds, vadd<S>(vsub<S>(ka1, ka2), ka3), lam);
+          const Vec<S> ka4 = vnmul<S>(am, D);
+          sw.events(rec, g1);
+          sw.add(t0, vscale<S>(am, w8), ym, A, D);
+          const Vec<S> asum = vadd<S>(vaxpy<S>(3.0f, vadd<S>(ka2, ka3), ka1), ka4);
+          lam = vaxpy<S>(w8, asum, lam);
+          cur = nxt;
+        }
+      }
+      lam = vadd<S>(lam, vscale2<S>(vload2<S>(gs0 + (int64_t)i * gst, gs1 + (int64_t)i * gst), live));
+      t1 = t0;
+    }
+
+    if (started) {
+      sw.finish(sm, rec, gc0, gc1);  // a masked-off half carries zero cotangents: it only adds zeros
+    } else {  // T == 1: no evaluation at all
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        if (gc0) gc0[j] = 0.0f;
+        if (gc1) gc1[j] = 0.0f;
+      }
+    }
+    vstore2<S>(grad_y0 + pi.b0 * S, pi.ok0, grad_y0 + pi.b1 * S, pi.ok1, lam);
+  }
+
+  __syncthreads();
+  // flush block accumulators: grad_w = [ dw1t (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) ]
+  for (int i = tid; i < H; i += kBlock) atomicAdd(grad_w + i, sm.gw1t[i]);
+  for (int i = tid; i < K2 * H; i += kBlock) {
+    const int o = i / H, j = i % H;
+    const int base = (o < S) ? (H + o * H) : (H + S * H + S + (o - S) * H);
+    atomicAdd(grad_w + base + j, sm.G[o][j]);
+  }
+  if (tid < K2) {
+    const int base = (tid < S) ? (H + S * H + tid) : (H + S * H + S + S * H + (tid - S));
+    atomicAdd(grad_w + base, sm.gb[tid]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-shape launchers (instantiated in slode_mlp_inst_*.cu, dispatched from slode_mlp.cu)
+// ---------------------------------------------------------------------------------------------
+template <int H, int S, int METHOD>
+int launch_fwd(const FwdArgs& a) {
+  auto kern = mlp_fixed_fwd_kernel<H, S, METHOD>;
+  static int blocks_per_sm = 0;  // per instantiation
+  if (blocks_per_sm == 0) {
+    int n = 0;
+    SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, 0));
+    blocks_per_sm = std::max(n, 1);
+  }
+  const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
+  // whole waves of resident blocks; tiles are handed out grid-stride
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)a.sms * blocks_per_sm);
+  kern<<<grid, kBlock, 0, a.stream>>>(a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb);
+  SLODE_CUDA_TRY(cudaGetLastError());
+  return SLODE_OK;
+}
+
+template <int H, int S, int METHOD, int MODE>
+int launch_bwd(const BwdArgs& a) {
+  auto kern = mlp_fixed_bwd_kernel<H, S, METHOD, MODE>;
+  const size_t smem = sizeof(BwdSmem<H, S>);
+  static int blocks_per_sm = 0;  // per instantiation
+  if (blocks_per_sm == 0) {
+    SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, smem));
+    blocks_per_sm = std::max(n, 1);
+  }
+  const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)a.sms * blocks_per_sm);
+  float* ws = flip_workspace(sizeof(float) * (size_t)grid * kBlock * Sweep<H, S>::REC_PER_THREAD);
+  if (!ws) return SLODE_ECUDA;
+  kern<<<grid, kBlock, smem, a.stream>>>(a.B, a.T, a.t, a.c, a.w1t, a.Wg, a.Wd, a.sol, a.st, a.sb, a.gsol, a.gst,
+                                         a.gsb, a.gy0, a.gc, a.gw, ws);
+  SLODE_CUDA_TRY(cudaGetLastError());
+  return SLODE_OK;
+}
+
+template <int H, int S>
+int fwd_shape(const FwdArgs& a) {
+  switch (a.method) {
+    case SLODE_METHOD_EULER: return launch_fwd<H, S, SLODE_METHOD_EULER>(a);
+    case SLODE_METHOD_MIDPOINT: return launch_fwd<H, S, SLODE_METHOD_MIDPOINT>(a);
+    case SLODE_METHOD_RK4: return launch_fwd<H, S, SLODE_METHOD_RK4>(a);
+  }
+  set_error("fixed-grid forward: unknown method %d", a.method);
+  return SLODE_EINVAL;
+}
+
+template <int H, int S>
+int bwd_shape(const BwdArgs& a) {
+#define SLODE_BWD_CASE(M)                                                                            \
+  case M:                                                                                            \
+    return (a.mode == SLODE_BWD_DISCRETE) ? launch_bwd<H, S, M, SLODE_BWD_DISCRETE>(a)               \
+                                          : launch_bwd<H, S, M, SLODE_BWD_TDE_ADJOINT>(a);
+  switch (a.method) {
+    SLODE_BWD_CASE(SLODE_METHOD_EULER)
+    SLODE_BWD_CASE(SLODE_METHOD_MIDPOINT)
+    SLODE_BWD_CASE(SLODE_METHOD_RK4)
+  }
+#undef SLODE_BWD_CASE
+  set_error("fixed-grid backward: unknown method %d", a.method);
+  return SLODE_EINVAL;
+}
+
+}  // namespace slode
+
+// Defines the two entry functions of one compiled shape (looked up by slode_mlp.cu through slode_mlp_api.h).
+#define SLODE_DEFINE_SHAPE(H, S)                                                                         \
+  namespace slode {                                                                                      \
+  int mlp_fwd_##H##_##S(const FwdArgs& a, const PackSrc& w, float* staging) {                            \
+    const int rc = upload_pack<H, S>(w, staging, a.stream);                                              \
+    return rc ? rc : fwd_shape<H, S>(a);                                                                 \
+  }                                                                                                      \
+  int mlp_bwd_##H##_##S(const BwdArgs& a, const PackSrc& w, float* staging) {                            \
+    const int rc = upload_pack<H, S>(w, staging, a.stream);                                              \
+    return rc ? rc : bwd_shape<H, S>(a);                                                                 \
+  }                                                                                                      \
+  }
