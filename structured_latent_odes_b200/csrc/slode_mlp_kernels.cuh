@@ -152,6 +152,11 @@ template <int S> __device__ __forceinline__ Vec<S> vload2(const float* p0, const
   SLODE_FOR_S r.v[s] = pk(__ldg(p0 + s), __ldg(p1 + s));
   return r;
 }
+// pull the S floats at p (20-32 bytes, may straddle two sectors) towards L1 for a later vload2
+template <int S> __device__ __forceinline__ void vprefetch(const float* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p + S - 1));
+}
 template <int S> __device__ __forceinline__ void vstore2(float* p0, bool ok0, float* p1, bool ok1, const Vec<S>& a) {
 #pragma unroll
   SLODE_FOR_S {
@@ -437,35 +442,38 @@ struct Sweep {
     }
   }
 
-  // A relu gate of this trajectory flipped between the previous contributing evaluation and this one: record
-  // the prefix sums as they stand (before this evaluation is added) in the unit's slot of the thread's scratch.
-  // p_j(t) = w1t_j t + c_j is monotone in t, so each unit flips at most once per sweep.
-  template <int HALF>
-  __device__ __forceinline__ void events_half(float* __restrict__ rec, const Gate<H>& g) {
+  // A relu gate of one of the thread's trajectories flipped between the previous contributing evaluation and
+  // this one: record that trajectory's prefix sums as they stand (before this evaluation is added) in the
+  // unit's slot of the thread's scratch.  p_j(t) = w1t_j t + c_j is monotone in t, so each unit flips at most
+  // once per sweep.  One loop serves both halves (the half is selected at run time) to keep the code small.
+  __device__ __forceinline__ void events(float* __restrict__ rec, const Gate<H>& g) {
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-      uint32_t diff = g.w[HALF][w] ^ prev[HALF][w];
+      uint32_t d0 = g.w[0][w] ^ prev[0][w];
+      uint32_t d1 = g.w[1][w] ^ prev[1][w];
       const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
-      while (diff) {
-        const int q = __ffs(diff) - 1;
-        diff &= diff - 1;
+      while (d0 | d1) {
+        const bool hi = d0 == 0u;
+        const uint32_t d = hi ? d1 : d0;
+        const int q = __ffs(d) - 1;
+        if (hi) d1 &= d1 - 1; else d0 &= d0 - 1;
         const int j = 32 * w + (nw - 1 - q);
-        float4* dst = reinterpret_cast<float4*>(rec + (j * 2 + HALF) * REC);
+        float4* dst = reinterpret_cast<float4*>(rec + (j * 2 + (hi ? 1 : 0)) * REC);
         float v[REC];
 #pragma unroll
         for (int o = 0; o < K2; ++o) {
-          v[o] = half_of<HALF>(P[o]);
-          v[K2 + o] = half_of<HALF>(Q[o]);
+          float a, b;
+          unpk(P[o], a, b);
+          v[o] = hi ? b : a;
+          unpk(Q[o], a, b);
+          v[K2 + o] = hi ? b : a;
         }
 #pragma unroll
         for (int k = 0; k < REC / 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       }
-      prev[HALF][w] = g.w[HALF][w];
+      prev[0][w] = g.w[0][w];
+      prev[1][w] = g.w[1][w];
     }
-  }
-  __device__ __forceinline__ void events(float* __restrict__ rec, const Gate<H>& g) {
-    events_half<0>(rec, g);
-    events_half<1>(rec, g);
   }
 
   // add the cotangents of the head pre-activations of one evaluation at time te:
@@ -646,6 +654,12 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     for (int i = T - 2; i >= 0; --i) {
       const float t0 = __ldg(tgrid + i);
       const Vec<S> x = vload2<S>(xs0 + (int64_t)i * st, xs1 + (int64_t)i * st);
+      if (i > 0) {  // next interval's state and cotangent rows: in L1 by the time they are read
+        vprefetch<S>(xs0 + (int64_t)(i - 1) * st);
+        vprefetch<S>(xs1 + (int64_t)(i - 1) * st);
+        vprefetch<S>(gs0 + (int64_t)(i - 1) * gst);
+        vprefetch<S>(gs1 + (int64_t)(i - 1) * gst);
+      }
 
       if (MODE == SLODE_BWD_DISCRETE) {
         const float dt = t1 - t0;
