@@ -171,7 +171,7 @@ template <int S> __device__ __forceinline__ void vstore2(float* p0, bool ok0, fl
 // packed weights in constant memory
 // ---------------------------------------------------------------------------------------------
 constexpr int kPackMax = 8192;   // floats (32 KB of the 64 KB constant bank), one buffer per compiled shape
-constexpr int kSlots = 5;        // copies of the packed weights, one per evaluation site of a kernel
+constexpr int kSlots = 2;        // copies of the packed weights, one per evaluation site of a kernel
 constexpr int kBlock = 128;      // threads per block = 256 trajectories per tile
 }  // namespace slode
 
@@ -253,27 +253,41 @@ struct Gate {
   uint32_t w[2][NW];  // [half][word]; unit j sits at bit (n_w - 1 - (j - 32 word)) of its word
 };
 
-// One RHS evaluation at time t for both trajectories.  cj(j) returns the pair (c_j of traj0, c_j of traj1).
-template <int H, int S, bool MASK, int SLOT, class CLoad>
-__device__ __forceinline__ void mlp_eval(float t, CLoad cj, Vec<S>& A, Vec<S>& D, Gate<H>& gate) {
+// NE RHS evaluations (times t[0..NE)) for both trajectories in one pass over the weights.  The MLP sees only
+// (t, z), never the state, so all evaluations of one solver step can be taken together: every weight streamed
+// from constant memory then feeds NE FFMA2.  This matters because LDCU.128 sustains only one load per ~8 cycles
+// per SM sub-partition (profiles/microbench/ldcu_rate.cu): at one FFMA2 (2 cycles) per weight the weight stream
+// and the FMA pipe are exactly balanced and neither can be saturated; at NE >= 2 the kernel is FMA-bound.
+// cj(j) returns the pair (c_j of traj0, c_j of traj1).
+template <int H, int S, int NE, bool MASK, int SLOT, class CLoad>
+__device__ __forceinline__ void mlp_eval(const float (&t)[NE], CLoad cj, Vec<S> (&A)[NE], Vec<S> (&D)[NE],
+                                         Gate<H> (&gate)[NE]) {
   using P = Pack<H, S>;
   constexpr int K2 = 2 * S;
   constexpr int BASE = SLOT * P::N;
   constexpr int NW = Gate<H>::NW;
-  f2 acc[P::KP];
+  f2 acc[NE][P::KP];
   static_for<0, P::KP / 4>([&](auto I) {
     constexpr int q = decltype(I)::value;
     float b[4];
     ldc4<BASE + 4 * q>(b);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc[4 * q + r] = bc(b[r]);
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) acc[e][4 * q + r] = bc(b[r]);
+    }
   });
-  uint32_t neg[2][NW];
+  uint32_t neg[NE][2][NW];
   if (MASK) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) neg[0][w] = neg[1][w] = 0u;
+    for (int e = 0; e < NE; ++e) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) neg[e][0][w] = neg[e][1][w] = 0u;
+    }
   }
-  const f2 tt = bc(t);
+  f2 tt[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) tt[e] = bc(t[e]);
   static_for<0, H>([&](auto J) {
     constexpr int j = decltype(J)::value;
     float r[P::UNIT];
@@ -281,44 +295,51 @@ __device__ __forceinline__ void mlp_eval(float t, CLoad cj, Vec<S>& A, Vec<S>& D
       constexpr int q = decltype(Q)::value;
       ldc4<BASE + P::KP + j * P::UNIT + 4 * q>(r + 4 * q);
     });
-    float p0, p1;
-    unpk(fma2(bc(r[0]), tt, cj(j)), p0, p1);
-    if (MASK) {
-      neg[0][j / 32] = __funnelshift_l(__float_as_uint(p0), neg[0][j / 32], 1);
-      neg[1][j / 32] = __funnelshift_l(__float_as_uint(p1), neg[1][j / 32], 1);
-    }
-    const f2 h = pk(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f));
+    const f2 c = cj(j);
+    const f2 w1 = bc(r[0]);
+    f2 h[NE];
 #pragma unroll
-    for (int o = 0; o < K2; ++o) acc[o] = fma2(h, bc(r[1 + o]), acc[o]);
+    for (int e = 0; e < NE; ++e) {
+      float p0, p1;
+      unpk(fma2(w1, tt[e], c), p0, p1);
+      if (MASK) {
+        neg[e][0][j / 32] = __funnelshift_l(__float_as_uint(p0), neg[e][0][j / 32], 1);
+        neg[e][1][j / 32] = __funnelshift_l(__float_as_uint(p1), neg[e][1][j / 32], 1);
+      }
+      h[e] = pk(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f));
+    }
+#pragma unroll
+    for (int o = 0; o < K2; ++o) {
+      const f2 w = bc(r[1 + o]);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) acc[e][o] = fma2(h[e], w, acc[e][o]);
+    }
   });
   if (MASK) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
-      const uint32_t low = (nw == 32) ? 0xffffffffu : ((1u << nw) - 1u);
-      gate.w[0][w] = (~neg[0][w]) & low;
-      gate.w[1][w] = (~neg[1][w]) & low;
+    for (int e = 0; e < NE; ++e) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
+        const uint32_t low = (nw == 32) ? 0xffffffffu : ((1u << nw) - 1u);
+        gate[e].w[0][w] = (~neg[e][0][w]) & low;
+        gate[e].w[1][w] = (~neg[e][1][w]) & low;
+      }
     }
   }
   const f2 one = bc(1.0f);
 #pragma unroll
-  for (int o = 0; o < K2; ++o) {
-    float v0, v1;
-    unpk(acc[o], v0, v1);
-    const f2 e = add2(pk(ex2_approx(v0), ex2_approx(v1)), one);
-    unpk(e, v0, v1);
-    const f2 sg = pk(rcp_approx(v0), rcp_approx(v1));
-    if (o < S) A.v[o] = sg; else D.v[o - S] = sg;
+  for (int e = 0; e < NE; ++e) {
+#pragma unroll
+    for (int o = 0; o < K2; ++o) {
+      float v0, v1;
+      unpk(acc[e][o], v0, v1);
+      const f2 ex = add2(pk(ex2_approx(v0), ex2_approx(v1)), one);
+      unpk(ex, v0, v1);
+      const f2 sg = pk(rcp_approx(v0), rcp_approx(v1));
+      if (o < S) A[e].v[o] = sg; else D[e].v[o - S] = sg;
+    }
   }
-}
-
-// Scheduling fence: the RHS evaluations of one step do not depend on each other (the MLP sees only t), so ptxas
-// would interleave all of them and blow the register budget.  Making the next evaluation's time nominally
-// depend on the previous evaluation's outputs serialises them.
-template <int S>
-__device__ __forceinline__ float after(float t, const Vec<S>& a, const Vec<S>& d) {
-  asm volatile("" : "+f"(t) : "l"(a.v[0]), "l"(a.v[S - 1]), "l"(d.v[0]), "l"(d.v[S - 1]));
-  return t;
 }
 
 // f = A - D*x
@@ -326,10 +347,10 @@ template <int S>
 __device__ __forceinline__ Vec<S> rhs(const Vec<S>& A, const Vec<S>& D, const Vec<S>& x) { return vnfma<S>(D, x, A); }
 
 #ifndef SLODE_FWD_MINB
-#define SLODE_FWD_MINB 4
+#define SLODE_FWD_MINB 3
 #endif
 #ifndef SLODE_BWD_MINB
-#define SLODE_BWD_MINB 3
+#define SLODE_BWD_MINB 2
 #endif
 
 // trajectory pair of a thread
@@ -354,7 +375,6 @@ template <int H, int S, int METHOD>
 __global__ void __launch_bounds__(kBlock, SLODE_FWD_MINB)
 mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                      const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb) {
-  Gate<H> nogate;
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
@@ -367,10 +387,13 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     Vec<S> x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
     vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
     float t0 = __ldg(tgrid);
-    Vec<S> A, D, k1;
+    Vec<S> k1;
     if (METHOD == SLODE_METHOD_RK4) {  // k1 of the first step; afterwards carried over from the step before
-      mlp_eval<H, S, false, 4>(t0, cj, A, D, nogate);
-      k1 = rhs<S>(A, D, x);
+      Vec<S> A[1], D[1];
+      Gate<H> ng[1];
+      const float te[1] = {t0};
+      mlp_eval<H, S, 1, false, 1>(te, cj, A, D, ng);
+      k1 = rhs<S>(A[0], D[0], x);
     }
 
 #pragma unroll 1
@@ -378,27 +401,32 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       const float t1 = __ldg(tgrid + i + 1);
       const float dt = t1 - t0;
       if (METHOD == SLODE_METHOD_EULER) {
-        mlp_eval<H, S, false, 0>(t0, cj, A, D, nogate);
-        x = vaxpy<S>(dt, rhs<S>(A, D, x), x);
+        Vec<S> A[1], D[1];
+        Gate<H> ng[1];
+        const float te[1] = {t0};
+        mlp_eval<H, S, 1, false, 0>(te, cj, A, D, ng);
+        x = vaxpy<S>(dt, rhs<S>(A[0], D[0], x), x);
       } else if (METHOD == SLODE_METHOD_MIDPOINT) {
         const float half_dt = 0.5f * dt;
-        mlp_eval<H, S, false, 1>(t0, cj, A, D, nogate);
-        const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A, D, x), x);
-        mlp_eval<H, S, false, 2>(after<S>(t0 + half_dt, A, D), cj, A, D, nogate);
-        x = vaxpy<S>(dt, rhs<S>(A, D, ym), x);
-      } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func)
+        Vec<S> A[2], D[2];
+        Gate<H> ng[2];
+        const float te[2] = {t0, t0 + half_dt};
+        mlp_eval<H, S, 2, false, 0>(te, cj, A, D, ng);
+        const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A[0], D[0], x), x);
+        x = vaxpy<S>(dt, rhs<S>(A[1], D[1], ym), x);
+      } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func); the three new evaluations are taken together
+        Vec<S> A[3], D[3];
+        Gate<H> ng[3];
+        const float te[3] = {t0 + dt * kOneThird, t0 + dt * kTwoThirds, t1};
+        mlp_eval<H, S, 3, false, 0>(te, cj, A, D, ng);
         Vec<S> y = vaxpy<S>(dt * kOneThird, k1, x);
-        mlp_eval<H, S, false, 3>(after<S>(t0 + dt * kOneThird, k1, y), cj, A, D, nogate);
-        const Vec<S> k2 = rhs<S>(A, D, y);
+        const Vec<S> k2 = rhs<S>(A[0], D[0], y);
         y = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
-        mlp_eval<H, S, false, 0>(after<S>(t0 + dt * kTwoThirds, A, D), cj, A, D, nogate);
-        const Vec<S> k3 = rhs<S>(A, D, y);
+        const Vec<S> k3 = rhs<S>(A[1], D[1], y);
         y = vaxpy<S>(dt, vadd<S>(vsub<S>(k1, k2), k3), x);
-        const Vec<S> part = vaxpy<S>(3.0f, vadd<S>(k2, k3), k1);
-        mlp_eval<H, S, false, 1>(after<S>(t1, A, D), cj, A, D, nogate);
-        const Vec<S> k4 = rhs<S>(A, D, y);
-        x = vaxpy<S>(dt * 0.125f, vadd<S>(part, k4), x);
-        k1 = rhs<S>(A, D, x);
+        const Vec<S> k4 = rhs<S>(A[2], D[2], y);
+        x = vaxpy<S>(dt * 0.125f, vadd<S>(vaxpy<S>(3.0f, vadd<S>(k2, k3), k1), k4), x);
+        k1 = rhs<S>(A[2], D[2], x);
       }
       out0 += st;
       out1 += st;
@@ -415,7 +443,6 @@ template <int H, int S>
 struct BwdSmem {
   static constexpr int K2 = 2 * S;
   f2 c[H][kBlock];           // c_j of the thread's two trajectories
-  f2 stash[5 * S][kBlock];   // rk4: [0,2S) / [2S,4S) double-buffered (A,D) at a grid time, [4S,5S) stage point Y2
   float W[H][K2];            // original (unscaled) head weights, [unit][output]
   float w1t[H];
   float G[K2][H];            // block accumulators of dW, [output][unit]
@@ -491,20 +518,52 @@ struct Sweep {
     }
   }
 
+  // Sum K values over the 32 lanes of the warp with ~K (not 5K) shuffles: in every round each lane keeps half
+  // of its values and hands the other half to its partner, so after 5 rounds lane L holds the warp total of
+  // value (L mod NV) for the values that are left.  Returns the lane's slot index; slot v of round-5 lives in
+  // v[0] of the lanes with (lane % 32) bit pattern selecting it.  Implemented for K <= 32 padded to a power of 2.
+  template <int K>
+  __device__ __forceinline__ static float warp_sum_scatter(float (&v)[K], int lane, int& slot) {
+    // K is a power of two >= 1
+    int base = 0;
+    int n = K;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      if (n > 1) {
+        const int hn = n / 2;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < K / 2; ++k) {
+          if (k < hn) {
+            const float mine = upper ? v[k + hn] : v[k];
+            const float give = upper ? v[k] : v[k + hn];
+            v[k] = mine + __shfl_xor_sync(0xffffffffu, give, off);
+          }
+        }
+        if (upper) base += hn;
+        n = hn;
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+      }
+    }
+    slot = base;
+    return v[0];
+  }
+
   // End of the sweep: for every hidden unit (uniform loop, all lanes busy) combine the recorded and the final
   // prefix sums into the sums over the evaluations where the unit was active,
   //     active throughout: final      turned off: record      turned on: final - record      never: 0
-  // and turn them into dc_j (per trajectory), dw1t_j and dW_oj (warp shuffle reduction, one shared atomic per
-  // warp and value).
+  // and turn them into dc_j (per trajectory), dw1t_j and dW_oj (warp reduction, one shared atomic per warp and
+  // value).  The next unit's records are loaded while the current one is processed.
   __device__ __forceinline__ void finish(BwdSmem<H, S>& sm, const float* __restrict__ rec, float* gc0, float* gc1) {
     const int tid = threadIdx.x;
-    const bool lane0 = (tid & 31) == 0;
-#pragma unroll 1
-    for (int j = 0; j < H; ++j) {
+    const int lane = tid & 31;
+    constexpr int KR = (K2 + 1 <= 16) ? 16 : 32;  // values reduced per unit, padded to a power of two
+
+    auto coeffs = [&](int j, float (&arec)[2], float (&afin)[2]) {
       const int w = j >> 5;
       const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
       const int bit = nw - 1 - (j - 32 * w);
-      float arec[2], afin[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t fw = first[h][0], lw = prev[h][0];
@@ -516,22 +575,42 @@ struct Sweep {
         arec[h] = (f == l) ? 0.0f : (f ? 1.0f : -1.0f);
         afin[h] = l ? 1.0f : 0.0f;
       }
-      const f2 ar = pk(arec[0], arec[1]), af = pk(afin[0], afin[1]);
+    };
+    auto load = [&](int j, const float (&arec)[2], float4 (&a)[REC / 4], float4 (&b)[REC / 4]) {
       const float4* r0 = reinterpret_cast<const float4*>(rec + (j * 2 + 0) * REC);
       const float4* r1 = reinterpret_cast<const float4*>(rec + (j * 2 + 1) * REC);
+#pragma unroll
+      for (int k = 0; k < REC / 4; ++k) {
+        a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        b[k] = a[k];
+        if (arec[0] != 0.0f) a[k] = r0[k];
+        if (arec[1] != 0.0f) b[k] = r1[k];
+      }
+    };
+
+    float arec[2], afin[2];
+    float4 ra[REC / 4], rb[REC / 4];
+    coeffs(0, arec, afin);
+    load(0, arec, ra, rb);
+#pragma unroll 1
+    for (int j = 0; j < H; ++j) {
       float v0[REC], v1[REC];
 #pragma unroll
       for (int k = 0; k < REC / 4; ++k) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (arec[0] != 0.0f) a = r0[k];
-        if (arec[1] != 0.0f) b = r1[k];
-        v0[4 * k] = a.x; v0[4 * k + 1] = a.y; v0[4 * k + 2] = a.z; v0[4 * k + 3] = a.w;
-        v1[4 * k] = b.x; v1[4 * k + 1] = b.y; v1[4 * k + 2] = b.z; v1[4 * k + 3] = b.w;
+        v0[4 * k] = ra[k].x; v0[4 * k + 1] = ra[k].y; v0[4 * k + 2] = ra[k].z; v0[4 * k + 3] = ra[k].w;
+        v1[4 * k] = rb[k].x; v1[4 * k + 1] = rb[k].y; v1[4 * k + 2] = rb[k].z; v1[4 * k + 3] = rb[k].w;
+      }
+      const f2 ar = pk(arec[0], arec[1]), af = pk(afin[0], afin[1]);
+      if (j + 1 < H) {  // next unit's records: in flight during this unit's arithmetic
+        coeffs(j + 1, arec, afin);
+        load(j + 1, arec, ra, rb);
       }
       const f2 wj = bc(sm.w1t[j]);
       const f2 cj = sm.c[j][tid];
       f2 s1 = 0ull, s2 = 0ull;
-      float red[K2 + 1];
+      float red[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) red[k] = 0.0f;
 #pragma unroll
       for (int o = 0; o < K2; ++o) {
         const f2 pe = fma2(ar, pk(v0[o], v1[o]), mul2(af, P[o]));
@@ -551,46 +630,31 @@ struct Sweep {
         unpk(s2, lo, hi);
         red[K2] = lo + hi;
       }
-#pragma unroll
-      for (int k = 0; k <= K2; ++k) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
-      }
-      if (lane0) {
-#pragma unroll
-        for (int o = 0; o < K2; ++o) atomicAdd(&sm.G[o][j], red[o]);
-        atomicAdd(&sm.gw1t[j], red[K2]);
+      int slot;
+      const float tot = warp_sum_scatter<KR>(red, lane, slot);
+      // after the scatter-reduction the lanes 0, 32/KR, 2*32/KR, ... hold distinct slots; one lane per slot adds
+      if ((lane & (32 / KR - 1)) == 0 || KR == 32) {
+        if (slot < K2) atomicAdd(&sm.G[slot][j], tot);
+        else if (slot == K2) atomicAdd(&sm.gw1t[j], tot);
       }
     }
     // head biases: total of the cotangents over all evaluations
-    float tot[K2];
+    {
+      float red[KR];
 #pragma unroll
-    for (int o = 0; o < K2; ++o) {
-      float lo, hi;
-      unpk(P[o], lo, hi);
-      tot[o] = lo + hi;
+      for (int k = 0; k < KR; ++k) red[k] = 0.0f;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) tot[o] += __shfl_xor_sync(0xffffffffu, tot[o], off);
-    }
-    if (lane0) {
-#pragma unroll
-      for (int o = 0; o < K2; ++o) atomicAdd(&sm.gb[o], tot[o]);
+      for (int o = 0; o < K2; ++o) {
+        float lo, hi;
+        unpk(P[o], lo, hi);
+        red[o] = lo + hi;
+      }
+      int slot;
+      const float tot = warp_sum_scatter<KR>(red, lane, slot);
+      if (((lane & (32 / KR - 1)) == 0 || KR == 32) && slot < K2) atomicAdd(&sm.gb[slot], tot);
     }
   }
 };
-
-template <int S>
-__device__ __forceinline__ void stash_put(f2 (*st)[kBlock], int base, const Vec<S>& a) {
-#pragma unroll
-  SLODE_FOR_S st[base + s][threadIdx.x] = a.v[s];
-}
-template <int S>
-__device__ __forceinline__ Vec<S> stash_get(f2 (*st)[kBlock], int base) {
-  Vec<S> r;
-#pragma unroll
-  SLODE_FOR_S r.v[s] = st[base + s][threadIdx.x];
-  return r;
-}
 
 template <int H, int S, int METHOD, int MODE>
 __global__ void __launch_bounds__(kBlock, SLODE_BWD_MINB)
@@ -638,15 +702,16 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
 
     Sweep<H, S> sw;
     float t1 = __ldg(tgrid + T - 1);
-    Gate<H> g1, g2, g3;
     bool started = false;
-    int cur = 0;  // rk4: which half of the (A,D) double buffer holds the evaluation at t1
+    Vec<S> Ac, Dc;  // rk4: the evaluation at t1, carried over from the interval processed before
     if (METHOD == SLODE_METHOD_RK4) {
-      Vec<S> A, D;
-      mlp_eval<H, S, true, 4>(t1, cj, A, D, g1);
-      stash_put<S>(sm.stash, 0, A);
-      stash_put<S>(sm.stash, S, D);
-      sw.init(g1);
+      Vec<S> A[1], D[1];
+      Gate<H> g[1];
+      const float te[1] = {t1};
+      mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
+      Ac = A[0];
+      Dc = D[0];
+      sw.init(g[0]);
       started = true;
     }
 
@@ -664,85 +729,72 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       if (MODE == SLODE_BWD_DISCRETE) {
         const float dt = t1 - t0;
         if (METHOD == SLODE_METHOD_EULER) {
-          Vec<S> A, D;
-          mlp_eval<H, S, true, 2>(t0, cj, A, D, g1);
+          Vec<S> A[1], D[1];
+          Gate<H> g[1];
+          const float te[1] = {t0};
+          mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
           const Vec<S> gk = vscale<S>(lam, dt);
-          if (!started) { sw.init(g1); started = true; } else sw.events(rec, g1);
-          sw.add(t0, gk, x, A, D);
-          lam = vnfma<S>(gk, D, lam);
+          if (!started) { sw.init(g[0]); started = true; } else sw.events(rec, g[0]);
+          sw.add(t0, gk, x, A[0], D[0]);
+          lam = vnfma<S>(gk, D[0], lam);
         } else if (METHOD == SLODE_METHOD_MIDPOINT) {
           const float half_dt = 0.5f * dt;
-          const float tm = t0 + half_dt;
-          Vec<S> A1, D1, A2, D2;
-          mlp_eval<H, S, true, 3>(t0, cj, A1, D1, g1);
-          mlp_eval<H, S, true, 0>(after<S>(tm, A1, D1), cj, A2, D2, g2);
-          const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A1, D1, x), x);
+          Vec<S> A[2], D[2];
+          Gate<H> g[2];
+          const float te[2] = {t0, t0 + half_dt};
+          mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
+          const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A[0], D[0], x), x);
           Vec<S> gk = vscale<S>(lam, dt);  // dL/dk2
-          if (!started) { sw.init(g2); started = true; } else sw.events(rec, g2);
-          sw.add(tm, gk, ym, A2, D2);
-          const Vec<S> gy = vnmul<S>(gk, D2);  // dL/dy_mid
+          if (!started) { sw.init(g[1]); started = true; } else sw.events(rec, g[1]);
+          sw.add(te[1], gk, ym, A[1], D[1]);
+          const Vec<S> gy = vnmul<S>(gk, D[1]);  // dL/dy_mid
           lam = vadd<S>(lam, gy);
           gk = vscale<S>(gy, half_dt);  // dL/dk1
-          sw.events(rec, g1);
-          sw.add(t0, gk, x, A1, D1);
-          lam = vnfma<S>(gk, D1, lam);
-        } else {  // rk4 3/8
-          const float ta = t0 + dt * kOneThird;
-          const float tb = t0 + dt * kTwoThirds;
+          sw.events(rec, g[0]);
+          sw.add(t0, gk, x, A[0], D[0]);
+          lam = vnfma<S>(gk, D[0], lam);
+        } else {  // rk4 3/8: the three new evaluations (t0, ta, tb) are taken together
           const float dt3 = dt * kOneThird;
-          const int nxt = cur ^ 1;
-          Vec<S> A, D, k1, k2, Y3, Y4;
-          {  // stage 1 at t0: (A,D) go to the double buffer (needed last here, first in the next interval)
-            mlp_eval<H, S, true, 1>(t0, cj, A, D, g1);
-            stash_put<S>(sm.stash, 2 * S * nxt, A);
-            stash_put<S>(sm.stash, 2 * S * nxt + S, D);
-            k1 = rhs<S>(A, D, x);
-          }
-          Vec<S> A2, D2, A3, D3;
+          Vec<S> A[3], D[3];
+          Gate<H> g[3];
+          const float te[3] = {t0, t0 + dt * kOneThird, t0 + dt * kTwoThirds};
+          mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
+          Vec<S> Y2, Y3, Y4;
           {
-            const Vec<S> Y2 = vaxpy<S>(dt3, k1, x);
-            stash_put<S>(sm.stash, 4 * S, Y2);
-            mlp_eval<H, S, true, 2>(after<S>(ta, A, D), cj, A2, D2, g2);
-            k2 = rhs<S>(A2, D2, Y2);
-          }
-          Y3 = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
-          mlp_eval<H, S, true, 3>(after<S>(tb, A2, D2), cj, A3, D3, g3);
-          {
-            const Vec<S> k3 = rhs<S>(A3, D3, Y3);
+            const Vec<S> k1 = rhs<S>(A[0], D[0], x);
+            Y2 = vaxpy<S>(dt3, k1, x);
+            const Vec<S> k2 = rhs<S>(A[1], D[1], Y2);
+            Y3 = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
+            const Vec<S> k3 = rhs<S>(A[2], D[2], Y3);
             Y4 = vaxpy<S>(dt, vadd<S>(vsub<S>(k1, k2), k3), x);
           }
           const Vec<S> w = vscale<S>(lam, 0.125f * dt);
-          Vec<S> gk1, gk2, gk3, gy;
-          {  // stage 4 (time t1, evaluation carried in the double buffer): gk4 = w
-            const Vec<S> Ac = stash_get<S>(sm.stash, 2 * S * cur), Dc = stash_get<S>(sm.stash, 2 * S * cur + S);
-            sw.add(t1, w, Y4, Ac, Dc);
-            gy = vnmul<S>(w, Dc);
-          }
+          // stage 4 (time t1, carried evaluation; its gates are the sweep's current ones): gk4 = w
+          sw.add(t1, w, Y4, Ac, Dc);
+          Vec<S> gy = vnmul<S>(w, Dc);
           lam = vadd<S>(lam, gy);
-          gk1 = vaxpy<S>(dt, gy, w);
-          gk2 = vaxpy<S>(-dt, gy, vscale<S>(w, 3.0f));
-          gk3 = vaxpy<S>(dt, gy, vscale<S>(w, 3.0f));
+          Vec<S> gk1 = vaxpy<S>(dt, gy, w);
+          Vec<S> gk2 = vaxpy<S>(-dt, gy, vscale<S>(w, 3.0f));
+          const Vec<S> gk3 = vaxpy<S>(dt, gy, vscale<S>(w, 3.0f));
           // stage 3
-          sw.events(rec, g3);
-          sw.add(tb, gk3, Y3, A3, D3);
-          gy = vnmul<S>(gk3, D3);
+          sw.events(rec, g[2]);
+          sw.add(te[2], gk3, Y3, A[2], D[2]);
+          gy = vnmul<S>(gk3, D[2]);
           lam = vadd<S>(lam, gy);
           gk2 = vaxpy<S>(dt, gy, gk2);
           gk1 = vaxpy<S>(-dt3, gy, gk1);
           // stage 2
-          sw.events(rec, g2);
-          sw.add(ta, gk2, stash_get<S>(sm.stash, 4 * S), A2, D2);
-          gy = vnmul<S>(gk2, D2);
+          sw.events(rec, g[1]);
+          sw.add(te[1], gk2, Y2, A[1], D[1]);
+          gy = vnmul<S>(gk2, D[1]);
           lam = vadd<S>(lam, gy);
           gk1 = vaxpy<S>(dt3, gy, gk1);
           // stage 1 (time t0; its evaluation is the carried one of the next interval)
-          sw.events(rec, g1);
-          {
-            const Vec<S> A1 = stash_get<S>(sm.stash, 2 * S * nxt), D1 = stash_get<S>(sm.stash, 2 * S * nxt + S);
-            sw.add(t0, gk1, x, A1, D1);
-            lam = vnfma<S>(gk1, D1, lam);
-          }
-          cur = nxt;
+          sw.events(rec, g[0]);
+          sw.add(t0, gk1, x, A[0], D[0]);
+          lam = vnfma<S>(gk1, D[0], lam);
+          Ac = A[0];
+          Dc = D[0];
         }
       } else {
         // torchdiffeq.odeint_adjoint emulation: one step of the same method on the augmented system
@@ -751,63 +803,60 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         const float ds = t1 - t0;
         const Vec<S> y = vload2<S>(xs0 + (int64_t)(i + 1) * st, xs1 + (int64_t)(i + 1) * st);
         if (METHOD == SLODE_METHOD_EULER) {
-          Vec<S> A, D;
-          mlp_eval<H, S, true, 0>(t1, cj, A, D, g1);
+          Vec<S> A[1], D[1];
+          Gate<H> g[1];
+          const float te[1] = {t1};
+          mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
           const Vec<S> v = vscale<S>(lam, ds);
-          if (!started) { sw.init(g1); started = true; } else sw.events(rec, g1);
-          sw.add(t1, v, y, A, D);
-          lam = vnfma<S>(v, D, lam);
+          if (!started) { sw.init(g[0]); started = true; } else sw.events(rec, g[0]);
+          sw.add(t1, v, y, A[0], D[0]);
+          lam = vnfma<S>(v, D[0], lam);
         } else if (METHOD == SLODE_METHOD_MIDPOINT) {
           const float half = 0.5f * ds;
-          const float tm = t1 - half;
-          Vec<S> A1, D1, A2, D2;
-          mlp_eval<H, S, false, 1>(t1, cj, A1, D1, g1);
-          mlp_eval<H, S, true, 2>(after<S>(tm, A1, D1), cj, A2, D2, g2);
-          const Vec<S> ym = vaxpy<S>(-half, rhs<S>(A1, D1, y), y);   // y + half*(D1*y - A1)
-          const Vec<S> am = vaxpy<S>(-half, vmul<S>(lam, D1), lam);  // a + half*(-a*D1)
+          Vec<S> A[2], D[2];
+          Gate<H> g[2];
+          const float te[2] = {t1, t1 - half};
+          mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);  // the stage at t1 has weight 0: its gates are not used
+          const Vec<S> ym = vaxpy<S>(-half, rhs<S>(A[0], D[0], y), y);  // y + half*(D1*y - A1)
+          const Vec<S> am = vaxpy<S>(-half, vmul<S>(lam, D[0]), lam);   // a + half*(-a*D1)
           const Vec<S> v = vscale<S>(am, ds);
-          if (!started) { sw.init(g2); started = true; } else sw.events(rec, g2);
-          sw.add(tm, v, ym, A2, D2);
-          lam = vnfma<S>(v, D2, lam);
-        } else {  // rk4 3/8 on the augmented system; Ky = -f, Ka = -a*D
-          const float ta = t1 - ds * kOneThird;
-          const float tb = t1 - ds * kTwoThirds;
+          if (!started) { sw.init(g[1]); started = true; } else sw.events(rec, g[1]);
+          sw.add(te[1], v, ym, A[1], D[1]);
+          lam = vnfma<S>(v, D[1], lam);
+        } else {  // rk4 3/8 on the augmented system; Ky = -f, Ka = -a*D; new evaluations at ta, tb, t0 together
           const float w8 = 0.125f * ds;
-          const int nxt = cur ^ 1;
-          Vec<S> A, D;
-          const Vec<S> Ac = stash_get<S>(sm.stash, 2 * S * cur), Dc = stash_get<S>(sm.stash, 2 * S * cur + S);
+          Vec<S> A[3], D[3];
+          Gate<H> g[3];
+          const float te[3] = {t1 - ds * kOneThird, t1 - ds * kTwoThirds, t0};
+          mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
           // stage 1 at t1 (carried evaluation)
           const Vec<S> ky1 = vsub<S>(vmul<S>(Dc, y), Ac);
           const Vec<S> ka1 = vnmul<S>(lam, Dc);
           sw.add(t1, vscale<S>(lam, w8), y, Ac, Dc);
           // stage 2
-          mlp_eval<H, S, true, 3>(after<S>(ta, ky1, ka1), cj, A, D, g1);
           Vec<S> ym = vaxpy<S>(ds * kOneThird, ky1, y);
           Vec<S> am = vaxpy<S>(ds * kOneThird, ka1, lam);
-          const Vec<S> ky2 = vsub<S>(vmul<S>(D, ym), A);
-          const Vec<S> ka2 = vnmul<S>(am, D);
-          sw.events(rec, g1);
-          sw.add(ta, vscale<S>(am, 3.0f * w8), ym, A, D);
+          const Vec<S> ky2 = vsub<S>(vmul<S>(D[0], ym), A[0]);
+          const Vec<S> ka2 = vnmul<S>(am, D[0]);
+          sw.events(rec, g[0]);
+          sw.add(te[0], vscale<S>(am, 3.0f * w8), ym, A[0], D[0]);
           // stage 3
-          mlp_eval<H, S, true, 0>(after<S>(tb, A, D), cj, A, D, g1);
           ym = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ky1, ky2), y);
           am = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ka1, ka2), lam);
-          const Vec<S> ky3 = vsub<S>(vmul<S>(D, ym), A);
-          const Vec<S> ka3 = vnmul<S>(am, D);
-          sw.events(rec, g1);
-          sw.add(tb, vscale<S>(am, 3.0f * w8), ym, A, D);
+          const Vec<S> ky3 = vsub<S>(vmul<S>(D[1], ym), A[1]);
+          const Vec<S> ka3 = vnmul<S>(am, D[1]);
+          sw.events(rec, g[1]);
+          sw.add(te[1], vscale<S>(am, 3.0f * w8), ym, A[1], D[1]);
           // stage 4 at t0 (becomes the carried evaluation)
-          mlp_eval<H, S, true, 1>(after<S>(t0, A, D), cj, A, D, g1);
-          stash_put<S>(sm.stash, 2 * S * nxt, A);
-          stash_put<S>(sm.stash, 2 * S * nxt + S, D);
           ym = vaxpy<S>(ds, vadd<S>(vsub<S>(ky1, ky2), ky3), y);
           am = vaxpy<S>(ds, vadd<S>(vsub<S>(ka1, ka2), ka3), lam);
-          const Vec<S> ka4 = vnmul<S>(am, D);
-          sw.events(rec, g1);
-          sw.add(t0, vscale<S>(am, w8), ym, A, D);
+          const Vec<S> ka4 = vnmul<S>(am, D[2]);
+          sw.events(rec, g[2]);
+          sw.add(t0, vscale<S>(am, w8), ym, A[2], D[2]);
           const Vec<S> asum = vadd<S>(vaxpy<S>(3.0f, vadd<S>(ka2, ka3), ka1), ka4);
           lam = vaxpy<S>(w8, asum, lam);
-          cur = nxt;
+          Ac = A[2];
+          Dc = D[2];
         }
       }
       lam = vadd<S>(lam, vscale2<S>(vload2<S>(gs0 + (int64_t)i * gst, gs1 + (int64_t)i * gst), live));
