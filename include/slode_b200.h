@@ -111,6 +111,35 @@ int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
                         float* grad_y0, float* grad_c, float* grad_w,
                         void* stream);
 
+/*
+ * Adaptive Dormand-Prince 5(4) forward solve; replaces torchdiffeq.odeint(func=OdeFunc, y0, t, method="dopri5",
+ * rtol, atol) (models/blackbox_ode.py:44-45 with config.solver = "dopri5").  torchdiffeq semantics are kept:
+ * ONE step size for the whole batch (error ratio = RMS over all B*S elements), float64 controller time,
+ * Hairer initial step, FSAL, 4th-order dense output at the requested times.  The whole adaptive loop runs in one
+ * persistent cooperative kernel; the accepted-step sequence is deterministic.
+ *   t            (T) strictly increasing output times (float32)
+ *   first_step   > 0 to skip the initial-step selection (torchdiffeq options["first_step"]), else <= 0
+ *   max_attempts bound on attempted steps (torchdiffeq options["max_num_steps"])
+ *   replay_steps optional (n_replay, 3) float64 in the step_log format: take exactly these step sizes and
+ *                accept/reject decisions instead of running the controller (re-running a logged solve; parity
+ *                tests against a reference step sequence); NULL for the normal adaptive solve
+ *   ckpt_y       optional (ckpt_capacity, B, S): state at the start of every accepted step (the checkpoints the
+ *                reverse sweep needs); NULL to skip
+ *   step_log     optional (log_capacity, 3) float64: t0, dt, accepted(1/0) of every attempted step; NULL to skip
+ *   stats        device int64[4]: accepted steps, rejected steps, RHS evaluations per trajectory, status
+ *                (0 ok, 1 dt underflow, 2 max_attempts exceeded, 3 ckpt_capacity exceeded, 4 replay too short)
+ */
+int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S,
+                         const float* t, const float* c, const float* y0,
+                         const float* w1t, const float* Wg, const float* bg,
+                         const float* Wd, const float* bd,
+                         double rtol, double atol, double first_step, int64_t max_attempts,
+                         const double* replay_steps, int64_t n_replay,
+                         float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                         float* ckpt_y, int64_t ckpt_capacity,
+                         double* step_log, int64_t log_capacity,
+                         int64_t* stats, void* stream);
+
 /* element types of the CVS entry points */
 #define SLODE_F32 0
 #define SLODE_F64 1

@@ -1,0 +1,440 @@
+// Adaptive Dormand-Prince 5(4) solve of the SLODE blackbox latent ODE with torchdiffeq's BATCH-GLOBAL step
+// controller, as one persistent cooperative kernel for sm_100a.
+//
+// Reference: torchdiffeq.odeint(func, y0, t, method="dopri5", rtol, atol) as reachable from
+// models/blackbox_ode.py:44-45 (config.solver is a free string); algorithm restated in
+// oracle/torchdiffeq_oracle.py::_integrate_dopri5:
+//   * one step size for the whole (B,S) state: error ratio = rms over ALL B*S elements of err / (atol + rtol *
+//     max(|y0|,|y1|)), accept iff ratio <= 1, dt <- dt * min(10, max(0.9 / ratio^(1/5), 0.2 (1 if accepted)));
+//   * controller time and dt in float64, cast to float32 at every RHS call;
+//   * Hairer initial step (two extra batch-wide norms);
+//   * FSAL (k1 of a step is k7 of the last accepted one); outputs by the 4th-order interpolant through the
+//     DPS_C_MID midpoint, evaluated when an accepted step reaches an output time.
+//
+// Mapping.  The whole adaptive loop runs on the device: all blocks are co-resident (cooperative launch) and meet
+// at one grid barrier per attempted step, where the per-block partial sums of the squared error ratio (double)
+// are combined in a fixed order, so every thread takes the same decision and the step sequence is deterministic.
+// One thread = two trajectories (fp32x2 halves, see slode_mlp_kernels.cuh).  The five distinct stage times of an
+// attempt (the 6th and 7th stage share t1) are evaluated in ONE pass over the weights (the MLP sees only (t,z)).
+// Trajectory state lives in global scratch (y, f, and the candidate y1 / f1 / y_mid of the attempt in flight) so
+// that any batch size works; for the reference's batch sizes all of it stays in L2.
+#pragma once
+
+#include "slode_mlp_kernels.cuh"
+
+namespace slode {
+
+constexpr int kDopriStatusOk = 0, kDopriStatusUnderflow = 1, kDopriStatusMaxSteps = 2, kDopriStatusCkptFull = 3,
+              kDopriStatusReplayShort = 4;
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(counter, 1ull);
+    const unsigned long long target = (ticket / gridDim.x + 1ull) * gridDim.x;
+    while (*reinterpret_cast<volatile unsigned long long*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// block partial sums of NV doubles -> partial[(buf*3 + v) * grid + block]
+template <int NV>
+__device__ __forceinline__ void block_partials(double (&v)[NV], double* partial, int buf, double* sm_red) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sm_red[warp * 3 + k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int w = 0; w < kBlock / 32; ++w) s += sm_red[w * 3 + k];
+      partial[((size_t)buf * 3 + k) * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
+// after the grid barrier: every block sums the per-block partials in the same fixed order
+template <int NV>
+__device__ __forceinline__ void grid_totals(double (&tot)[NV], const double* partial, int buf, double* sm_red) {
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += 32)
+        s += *reinterpret_cast<const volatile double*>(&partial[((size_t)buf * 3 + k) * gridDim.x + b]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (threadIdx.x == 0) sm_red[16 + k] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) tot[k] = sm_red[16 + k];
+  __syncthreads();
+}
+
+template <int S> __device__ __forceinline__ Vec<S> vabs(const Vec<S>& a) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = a.v[s] & 0x7fffffff7fffffffull;
+  return r;
+}
+template <int S> __device__ __forceinline__ void vload_rows(const float* base, const PairIdx& pi, Vec<S>& out) {
+  out = vload2<S>(base + pi.b0 * S, base + pi.b1 * S);
+}
+template <int S> __device__ __forceinline__ void vstore_rows(float* base, const PairIdx& pi, const Vec<S>& a) {
+  vstore2<S>(base + pi.b0 * S, pi.ok0, base + pi.b1 * S, pi.ok1, a);
+}
+// sum over both trajectories and all S components of (a/b)^2, masked by validity
+template <int S> __device__ __forceinline__ double sumsq_ratio(const Vec<S>& a, const Vec<S>& b, const PairIdx& pi) {
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+  SLODE_FOR_S {
+    float a0, a1, b0, b1;
+    unpk(a.v[s], a0, a1);
+    unpk(b.v[s], b0, b1);
+    const float r0 = __fdiv_rn(a0, b0), r1 = __fdiv_rn(a1, b1);
+    s0 = fmaf(r0, r0, s0);
+    s1 = fmaf(r1, r1, s1);
+  }
+  return (pi.ok0 ? (double)s0 : 0.0) + (pi.ok1 ? (double)s1 : 0.0);
+}
+
+// Dormand-Prince tableau (torchdiffeq _DORMAND_PRINCE_SHAMPINE_TABLEAU)
+__device__ constexpr float kDpAlpha[5] = {(float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), 1.0f};
+__device__ constexpr float kDpBeta[6][6] = {
+    {(float)(1.0 / 5), 0, 0, 0, 0, 0},
+    {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},
+    {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},
+    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
+    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656), 0},
+    {(float)(35.0 / 384), 0, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84)},
+};
+__device__ constexpr float kDpCErr[7] = {
+    (float)(35.0 / 384 - 1951.0 / 21600), 0.0f, (float)(500.0 / 1113 - 22642.0 / 50085),
+    (float)(125.0 / 192 - 451.0 / 720), (float)(-2187.0 / 6784 - -12231.0 / 42400),
+    (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60.0)};
+__device__ constexpr float kDpCMid[7] = {
+    (float)(6025192743.0 / 30085553152.0 / 2), 0.0f, (float)(51252292925.0 / 65400821598.0 / 2),
+    (float)(-2691868925.0 / 45128329728.0 / 2), (float)(187940372067.0 / 1594534317056.0 / 2),
+    (float)(-1776094331.0 / 19743644256.0 / 2), (float)(11237099.0 / 235043384.0 / 2)};
+
+// y0 + sum_j k[j] * (coef[j] * dt)   (torchdiffeq: kk.matmul(coef * dt), fp32)
+template <int S, int N>
+__device__ __forceinline__ Vec<S> combine(const Vec<S>& y0, const Vec<S> (&k)[7], const float* coef, float dt) {
+  Vec<S> acc;
+  bool first = true;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    if (coef[j] != 0.0f) {
+      const f2 cj = bc(__fmul_rn(coef[j], dt));
+#pragma unroll
+      SLODE_FOR_S acc.v[s] = first ? mul2(k[j].v[s], cj) : fma2(k[j].v[s], cj, acc.v[s]);
+      first = false;
+    }
+  }
+  return vadd<S>(y0, acc);
+}
+
+template <int H, int S>
+__global__ void __launch_bounds__(kBlock, 1)
+dopri5_fwd_kernel(Dopri5Args p) {
+  __shared__ double sm_red[32];
+  const int64_t ntiles = ((p.B + 1) / 2 + kBlock - 1) / kBlock;
+  const double nelem = (double)p.B * S;
+  const f2 rtol2 = bc(p.rtol), atol2 = bc(p.atol);
+
+  auto cload = [&](const PairIdx& pi) {
+    return [=](int j) { return pk(__ldg(p.c + pi.b0 * H + j), __ldg(p.c + pi.b1 * H + j)); };
+  };
+
+  // ---- f0 = func(t[0], y0); sol[0] = y0; norms d0, d1 of Hairer's initial step ---------------------------
+  const double t_start = (double)__ldg(p.t);
+  {
+    double part[2] = {0.0, 0.0};
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const PairIdx pi = pair_index(tile, p.B);
+      Vec<S> y, A[1], D[1];
+      Gate<H> ng[1];
+      vload_rows<S>(p.y0, pi, y);
+      const float te[1] = {(float)t_start};
+      mlp_eval<H, S, 1, false, 0>(te, cload(pi), A, D, ng);
+      const Vec<S> f = rhs<S>(A[0], D[0], y);
+      vstore_rows<S>(p.ys, pi, y);
+      vstore_rows<S>(p.fs, pi, f);
+      vstore2<S>(p.sol + pi.b0 * p.sb, pi.ok0, p.sol + pi.b1 * p.sb, pi.ok1, y);
+      Vec<S> scale;
+      const Vec<S> ay = vabs<S>(y);
+#pragma unroll
+      SLODE_FOR_S scale.v[s] = fma2(ay.v[s], rtol2, atol2);
+      part[0] += sumsq_ratio<S>(y, scale, pi);
+      part[1] += sumsq_ratio<S>(f, scale, pi);
+    }
+    block_partials<2>(part, p.partial, 0, sm_red);
+  }
+  grid_barrier(p.barrier);
+  double dt;
+  int64_t n_rhs = 1;
+  if (p.T < 2) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      p.stats[0] = 0; p.stats[1] = 0; p.stats[2] = n_rhs; p.stats[3] = kDopriStatusOk;
+    }
+    return;
+  }
+  if (p.replay) {
+    dt = p.n_replay > 0 ? p.replay[1] : 0.0;
+  } else if (p.first_step > 0.0) {
+    dt = p.first_step;
+  } else {
+    double tot[2];
+    grid_totals<2>(tot, p.partial, 0, sm_red);
+    const float d0 = sqrtf((float)(tot[0] / nelem)), d1 = sqrtf((float)(tot[1] / nelem));
+    const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : __fdiv_rn(__fmul_rn(0.01f, d0), d1);
+    double part[1] = {0.0};
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const PairIdx pi = pair_index(tile, p.B);
+      Vec<S> y, f, A[1], D[1];
+      Gate<H> ng[1];
+      vload_rows<S>(p.ys, pi, y);
+      vload_rows<S>(p.fs, pi, f);
+      const float te[1] = {__fadd_rn((float)t_start, h0)};
+      mlp_eval<H, S, 1, false, 1>(te, cload(pi), A, D, ng);
+      const Vec<S> y1 = vaxpy<S>(h0, f, y);
+      const Vec<S> f1 = rhs<S>(A[0], D[0], y1);
+      Vec<S> scale;
+      const Vec<S> ay = vabs<S>(y);
+#pragma unroll
+      SLODE_FOR_S scale.v[s] = fma2(ay.v[s], rtol2, atol2);
+      part[0] += sumsq_ratio<S>(vsub<S>(f1, f), scale, pi);
+    }
+    block_partials<1>(part, p.partial, 1, sm_red);
+    grid_barrier(p.barrier);
+    double tot2[1];
+    grid_totals<1>(tot2, p.partial, 1, sm_red);
+    n_rhs += 1;
+    const float d2 = __fdiv_rn(sqrtf((float)(tot2[0] / nelem)), h0);
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, __fmul_rn(h0, 1e-3f));
+    else h1 = powf(__fdiv_rn(0.01f, fmaxf(d1, d2)), 1.0f / 5.0f);
+    dt = (double)fminf(__fmul_rn(100.0f, h0), h1);
+  }
+
+  // ---- adaptive loop ---------------------------------------------------------------------------------------
+  double t_cur = t_start;           // end time of the last accepted step
+  int out_idx = 1;                  // next output time to produce
+  int64_t attempt = 0, n_acc = 0, n_rej = 0;
+  int status = kDopriStatusOk;
+  bool prev_acc = false;            // the previous attempt was accepted and still has to be committed
+  double pv_t0 = 0.0, pv_t1 = 0.0, pv_dt = 0.0;
+  int emit_lo = 0, emit_hi = 0;
+  int buf = 0;
+
+  // commit an accepted step for one trajectory pair: interpolated outputs, checkpoint, state <- candidate
+  auto commit = [&](const PairIdx& pi, Vec<S>& y, Vec<S>& f) {
+    Vec<S> y1, f1, ym;
+    vload_rows<S>(p.cy1, pi, y1);
+    vload_rows<S>(p.cf1, pi, f1);
+    vload_rows<S>(p.cym, pi, ym);
+    if (p.ckpt_y) vstore_rows<S>(p.ckpt_y + (size_t)(n_acc - 1) * p.B * S, pi, y);
+    if (emit_hi > emit_lo) {
+      const float dtf = (float)pv_dt;
+      const f2 d2 = bc(dtf);
+      Vec<S> ca, cb, cc, cd;
+#pragma unroll
+      SLODE_FOR_S {
+        const f2 df = sub2(f1.v[s], f.v[s]);
+        const f2 sy = add2(y1.v[s], y.v[s]);
+        // a = 2 dt (f1 - f0) - 8 (y1 + y0) + 16 y_mid
+        ca.v[s] = add2(sub2(mul2(mul2(bc(2.0f), d2), df), mul2(bc(8.0f), sy)), mul2(bc(16.0f), ym.v[s]));
+        // b = dt (5 f0 - 3 f1) + 18 y0 + 14 y1 - 32 y_mid
+        cb.v[s] = sub2(add2(add2(mul2(d2, sub2(mul2(bc(5.0f), f.v[s]), mul2(bc(3.0f), f1.v[s]))), mul2(bc(18.0f), y.v[s])),
+                            mul2(bc(14.0f), y1.v[s])), mul2(bc(32.0f), ym.v[s]));
+        // c = dt (f1 - 4 f0) - 11 y0 - 5 y1 + 16 y_mid
+        cc.v[s] = add2(sub2(sub2(mul2(d2, sub2(f1.v[s], mul2(bc(4.0f), f.v[s]))), mul2(bc(11.0f), y.v[s])),
+                            mul2(bc(5.0f), y1.v[s])), mul2(bc(16.0f), ym.v[s]));
+        cd.v[s] = mul2(d2, f.v[s]);
+      }
+      const float ft0 = (float)pv_t0, ft1 = (float)pv_t1;
+      for (int i = emit_lo; i < emit_hi; ++i) {
+        const float x = __fdiv_rn(__fsub_rn(__ldg(p.t + i), ft0), __fsub_rn(ft1, ft0));
+        const f2 x1 = bc(x);
+        Vec<S> o;
+#pragma unroll
+        SLODE_FOR_S {
+          f2 tot = fma2(x1, cd.v[s], y.v[s]);
+          f2 xp = mul2(x1, x1);
+          tot = fma2(xp, cc.v[s], tot);
+          xp = mul2(xp, x1);
+          tot = fma2(xp, cb.v[s], tot);
+          xp = mul2(xp, x1);
+          tot = fma2(xp, ca.v[s], tot);
+          o.v[s] = tot;
+        }
+        vstore2<S>(p.sol + (int64_t)i * p.st + pi.b0 * p.sb, pi.ok0, p.sol + (int64_t)i * p.st + pi.b1 * p.sb, pi.ok1, o);
+      }
+    }
+    y = y1;
+    f = f1;
+    vstore_rows<S>(p.ys, pi, y);
+    vstore_rows<S>(p.fs, pi, f);
+  };
+
+  while (out_idx < p.T) {
+    if (attempt >= p.max_attempts) { status = kDopriStatusMaxSteps; break; }
+    if (p.replay) {  // prescribed step sequence (tests / replaying a logged solve): dt and the decision are given
+      if (attempt >= p.n_replay) { status = kDopriStatusReplayShort; break; }
+      dt = p.replay[attempt * 3 + 1];
+    }
+    const double a_t0 = t_cur, a_dt = dt, a_t1 = a_t0 + a_dt;
+    if (!(a_t1 > a_t0)) { status = kDopriStatusUnderflow; break; }
+    if (p.ckpt_y && n_acc >= p.ckpt_cap) { status = kDopriStatusCkptFull; break; }
+    const float ft0 = (float)a_t0, fdt = (float)a_dt, ft1 = (float)a_t1;
+    float te[5];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) te[e] = __fadd_rn(ft0, __fmul_rn(kDpAlpha[e], fdt));
+    te[4] = ft1;
+
+    double part[1] = {0.0};
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const PairIdx pi = pair_index(tile, p.B);
+      Vec<S> y, k[7];
+      vload_rows<S>(p.ys, pi, y);
+      vload_rows<S>(p.fs, pi, k[0]);
+      if (prev_acc) commit(pi, y, k[0]);
+      Vec<S> A[5], D[5];
+      Gate<H> ng[5];
+      mlp_eval<H, S, 5, false, 0>(te, cload(pi), A, D, ng);
+      Vec<S> yi;
+      yi = combine<S, 1>(y, k, kDpBeta[0], fdt); k[1] = rhs<S>(A[0], D[0], yi);
+      yi = combine<S, 2>(y, k, kDpBeta[1], fdt); k[2] = rhs<S>(A[1], D[1], yi);
+      yi = combine<S, 3>(y, k, kDpBeta[2], fdt); k[3] = rhs<S>(A[2], D[2], yi);
+      yi = combine<S, 4>(y, k, kDpBeta[3], fdt); k[4] = rhs<S>(A[3], D[3], yi);
+      yi = combine<S, 5>(y, k, kDpBeta[4], fdt); k[5] = rhs<S>(A[4], D[4], yi);
+      const Vec<S> y1 = combine<S, 6>(y, k, kDpBeta[5], fdt);
+      k[6] = rhs<S>(A[4], D[4], y1);
+      // error estimate and tolerance
+      Vec<S> err, tol;
+      {
+        Vec<S> zero;
+#pragma unroll
+        SLODE_FOR_S zero.v[s] = 0ull;
+        err = combine<S, 7>(zero, k, kDpCErr, fdt);
+        const Vec<S> a0 = vabs<S>(y), a1 = vabs<S>(y1);
+#pragma unroll
+        SLODE_FOR_S {
+          float p0, p1, q0, q1;
+          unpk(a0.v[s], p0, p1);
+          unpk(a1.v[s], q0, q1);
+          tol.v[s] = fma2(pk(fmaxf(p0, q0), fmaxf(p1, q1)), rtol2, atol2);
+        }
+      }
+      part[0] += sumsq_ratio<S>(err, tol, pi);
+      vstore_rows<S>(p.cy1, pi, y1);
+      vstore_rows<S>(p.cf1, pi, k[6]);
+      vstore_rows<S>(p.cym, pi, combine<S, 7>(y, k, kDpCMid, fdt));
+    }
+    block_partials<1>(part, p.partial, buf, sm_red);
+    grid_barrier(p.barrier);
+    double tot[1];
+    grid_totals<1>(tot, p.partial, buf, sm_red);
+    buf ^= 1;
+    n_rhs += 6;
+    const float ratio = sqrtf((float)(tot[0] / nelem));
+    const bool accept = p.replay ? (p.replay[attempt * 3 + 2] != 0.0) : (ratio <= 1.0f);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.step_log && attempt < p.log_cap) {
+      p.step_log[attempt * 3 + 0] = a_t0;
+      p.step_log[attempt * 3 + 1] = a_dt;
+      p.step_log[attempt * 3 + 2] = accept ? 1.0 : 0.0;
+    }
+    ++attempt;
+    if (accept) {
+      ++n_acc;
+      pv_t0 = a_t0; pv_t1 = a_t1; pv_dt = a_dt;
+      t_cur = a_t1;
+      emit_lo = out_idx;
+      while (out_idx < p.T && (double)__ldg(p.t + out_idx) <= a_t1) ++out_idx;
+      emit_hi = out_idx;
+    } else {
+      ++n_rej;
+    }
+    prev_acc = accept;
+    // torchdiffeq _optimal_step_size (float64)
+    {
+      double factor;
+      if (ratio == 0.0f) {
+        factor = 10.0;
+      } else {
+        const double dfac = (ratio < 1.0f) ? 1.0 : 0.2;
+        factor = fmin(10.0, fmax(0.9 / pow((double)ratio, 0.2), dfac));
+      }
+      dt = a_dt * factor;
+    }
+  }
+  // commit the last accepted step
+  if (prev_acc) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const PairIdx pi = pair_index(tile, p.B);
+      Vec<S> y, f;
+      vload_rows<S>(p.ys, pi, y);
+      vload_rows<S>(p.fs, pi, f);
+      commit(pi, y, f);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.stats[0] = n_acc; p.stats[1] = n_rej; p.stats[2] = n_rhs; p.stats[3] = status;
+  }
+}
+
+template <int H, int S>
+int launch_dopri5_fwd(Dopri5Args a, const PackSrc& w, float* staging, cudaStream_t stream, int sms) {
+  int rc = upload_pack<H, S>(w, staging, stream);
+  if (rc) return rc;
+  auto kern = dopri5_fwd_kernel<H, S>;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    int n = 0;
+    SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, 0));
+    blocks_per_sm = std::max(n, 1);
+  }
+  const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * blocks_per_sm);
+  // scratch: 5 state arrays, partial sums, barrier counter
+  const size_t nstate = (size_t)a.B * S;
+  const size_t bytes = sizeof(float) * 5 * nstate + 256 + sizeof(double) * 6 * (size_t)grid + 256;
+  char* ws = reinterpret_cast<char*>(flip_workspace(bytes));
+  if (!ws) return SLODE_ECUDA;
+  a.ys = reinterpret_cast<float*>(ws);
+  a.fs = a.ys + nstate;
+  a.cy1 = a.fs + nstate;
+  a.cf1 = a.cy1 + nstate;
+  a.cym = a.cf1 + nstate;
+  size_t off = (sizeof(float) * 5 * nstate + 255) / 256 * 256;
+  a.partial = reinterpret_cast<double*>(ws + off);
+  off += (sizeof(double) * 6 * (size_t)grid + 255) / 256 * 256;
+  a.barrier = reinterpret_cast<unsigned long long*>(ws + off);
+  SLODE_CUDA_TRY(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned long long), stream));
+  void* args[] = {&a};
+  SLODE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kBlock), args, 0, stream));
+  return SLODE_OK;
+}
+
+}  // namespace slode
+
+#define SLODE_DEFINE_DOPRI5(H, S)                                                                       \
+  namespace slode {                                                                                     \
+  int dopri5_fwd_##H##_##S(const Dopri5Args& a, const PackSrc& w, float* staging, cudaStream_t stream,  \
+                           int sms) {                                                                   \
+    return launch_dopri5_fwd<H, S>(a, w, staging, stream, sms);                                         \
+  }                                                                                                     \
+  }

@@ -11,9 +11,10 @@ struct ShapeEntry {
   int H, S;
   mlp_fwd_fn fwd;
   mlp_bwd_fn bwd;
+  dopri5_fwd_fn dopri5_fwd;
 };
 static const ShapeEntry kShapes[] = {
-#define X(h, s) {h, s, mlp_fwd_##h##_##s, mlp_bwd_##h##_##s},
+#define X(h, s) {h, s, mlp_fwd_##h##_##s, mlp_bwd_##h##_##s, dopri5_fwd_##h##_##s},
     SLODE_SHAPES(X)
 #undef X
 };
@@ -124,5 +125,42 @@ extern "C" int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->bwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_bwd_launches = 2;
+  return rc;
+}
+
+extern "C" int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S, const float* t, const float* c, const float* y0,
+                                    const float* w1t, const float* Wg, const float* bg, const float* Wd,
+                                    const float* bd, double rtol, double atol, double first_step,
+                                    int64_t max_attempts, const double* replay_steps, int64_t n_replay, float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                                    float* ckpt_y, int64_t ckpt_capacity, double* step_log, int64_t log_capacity,
+                                    int64_t* stats, void* stream_) {
+  int rc = check_common("slode_mlp_dopri5_fwd", B, T, H, S);
+  if (rc) return rc;
+  if (!(rtol >= 0.0) || !(atol >= 0.0) || (rtol == 0.0 && atol == 0.0) || max_attempts < 1 || ckpt_capacity < 0 ||
+      log_capacity < 0) {
+    set_error("slode_mlp_dopri5_fwd: bad tolerances / capacities (rtol=%g atol=%g max_attempts=%lld)", rtol, atol,
+              (long long)max_attempts);
+    return SLODE_EINVAL;
+  }
+  if (!t || !w1t || !Wg || !bg || !Wd || !bd || !stats || (B > 0 && (!c || !y0 || !sol))) {
+    set_error("slode_mlp_dopri5_fwd: null pointer");
+    return SLODE_EINVAL;
+  }
+  g_fwd_launches = 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (B == 0) {
+    if (cudaMemsetAsync(stats, 0, 4 * sizeof(int64_t), stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "memset");
+    return SLODE_OK;
+  }
+  PackGuard guard(stream);
+  if (guard.status) return guard.status;
+  Dopri5Args a{};
+  a.B = B; a.T = T; a.t = t; a.c = c; a.y0 = y0; a.sol = sol; a.st = sol_stride_t; a.sb = sol_stride_b;
+  a.rtol = (float)rtol; a.atol = (float)atol; a.first_step = first_step; a.max_attempts = max_attempts;
+  a.replay = replay_steps; a.n_replay = replay_steps ? n_replay : 0;
+  a.ckpt_y = ckpt_y; a.ckpt_cap = ckpt_capacity; a.step_log = step_log; a.log_cap = log_capacity; a.stats = stats;
+  const PackSrc w{w1t, Wg, bg, Wd, bd};
+  rc = find_shape(H, S)->dopri5_fwd(a, w, guard.staging, stream, guard.sms);
+  if (rc == SLODE_OK) g_fwd_launches = 2;
   return rc;
 }

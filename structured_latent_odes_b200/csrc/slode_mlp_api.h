@@ -35,15 +35,41 @@ struct BwdArgs {
   int sms;
 };
 
+// dopri5 forward (slode_dopri5_kernels.cuh); scratch pointers are filled in by the launcher
+struct Dopri5Args {
+  int64_t B;
+  int T;
+  const float *t, *c, *y0;
+  float* sol;
+  int64_t st, sb;
+  float rtol, atol;
+  double first_step;      // <= 0: Hairer's selection
+  const double* replay;   // optional (n_replay,3) prescribed (t0, dt, accepted) sequence
+  int64_t n_replay;
+  int64_t max_attempts;
+  // scratch (library-owned)
+  float *ys, *fs, *cy1, *cf1, *cym;    // (B,S) each
+  double* partial;                      // [2][3][grid]
+  unsigned long long* barrier;          // monotonic arrival counter (zeroed before the launch)
+  // optional outputs
+  float* ckpt_y;        // (ckpt_cap, B, S): state at the start of every accepted step (for the reverse sweep)
+  int64_t ckpt_cap;
+  double* step_log;     // (log_cap, 3): t0, dt, accepted(1/0) of every attempted step
+  int64_t log_cap;
+  int64_t* stats;       // [0] accepted, [1] rejected, [2] RHS evaluations per trajectory, [3] status (0 ok)
+};
+
 typedef int (*mlp_fwd_fn)(const FwdArgs&, const PackSrc&, float* staging);
 typedef int (*mlp_bwd_fn)(const BwdArgs&, const PackSrc&, float* staging);
+typedef int (*dopri5_fwd_fn)(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 
 // (25,5): CVS / challenge configs; (25,8): proc config; the rest serve tests and the width sweep.
 #define SLODE_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5)
 
 #define SLODE_DECLARE_SHAPE(H, S)                                         \
   int mlp_fwd_##H##_##S(const FwdArgs&, const PackSrc&, float* staging);  \
-  int mlp_bwd_##H##_##S(const BwdArgs&, const PackSrc&, float* staging);
+  int mlp_bwd_##H##_##S(const BwdArgs&, const PackSrc&, float* staging);  \
+  int dopri5_fwd_##H##_##S(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 SLODE_SHAPES(SLODE_DECLARE_SHAPE)
 #undef SLODE_DECLARE_SHAPE
 

@@ -210,6 +210,69 @@ class _MlpFixedSolve(torch.autograd.Function):
         return grad_y0, grad_c, gw1t, gWg, gbg, gWd, gbd, None, None, None, None
 
 
+class SolverStats:
+    """Bookkeeping of the last dopri5 solve on this process (``last_dopri5_stats``): accepted / rejected step
+    counts, RHS evaluations per trajectory, and -- when ``options={"log_steps": True}`` -- the (t0, dt, accepted)
+    record of every attempted step as a float64 CPU tensor."""
+
+    def __init__(self):
+        self.n_accept = self.n_reject = self.n_rhs = 0
+        self.steps = None
+
+
+last_dopri5_stats = SolverStats()
+_DOPRI5_STATUS = {1: "underflow in dt", 2: "max_num_steps exceeded", 3: "checkpoint capacity exceeded",
+                  4: "replay_steps ended before the last output time"}
+
+
+def _dopri5_forward(y0, c, w, t, rtol, atol, options, layout, want_ckpt):
+    """Runs slode_mlp_dopri5_fwd; returns (sol, ckpt or None, steps (n,3) float64 device tensor or None)."""
+    opts = dict(options or {})
+    first_step = opts.pop("first_step", None)
+    max_num_steps = int(opts.pop("max_num_steps", 1 << 20))
+    log_steps = bool(opts.pop("log_steps", False)) or want_ckpt
+    replay = opts.pop("replay_steps", None)
+    if replay is not None:
+        replay = torch.as_tensor(replay, dtype=torch.float64).reshape(-1, 3).to(y0.device).contiguous()
+    if opts:
+        raise NotImplementedError(f"dopri5 options {sorted(opts)} are not supported (supported: first_step, "
+                                  "max_num_steps, log_steps, replay_steps)")
+    B, S = y0.shape
+    H = c.shape[1]
+    T = t.numel()
+    dev = y0.device
+    if layout == "bts":
+        sol = torch.empty((B, T, S), device=dev, dtype=torch.float32).permute(1, 0, 2)
+    else:
+        sol = torch.empty((T, B, S), device=dev, dtype=torch.float32)
+    stats = torch.zeros(4, device=dev, dtype=torch.int64)
+    cap = 64 if want_ckpt else 0
+    log_cap = 4096 if log_steps else 0
+    while True:
+        ckpt = torch.empty((cap, B, S), device=dev, dtype=torch.float32) if cap else None
+        log = torch.zeros((log_cap, 3), device=dev, dtype=torch.float64) if log_cap else None
+        with torch.cuda.device(dev), _timed("fwd"):
+            rc = _cabi.lib().slode_mlp_dopri5_fwd(
+                B, T, H, S, _ptr(t), _ptr(c), _ptr(y0), *[_ptr(x) for x in w], float(rtol), float(atol),
+                float(first_step) if first_step is not None else -1.0, max_num_steps, _ptr(replay),
+                replay.shape[0] if replay is not None else 0, _ptr(sol), sol.stride(0),
+                sol.stride(1), _ptr(ckpt), cap, _ptr(log), log_cap, _ptr(stats),
+                torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_mlp_dopri5_fwd")
+        n_acc, n_rej, n_rhs, status = (int(v) for v in stats.tolist())  # the adaptive loop has to finish anyway
+        if status == 3 or (log_cap and n_acc + n_rej > log_cap):
+            cap = max(2 * cap, 64) if want_ckpt else 0
+            log_cap = max(2 * log_cap, n_acc + n_rej) if log_cap else 0
+            continue  # deterministic step sequence: the re-run reproduces the same steps with room for all of them
+        if status != 0:
+            raise _cabi.SlodeError(f"dopri5: {_DOPRI5_STATUS.get(status, status)} after {n_acc + n_rej} attempted steps")
+        break
+    last_dopri5_stats.n_accept, last_dopri5_stats.n_reject, last_dopri5_stats.n_rhs = n_acc, n_rej, n_rhs
+    steps = log[: n_acc + n_rej] if log is not None else None
+    last_dopri5_stats.steps = steps.cpu() if steps is not None else None
+    return sol, (ckpt[:n_acc] if ckpt is not None else None), steps
+
+
 def _solve_blackbox(func, y0, t, method, mode, layout):
     z, hid, gro, deg = _check_blackbox(func)
     B, S = y0.shape
@@ -233,6 +296,30 @@ def _solve_blackbox(func, y0, t, method, mode, layout):
                                 _cabi.METHODS[method], mode, layout)
 
 
+def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
+    z, hid, gro, deg = _check_blackbox(func)
+    B, S = y0.shape
+    if z.shape[0] != B:
+        raise ValueError(f"constants batch {z.shape[0]} != y0 batch {B}")
+    H = hid.out_features
+    if gro.out_features != S or not _cabi.lib().slode_mlp_supported(H, S):
+        raise NotImplementedError(f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled kernel; available: "
+                                  f"{_cabi.supported_shapes()}")
+    if t.numel() > 1 and bool(t[0] > t[-1]):
+        raise NotImplementedError("dopri5 with decreasing output times (the reference always integrates forward)")
+    needs_grad = torch.is_grad_enabled() and (y0.requires_grad or z.requires_grad
+                                              or any(p.requires_grad for p in func.parameters()))
+    if needs_grad:
+        raise NotImplementedError(
+            "reverse-mode gradient through dopri5 is not built yet: run under torch.no_grad() (evaluation / "
+            "multiple_samples), or train with a fixed-grid solver as every shipped config does")
+    W1 = hid.weight.detach()
+    c = torch.addmm(hid.bias.detach(), z.detach().to(torch.float32), W1[:, 1:].t()).contiguous()
+    w = [x.detach().contiguous() for x in (W1[:, 0], gro.weight, gro.bias, deg.weight, deg.bias)]
+    sol, _, _ = _dopri5_forward(y0.detach().contiguous(), c, w, t, rtol, atol, options, layout, want_ckpt=False)
+    return sol
+
+
 # ----------------------------------------------------------------------------------------------
 # public API
 # ----------------------------------------------------------------------------------------------
@@ -247,7 +334,7 @@ def _solve(func, y0, t, rtol, atol, method, options, event_fn, mode, layout):
         return _cvs.solve_cvs(func, y0, t, method, mode, layout, options)
     if is_blackbox_func(func):
         if method == "dopri5":
-            raise NotImplementedError("dopri5 for the blackbox dynamics is not built yet")
+            return _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout)
         return _solve_blackbox(func, y0, t, method, mode, layout)
     raise NotImplementedError(
         f"func of type {type(func).__name__} has no fused kernel; supported: OdeFunc over Dynamics "

@@ -1,0 +1,161 @@
+"""dopri5 with torchdiffeq's batch-global controller: identical accept/reject sequence, step sizes and trajectories
+against the oracle (``oracle/torchdiffeq_oracle.py``) and the committed golden fixture produced by the reference's
+real classes (``tests/golden/blackbox_golden.npz``, case ``chal``)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import slode_testutil as U
+from oracle import slode_port
+from oracle import torchdiffeq_oracle as tde
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(shape, seed=12):
+    o = U.make_oracle(shape, "dopri5", False, seed=seed)
+    p = U.make_product(o)
+    return o, p
+
+
+def _run(o, p, z, rtol, atol, options=None, replay=None):
+    import structured_latent_odes_b200 as slode
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    with torch.no_grad():
+        want = tde.odeint(slode_port.OdeFunc(z, o.dynamics), o.latent_to_ode_net(z), o.times, method="dopri5",
+                          rtol=rtol, atol=atol, options=options)
+        acc_o, dts_o, nrhs_o = list(tde.last_stats.accepted), list(tde.last_stats.dts), tde.last_stats.n_rhs
+        zc = z.cuda()
+        opts = dict(options or {})
+        opts["log_steps"] = True
+        if replay is not None:
+            opts["replay_steps"] = replay
+        got = slode.odeint(p.gen_dynamics(zc), p.initialize_state(zc), p.times, method="dopri5", rtol=rtol, atol=atol,
+                           options=opts)
+    st = api.last_dopri5_stats
+    return want, got, acc_o, dts_o, nrhs_o, st
+
+
+def _oracle_steps(acc, dts, t0):
+    """the oracle's (accepted, dt) lists in the step_log format (t0 column is informational)"""
+    rows, t = [], float(t0)
+    for a, d in zip(acc, dts):
+        rows.append((t, d, 1.0 if a else 0.0))
+        if a:
+            t = t + d
+    return torch.tensor(rows, dtype=torch.float64)
+
+
+@pytest.mark.parametrize("shape,B,rtol,atol", [("cvs", 8, 1e-5, 1e-6), ("chal", 35, 1e-5, 1e-6), ("proc", 78, 1e-4, 1e-5),
+                                               ("small", 300, 1e-6, 1e-7), ("cvs", 1, 1e-5, 1e-6)])
+def test_replaying_the_oracle_step_sequence_gives_the_oracle_trajectories(shape, B, rtol, atol):
+    """Stage arithmetic, FSAL, float64 time keeping and the dense output: with the oracle's own accept/reject
+    decisions and step sizes prescribed, trajectories agree to fp32 rounding (1e-5)."""
+    o, p = _pair(shape)
+    L = U.SHAPES[shape][0]
+    z = torch.randn(B, L, generator=torch.Generator().manual_seed(5))
+    want, got_free, acc_o, dts_o, nrhs_o, st = _run(o, p, z, rtol, atol)
+    # Hairer's initial step: two batch-wide norms and one extra RHS evaluation, bit-for-bit the oracle's value
+    assert st.steps[0, 1].item() == pytest.approx(dts_o[0], rel=1e-6)
+    # free-running controller: the fp32 error estimate is rounding-noise dominated at these tolerances (err ~1e-10
+    # against terms ~1e-3), so step sizes drift apart; the solutions still agree to a few rtol
+    assert U.rel_err(got_free, want) < 20 * rtol
+    _, got, _, _, _, st2 = _run(o, p, z, rtol, atol, options=None, replay=_oracle_steps(acc_o, dts_o, o.times[0]))
+    assert [bool(a) for a in st2.steps[:, 2]] == acc_o
+    assert np.array_equal(st2.steps[:, 1].numpy(), np.array(dts_o))
+    assert st2.n_accept == sum(acc_o) and st2.n_reject == len(acc_o) - sum(acc_o)
+    assert U.rel_err(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("shape,B", [("cvs", 64), ("proc", 78)])
+def test_controller_matches_the_oracle_where_the_error_estimate_is_above_rounding(shape, B):
+    """At rtol=1e-3 / atol=1e-4 the embedded error estimate (~1e-4) is far above fp32 rounding (~1e-9): the
+    batch-global controller must then reproduce the oracle's accept/reject sequence and step sizes."""
+    o, p = _pair(shape)
+    L = U.SHAPES[shape][0]
+    z = torch.randn(B, L, generator=torch.Generator().manual_seed(6))
+    want, got, acc_o, dts_o, nrhs_o, st = _run(o, p, z, 1e-3, 1e-4)
+    steps = st.steps.numpy()
+    assert steps.shape[0] == len(acc_o)
+    assert [bool(a) for a in steps[:, 2]] == acc_o
+    assert np.allclose(steps[:, 1], np.array(dts_o), rtol=5e-3)
+    assert st.n_rhs == nrhs_o
+    assert U.rel_err(got, want) < 1e-4
+
+
+def test_golden_fixture_from_reference_classes(golden_dir):
+    """tests/golden/blackbox_golden.npz case ``chal``: dopri5 output of the reference's REAL OdeModel / OdeFunc /
+    Dynamics classes with its logged step sequence."""
+    import structured_latent_odes_b200 as slode
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    g = np.load(os.path.join(golden_dir, "blackbox_golden.npz"))
+    times = torch.from_numpy(g["chal/times"]).cuda()
+    W = {k[len("chal/w/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("chal/w/")}
+    m = slode.OdeModel()
+    m.init_with_params(times, 5, 15, 25, False, "dopri5", "cuda")
+    m.load_state_dict(W, strict=False)
+    m = m.cuda()
+    z = torch.from_numpy(g["chal/z"]).cuda()
+    replay = _oracle_steps(list(g["chal/dopri5/0/accepted"]), list(g["chal/dopri5/0/dts"]), 0.0)
+    with torch.no_grad():
+        free = slode.odeint(m.gen_dynamics(z), m.initialize_state(z), times, method="dopri5", rtol=1e-5, atol=1e-6,
+                            options={"log_steps": True}).permute(1, 0, 2)
+        first_dt = api.last_dopri5_stats.steps[0, 1].item()
+        sol = slode.odeint(m.gen_dynamics(z), m.initialize_state(z), times, method="dopri5", rtol=1e-5, atol=1e-6,
+                           options={"replay_steps": replay}).permute(1, 0, 2)
+    assert first_dt == pytest.approx(float(g["chal/dopri5/0/dts"][0]), rel=1e-6)
+    assert U.rel_err(sol, torch.from_numpy(g["chal/dopri5/0/sol"])) < 1e-5
+    assert U.rel_err(free, torch.from_numpy(g["chal/dopri5/0/sol"])) < 2e-4
+
+
+def test_first_step_option_and_determinism():
+    o, p = _pair("cvs")
+    z = torch.randn(16, 15, generator=torch.Generator().manual_seed(9))
+    want, got, acc_o, dts_o, _, st = _run(o, p, z, 1e-5, 1e-6, options={"first_step": 0.05})
+    assert st.steps[0, 1].item() == pytest.approx(0.05)
+    assert U.rel_err(got, want) < 2e-4  # free-running controller at a noise-dominated tolerance, see above
+    _, got2, _, _, _, st2 = _run(o, p, z, 1e-5, 1e-6, options={"first_step": 0.05})
+    assert torch.equal(got, got2) and torch.equal(st.steps, st2.steps)  # bitwise reproducible step sequence
+
+
+def test_controller_is_batch_global_on_device():
+    """A large batch takes ONE step sequence (F6): every trajectory of the batch shares the accepted times, and the
+    sequence differs from the one a sub-batch would take alone."""
+    o, p = _pair("cvs")
+    import structured_latent_odes_b200 as slode
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(70000, 15, generator=g).cuda()   # more pairs than one wave of resident threads
+    with torch.no_grad():
+        full = slode.odeint(p.gen_dynamics(z), p.initialize_state(z), p.times, method="dopri5", rtol=1e-4, atol=1e-5,
+                            options={"log_steps": True})
+        steps_full = api.last_dopri5_stats.steps.clone()
+        sub = slode.odeint(p.gen_dynamics(z[:7]), p.initialize_state(z[:7]), p.times, method="dopri5", rtol=1e-4,
+                           atol=1e-5, options={"log_steps": True})
+        steps_sub = api.last_dopri5_stats.steps.clone()
+    assert steps_full.shape != steps_sub.shape or not torch.equal(steps_full, steps_sub)
+    assert U.rel_err(full[:, :7], sub) < 1e-3  # both within tolerance of the true solution, not bit-equal
+    # oracle spot check of the big batch is exact only with the same global controller: replay its step sizes
+    zc = z[:64].cpu()
+    with torch.no_grad():
+        ref = tde.odeint(slode_port.OdeFunc(zc, o.dynamics), o.latent_to_ode_net(zc), o.times, method="dopri5",
+                         rtol=1e-9, atol=1e-11)
+    assert U.rel_err(full[:, :64], ref) < 5e-4
+
+
+def test_errors():
+    import structured_latent_odes_b200 as slode
+    o, p = _pair("cvs")
+    z = torch.randn(4, 15).cuda()
+    f, y0 = p.gen_dynamics(z), p.initialize_state(z).detach()
+    with torch.no_grad():
+        with pytest.raises(Exception, match="max_num_steps"):
+            slode.odeint(f, y0, p.times, method="dopri5", rtol=1e-5, atol=1e-6, options={"max_num_steps": 3})
+        with pytest.raises(NotImplementedError):
+            slode.odeint(f, y0, p.times.flip(0), method="dopri5", rtol=1e-5, atol=1e-6)
+        one = slode.odeint(f, y0, p.times[:1], method="dopri5", rtol=1e-5, atol=1e-6)
+        assert torch.equal(one[0], y0)
+    with pytest.raises(NotImplementedError, match="gradient"):
+        slode.odeint(f, y0.requires_grad_(True), p.times, method="dopri5", rtol=1e-5, atol=1e-6)
