@@ -140,6 +140,27 @@ int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S,
                          double* step_log, int64_t log_capacity,
                          int64_t* stats, void* stream);
 
+/*
+ * Reverse-mode gradient of slode_mlp_dopri5_fwd: exact gradient of the accepted-step sequence (what autograd
+ * through torchdiffeq.odeint(method="dopri5") gives; step sizes and accept/reject decisions carry no gradient).
+ *   accepted_steps (n_accepted, 2) float64: t0, dt of every accepted step (rows of step_log with accepted = 1)
+ *   emit_ranges    (n_accepted + 1) int32: output times [emit[n], emit[n+1]) were interpolated in accepted step n
+ *                  (emit[0] = 1: sol[0] is y0 itself)
+ *   ckpt_y         the checkpoints written by the forward call
+ *   grad_* as for slode_mlp_fixed_bwd (grad_w accumulated into; caller zero-fills).
+ * The torchdiffeq.odeint_adjoint variant of dopri5 (an ADAPTIVE backward solve whose error norm spans the
+ * parameter adjoints) is not provided.
+ */
+int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S,
+                         const float* t, const float* c,
+                         const float* w1t, const float* Wg, const float* bg,
+                         const float* Wd, const float* bd,
+                         int64_t n_accepted, const double* accepted_steps, const int* emit_ranges,
+                         const float* ckpt_y,
+                         const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
+                         float* grad_y0, float* grad_c, float* grad_w,
+                         void* stream);
+
 /* element types of the CVS entry points */
 #define SLODE_F32 0
 #define SLODE_F64 1

@@ -438,3 +438,215 @@ int launch_dopri5_fwd(Dopri5Args a, const PackSrc& w, float* staging, cudaStream
     return launch_dopri5_fwd<H, S>(a, w, staging, stream, sms);                                         \
   }                                                                                                     \
   }
+
+// =============================================================================================
+// Reverse sweep of the adaptive solve: exact gradient of the accepted-step sequence
+// (== autograd through torchdiffeq.odeint(method="dopri5"): step sizes and accept/reject decisions carry no
+// gradient, oracle/torchdiffeq_oracle.py::_optimal_step_size / _select_initial_step).
+//
+// One thread = two trajectories; accepted steps are walked backwards from the checkpointed step-start states
+// ckpt_y[n] written by the forward kernel.  Per step: recompute the six stages (five new MLP evaluations, taken
+// as 3 + 2 in two passes over the weights; the evaluation at t1 is carried over from the step processed before),
+// inject the cotangents of the outputs interpolated inside the step, then run the stage adjoints in decreasing
+// time order with the same prefix-sum / flip-record bookkeeping as the fixed-grid sweep.
+// =============================================================================================
+namespace slode {
+
+template <int H, int S>
+__global__ void __launch_bounds__(kBlock, 1)
+dopri5_bwd_kernel(Dopri5BwdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem<H, S>& sm = *reinterpret_cast<BwdSmem<H, S>*>(smem_raw);
+  constexpr int K2 = 2 * S;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < H * K2; i += kBlock) {
+    const int j = i / K2, o = i % K2;
+    sm.W[j][o] = (o < S) ? p.Wg[o * H + j] : p.Wd[(o - S) * H + j];
+  }
+  for (int i = tid; i < H; i += kBlock) {
+    sm.w1t[i] = p.w1t[i];
+    sm.gw1t[i] = 0.0f;
+  }
+  for (int i = tid; i < K2 * H; i += kBlock) (&sm.G[0][0])[i] = 0.0f;
+  if (tid < K2) sm.gb[tid] = 0.0f;
+  __syncthreads();
+
+  const int64_t ntiles = ((p.B + 1) / 2 + kBlock - 1) / kBlock;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const PairIdx pi = pair_index(tile, p.B);
+    float* gc0 = pi.ok0 ? p.gc + pi.b0 * H : nullptr;
+    float* gc1 = pi.ok1 ? p.gc + pi.b1 * H : nullptr;
+    float* rec = p.flip_ws + ((size_t)blockIdx.x * kBlock + tid) * Sweep<H, S>::REC_PER_THREAD;
+#pragma unroll
+    for (int j = 0; j < H; ++j)
+      sm.c[j][tid] = pk(ld_stream(p.c + pi.b0 * H + j), ld_stream(p.c + pi.b1 * H + j));
+    auto cj = [&](int j) { return sm.c[j][tid]; };
+    const float* gs0 = p.gsol + pi.b0 * p.gsb;
+    const float* gs1 = p.gsol + pi.b1 * p.gsb;
+    const f2 live = pk(pi.ok0 ? 1.0f : 0.0f, pi.ok1 ? 1.0f : 0.0f);
+
+    Sweep<H, S> sw;
+    Vec<S> lam;
+#pragma unroll
+    SLODE_FOR_S lam.v[s] = 0ull;
+    Vec<S> Ac, Dc;  // evaluation at the end time of the step in hand (= start time of the step processed before)
+    bool started = false;
+    if (p.n_acc > 0) {
+      const double lt0 = p.acc_steps[(p.n_acc - 1) * 2], ldt = p.acc_steps[(p.n_acc - 1) * 2 + 1];
+      Vec<S> A[1], D[1];
+      Gate<H> g[1];
+      const float te[1] = {(float)(lt0 + ldt)};
+      mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
+      Ac = A[0];
+      Dc = D[0];
+      sw.init(g[0]);
+      started = true;
+    }
+
+#pragma unroll 1
+    for (int64_t n = p.n_acc - 1; n >= 0; --n) {
+      const double dt0 = p.acc_steps[n * 2], ddt = p.acc_steps[n * 2 + 1];
+      const float ft0 = (float)dt0, fdt = (float)ddt, ft1 = (float)(dt0 + ddt);
+      float ts[6];  // stage times 1..6 (7 shares t1)
+      ts[0] = ft0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ts[e + 1] = __fadd_rn(ft0, __fmul_rn(kDpAlpha[e], fdt));
+      ts[5] = ft1;
+      Vec<S> A[6], D[6];
+      Gate<H> g[5];
+      {
+        Vec<S> A3[3], D3[3], A2[2], D2[2];
+        Gate<H> g3[3], g2[2];
+        const float ta[3] = {ts[0], ts[1], ts[2]};
+        const float tb[2] = {ts[3], ts[4]};
+        mlp_eval<H, S, 3, true, 0>(ta, cj, A3, D3, g3);
+        mlp_eval<H, S, 2, true, 1>(tb, cj, A2, D2, g2);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { A[e] = A3[e]; D[e] = D3[e]; g[e] = g3[e]; }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { A[3 + e] = A2[e]; D[3 + e] = D2[e]; g[3 + e] = g2[e]; }
+      }
+      A[5] = Ac;
+      D[5] = Dc;
+      // ---- recompute the stages -----------------------------------------------------------------------
+      Vec<S> Y[7], k[7];
+      Y[0] = vload2<S>(p.ckpt_y + ((size_t)n * p.B + pi.b0) * S, p.ckpt_y + ((size_t)n * p.B + pi.b1) * S);
+      k[0] = rhs<S>(A[0], D[0], Y[0]);
+      Y[1] = combine<S, 1>(Y[0], k, kDpBeta[0], fdt); k[1] = rhs<S>(A[1], D[1], Y[1]);
+      Y[2] = combine<S, 2>(Y[0], k, kDpBeta[1], fdt); k[2] = rhs<S>(A[2], D[2], Y[2]);
+      Y[3] = combine<S, 3>(Y[0], k, kDpBeta[2], fdt); k[3] = rhs<S>(A[3], D[3], Y[3]);
+      Y[4] = combine<S, 4>(Y[0], k, kDpBeta[3], fdt); k[4] = rhs<S>(A[4], D[4], Y[4]);
+      Y[5] = combine<S, 5>(Y[0], k, kDpBeta[4], fdt); k[5] = rhs<S>(A[5], D[5], Y[5]);
+      Y[6] = combine<S, 6>(Y[0], k, kDpBeta[5], fdt);  // = y1
+      // ---- cotangents of the outputs interpolated inside this step --------------------------------------
+      Vec<S> gy0i, gy1, gym, gf0, gf1;
+#pragma unroll
+      SLODE_FOR_S { gy0i.v[s] = 0ull; gy1.v[s] = lam.v[s]; gym.v[s] = 0ull; gf0.v[s] = 0ull; gf1.v[s] = 0ull; }
+      for (int i = p.emit[n]; i < p.emit[n + 1]; ++i) {
+        const float x = __fdiv_rn(__fsub_rn(__ldg(p.t + i), ft0), __fsub_rn(ft1, ft0));
+        const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+        const f2 w0 = bc(1.0f - 11.0f * x2 + 18.0f * x3 - 8.0f * x4);
+        const f2 w1 = bc(-5.0f * x2 + 14.0f * x3 - 8.0f * x4);
+        const f2 wm = bc(16.0f * x2 - 32.0f * x3 + 16.0f * x4);
+        const f2 wf0 = bc(fdt * (x - 4.0f * x2 + 5.0f * x3 - 2.0f * x4));
+        const f2 wf1 = bc(fdt * (x2 - 3.0f * x3 + 2.0f * x4));
+        const Vec<S> gi = vscale2<S>(vload2<S>(gs0 + (int64_t)i * p.gst, gs1 + (int64_t)i * p.gst), live);
+#pragma unroll
+        SLODE_FOR_S {
+          gy0i.v[s] = fma2(w0, gi.v[s], gy0i.v[s]);
+          gy1.v[s] = fma2(w1, gi.v[s], gy1.v[s]);
+          gym.v[s] = fma2(wm, gi.v[s], gym.v[s]);
+          gf0.v[s] = fma2(wf0, gi.v[s], gf0.v[s]);
+          gf1.v[s] = fma2(wf1, gi.v[s], gf1.v[s]);
+        }
+      }
+      // ---- stage adjoints, decreasing time ---------------------------------------------------------------
+      Vec<S> gk[7];
+      // k7 = f(t1, y1) enters the interpolant as f1 and y_mid
+      gk[6] = vaxpy<S>(__fmul_rn(kDpCMid[6], fdt), gym, gf1);
+      sw.add(ft1, gk[6], Y[6], A[5], D[5]);                       // same gates as the sweep's current ones
+      gy1 = vnfma<S>(gk[6], D[5], gy1);                            // through y1 inside k7
+      // y1 = y0 + dt sum_j b_j k_j,  y_mid = y0 + dt sum_j cmid_j k_j
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const f2 cb = bc(__fmul_rn(kDpBeta[5][j], fdt)), cm = bc(__fmul_rn(kDpCMid[j], fdt));
+#pragma unroll
+        SLODE_FOR_S gk[j].v[s] = fma2(cb, gy1.v[s], mul2(cm, gym.v[s]));
+      }
+      gk[0] = vadd<S>(gk[0], gf0);
+      Vec<S> gy0 = vadd<S>(vadd<S>(gy1, gym), gy0i);
+#pragma unroll
+      for (int i = 5; i >= 0; --i) {  // stage i+1 at time ts[i], state Y[i]
+        if (i < 5) sw.events(rec, g[i]);
+        sw.add(ts[i], gk[i], Y[i], A[i], D[i]);
+        const Vec<S> gY = vnmul<S>(gk[i], D[i]);
+        gy0 = vadd<S>(gy0, gY);
+        if (i > 0) {
+#pragma unroll
+          for (int j = 0; j < i; ++j) {
+            if (kDpBeta[i - 1][j] != 0.0f) gk[j] = vaxpy<S>(__fmul_rn(kDpBeta[i - 1][j], fdt), gY, gk[j]);
+          }
+        }
+      }
+      lam = gy0;
+      Ac = A[0];
+      Dc = D[0];
+    }
+    // sol[0] = y0
+    lam = vadd<S>(lam, vscale2<S>(vload2<S>(gs0, gs1), live));
+    if (started) {
+      sw.finish(sm, rec, gc0, gc1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        if (gc0) gc0[j] = 0.0f;
+        if (gc1) gc1[j] = 0.0f;
+      }
+    }
+    vstore2<S>(p.gy0 + pi.b0 * S, pi.ok0, p.gy0 + pi.b1 * S, pi.ok1, lam);
+  }
+
+  __syncthreads();
+  for (int i = tid; i < H; i += kBlock) atomicAdd(p.gw + i, sm.gw1t[i]);
+  for (int i = tid; i < K2 * H; i += kBlock) {
+    const int o = i / H, j = i % H;
+    const int base = (o < S) ? (H + o * H) : (H + S * H + S + (o - S) * H);
+    atomicAdd(p.gw + base + j, sm.G[o][j]);
+  }
+  if (tid < K2) {
+    const int base = (tid < S) ? (H + S * H + tid) : (H + S * H + S + S * H + (tid - S));
+    atomicAdd(p.gw + base, sm.gb[tid]);
+  }
+}
+
+template <int H, int S>
+int launch_dopri5_bwd(Dopri5BwdArgs a, const PackSrc& w, float* staging, cudaStream_t stream, int sms) {
+  int rc = upload_pack<H, S>(w, staging, stream);
+  if (rc) return rc;
+  auto kern = dopri5_bwd_kernel<H, S>;
+  const size_t smem = sizeof(BwdSmem<H, S>);
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, smem));
+    blocks_per_sm = std::max(n, 1);
+  }
+  const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * blocks_per_sm);
+  a.flip_ws = flip_workspace(sizeof(float) * (size_t)grid * kBlock * Sweep<H, S>::REC_PER_THREAD);
+  if (!a.flip_ws) return SLODE_ECUDA;
+  kern<<<grid, kBlock, smem, stream>>>(a);
+  SLODE_CUDA_TRY(cudaGetLastError());
+  return SLODE_OK;
+}
+
+}  // namespace slode
+
+#define SLODE_DEFINE_DOPRI5_BWD(H, S)                                                                       \
+  namespace slode {                                                                                         \
+  int dopri5_bwd_##H##_##S(const Dopri5BwdArgs& a, const PackSrc& w, float* staging, cudaStream_t stream,   \
+                           int sms) {                                                                       \
+    return launch_dopri5_bwd<H, S>(a, w, staging, stream, sms);                                             \
+  }                                                                                                         \
+  }

@@ -12,9 +12,10 @@ struct ShapeEntry {
   mlp_fwd_fn fwd;
   mlp_bwd_fn bwd;
   dopri5_fwd_fn dopri5_fwd;
+  dopri5_bwd_fn dopri5_bwd;
 };
 static const ShapeEntry kShapes[] = {
-#define X(h, s) {h, s, mlp_fwd_##h##_##s, mlp_bwd_##h##_##s, dopri5_fwd_##h##_##s},
+#define X(h, s) {h, s, mlp_fwd_##h##_##s, mlp_bwd_##h##_##s, dopri5_fwd_##h##_##s, dopri5_bwd_##h##_##s},
     SLODE_SHAPES(X)
 #undef X
 };
@@ -162,5 +163,37 @@ extern "C" int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S, const float*
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->dopri5_fwd(a, w, guard.staging, stream, guard.sms);
   if (rc == SLODE_OK) g_fwd_launches = 2;
+  return rc;
+}
+
+extern "C" int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S, const float* t, const float* c, const float* w1t,
+                                    const float* Wg, const float* bg, const float* Wd, const float* bd,
+                                    int64_t n_accepted, const double* accepted_steps, const int* emit_ranges,
+                                    const float* ckpt_y, const float* grad_sol, int64_t gsol_stride_t,
+                                    int64_t gsol_stride_b, float* grad_y0, float* grad_c, float* grad_w,
+                                    void* stream_) {
+  int rc = check_common("slode_mlp_dopri5_bwd", B, T, H, S);
+  if (rc) return rc;
+  if (n_accepted < 0 || (T > 1 && n_accepted < 1)) {
+    set_error("slode_mlp_dopri5_bwd: n_accepted=%lld for T=%d", (long long)n_accepted, T);
+    return SLODE_EINVAL;
+  }
+  if (!t || !w1t || !Wg || !bg || !Wd || !bd || !grad_w || (n_accepted > 0 && (!accepted_steps || !emit_ranges)) ||
+      (B > 0 && (!c || !grad_sol || !grad_y0 || !grad_c || (n_accepted > 0 && !ckpt_y)))) {
+    set_error("slode_mlp_dopri5_bwd: null pointer");
+    return SLODE_EINVAL;
+  }
+  g_bwd_launches = 0;
+  if (B == 0) return SLODE_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PackGuard guard(stream);
+  if (guard.status) return guard.status;
+  Dopri5BwdArgs a{};
+  a.B = B; a.T = T; a.t = t; a.c = c; a.w1t = w1t; a.Wg = Wg; a.Wd = Wd; a.n_acc = n_accepted;
+  a.acc_steps = accepted_steps; a.emit = emit_ranges; a.ckpt_y = ckpt_y; a.gsol = grad_sol; a.gst = gsol_stride_t;
+  a.gsb = gsol_stride_b; a.gy0 = grad_y0; a.gc = grad_c; a.gw = grad_w;
+  const PackSrc w{w1t, Wg, bg, Wd, bd};
+  rc = find_shape(H, S)->dopri5_bwd(a, w, guard.staging, stream, guard.sms);
+  if (rc == SLODE_OK) g_bwd_launches = 2;
   return rc;
 }

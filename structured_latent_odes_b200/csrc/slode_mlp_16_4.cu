@@ -5,3 +5,4 @@
 
 SLODE_DEFINE_SHAPE(16, 4)
 SLODE_DEFINE_DOPRI5(16, 4)
+SLODE_DEFINE_DOPRI5_BWD(16, 4)

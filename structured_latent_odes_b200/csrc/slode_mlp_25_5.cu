@@ -5,3 +5,4 @@
 
 SLODE_DEFINE_SHAPE(25, 5)
 SLODE_DEFINE_DOPRI5(25, 5)
+SLODE_DEFINE_DOPRI5_BWD(25, 5)

@@ -5,3 +5,4 @@
 
 SLODE_DEFINE_SHAPE(32, 5)
 SLODE_DEFINE_DOPRI5(32, 5)
+SLODE_DEFINE_DOPRI5_BWD(32, 5)

@@ -59,9 +59,25 @@ struct Dopri5Args {
   int64_t* stats;       // [0] accepted, [1] rejected, [2] RHS evaluations per trajectory, [3] status (0 ok)
 };
 
+// dopri5 reverse sweep; flip_ws is filled in by the launcher
+struct Dopri5BwdArgs {
+  int64_t B;
+  int T;
+  const float *t, *c, *w1t, *Wg, *Wd;
+  int64_t n_acc;
+  const double* acc_steps;   // (n_acc, 2): t0, dt of every accepted step
+  const int* emit;           // (n_acc + 1): outputs [emit[n], emit[n+1]) were interpolated inside accepted step n
+  const float* ckpt_y;       // (n_acc, B, S)
+  const float* gsol;
+  int64_t gst, gsb;
+  float *gy0, *gc, *gw;
+  float* flip_ws;
+};
+
 typedef int (*mlp_fwd_fn)(const FwdArgs&, const PackSrc&, float* staging);
 typedef int (*mlp_bwd_fn)(const BwdArgs&, const PackSrc&, float* staging);
 typedef int (*dopri5_fwd_fn)(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
+typedef int (*dopri5_bwd_fn)(const Dopri5BwdArgs&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 
 // (25,5): CVS / challenge configs; (25,8): proc config; the rest serve tests and the width sweep.
 #define SLODE_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5)
@@ -69,7 +85,8 @@ typedef int (*dopri5_fwd_fn)(const Dopri5Args&, const PackSrc&, float* staging, 
 #define SLODE_DECLARE_SHAPE(H, S)                                         \
   int mlp_fwd_##H##_##S(const FwdArgs&, const PackSrc&, float* staging);  \
   int mlp_bwd_##H##_##S(const BwdArgs&, const PackSrc&, float* staging);  \
-  int dopri5_fwd_##H##_##S(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
+  int dopri5_fwd_##H##_##S(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms); \
+  int dopri5_bwd_##H##_##S(const Dopri5BwdArgs&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 SLODE_SHAPES(SLODE_DECLARE_SHAPE)
 #undef SLODE_DECLARE_SHAPE
 

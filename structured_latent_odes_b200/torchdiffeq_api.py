@@ -296,6 +296,58 @@ def _solve_blackbox(func, y0, t, method, mode, layout):
                                 _cabi.METHODS[method], mode, layout)
 
 
+class _MlpDopri5Solve(torch.autograd.Function):
+    """dopri5 solve with the exact gradient of its accepted-step sequence (odeint + autograd parity)."""
+
+    @staticmethod
+    def forward(ctx, y0, c, w1t, Wg, bg, Wd, bd, t, rtol, atol, options, layout):
+        w = [x.detach().contiguous() for x in (w1t, Wg, bg, Wd, bd)]
+        cc = c.contiguous()
+        sol, ckpt, steps = _dopri5_forward(y0.contiguous(), cc, w, t, rtol, atol, options, layout, want_ckpt=True)
+        # accepted steps and the output times interpolated inside each of them (tiny, host side)
+        log = steps.cpu() if steps is not None else torch.zeros((0, 3), dtype=torch.float64)
+        acc = log[log[:, 2] != 0][:, :2].contiguous()
+        tt = t.detach().double().cpu()
+        emit, out_idx = [1], 1
+        for t0, dt in acc.tolist():
+            t1 = t0 + dt
+            while out_idx < tt.numel() and float(tt[out_idx]) <= t1:
+                out_idx += 1
+            emit.append(out_idx)
+        ctx.save_for_backward(cc, *w, t, ckpt if ckpt is not None else sol.new_zeros(0))
+        ctx.acc = acc.to(y0.device)
+        ctx.emit = torch.tensor(emit, dtype=torch.int32, device=y0.device)
+        ctx.shape = tuple(sol.shape)
+        return sol
+
+    @staticmethod
+    def backward(ctx, grad_sol):
+        cc, w1t, Wg, bg, Wd, bd, t, ckpt = ctx.saved_tensors
+        T, B, S = ctx.shape
+        H = cc.shape[1]
+        strides = _dense_tbs_strides(grad_sol)
+        if strides is None or grad_sol.dtype != torch.float32:
+            grad_sol = grad_sol.to(torch.float32).contiguous()
+            strides = (grad_sol.stride(0), grad_sol.stride(1))
+        dev = cc.device
+        grad_y0 = torch.empty((B, S), device=dev, dtype=torch.float32)
+        grad_c = torch.empty((B, H), device=dev, dtype=torch.float32)
+        grad_w = torch.zeros(H + 2 * (S * H + S), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev), _timed("bwd"):
+            rc = _cabi.lib().slode_mlp_dopri5_bwd(
+                B, T, H, S, _ptr(t), _ptr(cc), _ptr(w1t), _ptr(Wg), _ptr(bg), _ptr(Wd), _ptr(bd), ctx.acc.shape[0],
+                _ptr(ctx.acc), _ptr(ctx.emit), _ptr(ckpt), _ptr(grad_sol), strides[0], strides[1], _ptr(grad_y0),
+                _ptr(grad_c), _ptr(grad_w), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_mlp_dopri5_bwd")
+        o = 0
+        gw1t = grad_w[o:o + H]; o += H
+        gWg = grad_w[o:o + S * H].view(S, H); o += S * H
+        gbg = grad_w[o:o + S]; o += S
+        gWd = grad_w[o:o + S * H].view(S, H); o += S * H
+        gbd = grad_w[o:o + S]
+        return grad_y0, grad_c, gw1t, gWg, gbg, gWd, gbd, None, None, None, None, None
+
+
 def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
     z, hid, gro, deg = _check_blackbox(func)
     B, S = y0.shape
@@ -310,9 +362,15 @@ def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
     needs_grad = torch.is_grad_enabled() and (y0.requires_grad or z.requires_grad
                                               or any(p.requires_grad for p in func.parameters()))
     if needs_grad:
-        raise NotImplementedError(
-            "reverse-mode gradient through dopri5 is not built yet: run under torch.no_grad() (evaluation / "
-            "multiple_samples), or train with a fixed-grid solver as every shipped config does")
+        if mode == _cabi.BWD_TDE_ADJOINT:
+            raise NotImplementedError(
+                "odeint_adjoint with dopri5 (an adaptive backward solve whose error norm spans the parameter "
+                "adjoints) is not provided: use odeint (exact gradient of the accepted steps) or a fixed-grid "
+                "solver as every shipped config does")
+        W1g = hid.weight
+        cg = torch.addmm(hid.bias, z.to(torch.float32), W1g[:, 1:].t())
+        return _MlpDopri5Solve.apply(y0, cg, W1g[:, 0], gro.weight, gro.bias, deg.weight, deg.bias, t, rtol, atol,
+                                     options, layout)
     W1 = hid.weight.detach()
     c = torch.addmm(hid.bias.detach(), z.detach().to(torch.float32), W1[:, 1:].t()).contiguous()
     w = [x.detach().contiguous() for x in (W1[:, 0], gro.weight, gro.bias, deg.weight, deg.bias)]

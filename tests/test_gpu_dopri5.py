@@ -157,5 +157,58 @@ def test_errors():
             slode.odeint(f, y0, p.times.flip(0), method="dopri5", rtol=1e-5, atol=1e-6)
         one = slode.odeint(f, y0, p.times[:1], method="dopri5", rtol=1e-5, atol=1e-6)
         assert torch.equal(one[0], y0)
-    with pytest.raises(NotImplementedError, match="gradient"):
-        slode.odeint(f, y0.requires_grad_(True), p.times, method="dopri5", rtol=1e-5, atol=1e-6)
+    with pytest.raises(NotImplementedError, match="odeint_adjoint with dopri5"):
+        slode.odeint_adjoint(f, y0.requires_grad_(True), p.times, method="dopri5", rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,B,rtol,atol", [("cvs", 40, 1e-5, 1e-6), ("proc", 30, 1e-4, 1e-5), ("small", 129, 1e-6, 1e-7)])
+def test_gradients_equal_autograd_through_the_oracle_on_the_same_steps(shape, B, rtol, atol):
+    """odeint(dopri5) + backward == autograd through the oracle's unrolled adaptive solve.  The oracle's step
+    sequence is replayed on the device so both differentiate the same computation (see the replay test)."""
+    L, H, S, times = U.SHAPES[shape]
+    o, p = _pair(shape)
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(B, L, generator=g)
+    G = torch.randn(B, len(times), S, generator=g)
+    o.zero_grad()
+    zo = z.clone().requires_grad_(True)
+    sol_o = tde.odeint(slode_port.OdeFunc(zo, o.dynamics), o.latent_to_ode_net(zo), o.times, method="dopri5", rtol=rtol,
+                       atol=atol).permute(1, 0, 2)
+    replay = _oracle_steps(list(tde.last_stats.accepted), list(tde.last_stats.dts), o.times[0])
+    (sol_o * G).sum().backward()
+    import structured_latent_odes_b200 as slode
+    p.zero_grad()
+    zp = z.cuda().requires_grad_(True)
+    sol_p = slode.odeint(p.gen_dynamics(zp), p.initialize_state(zp), p.times, method="dopri5", rtol=rtol, atol=atol,
+                         options={"replay_steps": replay}).permute(1, 0, 2)
+    (sol_p * G.cuda()).sum().backward()
+    assert U.rel_err(sol_p, sol_o) < 1e-5
+    assert U.rel_err(zp.grad, zo.grad) < 2e-5
+    go = {k: v.grad for k, v in o.named_parameters() if v.grad is not None and ".prod." not in k and ".degr." not in k}
+    gp = {k: v.grad for k, v in p.named_parameters() if v.grad is not None and ".prod." not in k and ".degr." not in k}
+    assert set(go) == set(gp)
+    for k in go:
+        assert U.rel_err(gp[k], go[k]) < 2e-5, (k, U.rel_err(gp[k], go[k]))
+
+
+def test_free_running_gradient_is_consistent():
+    """Without replay the device picks its own steps; the gradient must still be the exact derivative of what it
+    computed: directional derivative check against a central finite difference on the same (logged) steps."""
+    import structured_latent_odes_b200 as slode
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    o, p = _pair("cvs")
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(32, 15, generator=g).cuda()
+    G = torch.randn(len(p.times), 32, 5, generator=g).cuda()
+    y0 = p.initialize_state(z).detach().requires_grad_(True)
+    f = p.gen_dynamics(z)
+    sol = slode.odeint(f, y0, p.times, method="dopri5", rtol=1e-5, atol=1e-6, options={"log_steps": True})
+    steps = api.last_dopri5_stats.steps.clone()
+    (sol * G).sum().backward()
+    v = torch.randn(32, 5, generator=torch.Generator().manual_seed(4)).cuda()
+    with torch.no_grad():  # the ODE is affine in the state: a finite difference on fixed steps is exact up to rounding
+        a = slode.odeint(f, y0 + v, p.times, method="dopri5", rtol=1e-5, atol=1e-6, options={"replay_steps": steps})
+        b = slode.odeint(f, y0 - v, p.times, method="dopri5", rtol=1e-5, atol=1e-6, options={"replay_steps": steps})
+    fd = 0.5 * ((a - b).double() * G.double()).sum()
+    an = (y0.grad.double() * v.double()).sum()
+    assert abs(fd - an) < 1e-4 * max(abs(fd), 1.0)
