@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Secondary measurements over the other BASELINE.json configs (the contract line is bench.py; this script writes
+one JSON line per case, for profiles/):
+
+  configs[0]  CVS default: midpoint, odeint_adjoint semantics, B=128, T=86
+  configs[1]  mechanistic CVS variant: 2^20 trajectories x 100 times, rk4, f32 (HBM-bound: GB/s reported)
+  configs[2]  challenge shape, dopri5 (batch-global controller), B in {35, 7000, 2^20}
+  configs[3]  proc shape (L=50, S=8, non-uniform t), B = 312 wells x {1, 200, 4096} samples, midpoint + rk4
+
+Timing: CUDA events, best of `reps` after 2 warm-ups; every tensor is device resident.
+"""
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import structured_latent_odes_b200 as slode  # noqa: E402
+from structured_latent_odes_b200 import torchdiffeq_api as api  # noqa: E402
+
+dev = "cuda"
+
+
+def timed(fn, reps=5):
+    for _ in range(2):
+        fn()
+    best = 1e30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def blackbox(name, B, T, L, H, S, method, adjoint, times=None, rtol=1e-5, atol=1e-6, grad=True):
+    torch.manual_seed(12)
+    t = torch.arange(0.0, T, 1.0, device=dev) if times is None else times.to(dev)
+    m = slode.OdeModel()
+    m.init_with_params(t, S, L, H, adjoint, method, dev)
+    m = m.to(dev)
+    z = torch.randn(B, L, device=dev)
+    G = torch.randn(T, B, S, device=dev).permute(1, 0, 2)
+
+    def fwd_bwd():
+        m.zero_grad(set_to_none=True)
+        if method == "dopri5":
+            f = m.gen_dynamics(z)
+            sol = slode.odeint(f, m.initialize_state(z), t, method="dopri5", rtol=rtol, atol=atol).permute(1, 0, 2)
+        else:
+            sol = m.solve_ODE(z)
+        sol.backward(G)
+
+    def fwd_only():
+        with torch.no_grad():
+            if method == "dopri5":
+                slode.odeint(m.gen_dynamics(z), m.initialize_state(z), t, method="dopri5", rtol=rtol, atol=atol)
+            else:
+                m.solve_ODE(z)
+
+    ms_f = timed(fwd_only)
+    out = {"case": name, "B": B, "T": T, "L": L, "H": H, "S": S, "method": method,
+           "gradient": "odeint_adjoint" if adjoint else "discrete", "fwd_ms": round(ms_f, 4),
+           "fwd_traj_steps_per_s": B * (T - 1) / (ms_f * 1e-3)}
+    if method == "dopri5":
+        st = api.last_dopri5_stats
+        out.update(rtol=rtol, atol=atol, accepted=st.n_accept, rejected=st.n_reject, rhs_evals=st.n_rhs)
+    if grad:
+        ms = timed(fwd_bwd)
+        out.update(fwd_bwd_ms=round(ms, 4), fwd_bwd_traj_steps_per_s=B * (T - 1) / (ms * 1e-3))
+    print(json.dumps(out), flush=True)
+
+
+def cvs_mech(B, T=100):
+    g = torch.Generator(device=dev).manual_seed(12)
+    ie = torch.where(torch.rand(B, device=dev, generator=g) < 0.5, -2.0, 0.0)
+    rm = torch.where(torch.rand(B, device=dev, generator=g) < 0.5, 0.5, 0.0)
+    f = slode.CvsMechanistic(ie, rm, learn_constants=True)
+    t = torch.arange(0.0, T, 1.0, device=dev)
+    y0 = torch.ones(B, 4, device=dev, requires_grad=True)
+    G = torch.randn(T, B, 4, device=dev)
+
+    def fwd():
+        with torch.no_grad():
+            slode.odeint(f, y0, t, method="rk4")
+
+    def fwd_bwd():
+        f.zero_grad(set_to_none=True)
+        y0.grad = None
+        slode.odeint(f, y0, t, method="rk4").backward(G)
+
+    ms_f, ms = timed(fwd), timed(fwd_bwd)
+    bytes_f = B * 4 * (T * 4 + 4 + 2)
+    bytes_b = B * 4 * (2 * T * 4 + 4 + 4)
+    print(json.dumps({"case": "configs[1] mechanistic CVS rk4 f32", "B": B, "T": T, "fwd_ms": round(ms_f, 4),
+                      "fwd_bwd_ms": round(ms, 4), "fwd_GBps": bytes_f / (ms_f * 1e-3) / 1e9,
+                      "bwd_GBps": bytes_b / ((ms - ms_f) * 1e-3) / 1e9,
+                      "fwd_bwd_traj_steps_per_s": B * (T - 1) / (ms * 1e-3)}), flush=True)
+
+    def gen():
+        slode.generate_cvs_latents(ie[:1000], rm[:1000])
+    print(json.dumps({"case": "CVS generator (f64 rk4 x8 substeps), 1000 x 86 like cvs_data.py", "ms": round(timed(gen), 4)}),
+          flush=True)
+
+
+if __name__ == "__main__":
+    big = 1 << 20
+    blackbox("configs[0] CVS default", 128, 86, 15, 25, 5, "midpoint", True)
+    blackbox("configs[0] CVS full train set", 810, 86, 15, 25, 5, "midpoint", True)
+    cvs_mech(big)
+    for B in (35, 7000, big):
+        blackbox("configs[2] challenge dopri5", B, 142, 15, 25, 5, "dopri5", False, rtol=1e-5, atol=1e-6)
+    blackbox("configs[2] challenge dopri5 torchdiffeq default tol", 7000, 142, 15, 25, 5, "dopri5", False, rtol=1e-7, atol=1e-9,
+             grad=False)
+    blackbox("configs[2] challenge midpoint (shipped solver)", 7000, 142, 15, 25, 5, "midpoint", True)
+    tt = torch.cat([torch.zeros(1), torch.cumsum(0.193 + 0.003 * torch.rand(99, generator=torch.Generator().manual_seed(7)), 0)])
+    for ns in (1, 200, 4096):
+        for method in ("midpoint", "rk4"):
+            blackbox(f"configs[3] proc 312 wells x {ns} samples", 312 * ns, 100, 50, 25, 8, method, method == "midpoint", times=tt)
+    blackbox("configs[1] blackbox rk4 (bench.py workload)", big, 100, 15, 25, 5, "rk4", False)
+    blackbox("configs[1] blackbox midpoint adjoint", big, 100, 15, 25, 5, "midpoint", True)

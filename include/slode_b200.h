@@ -112,6 +112,40 @@ int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
                         void* stream);
 
 /*
+ * Fused variants of slode_mlp_fixed_fwd / _bwd: the solve together with the two small nets in front of it, i.e.
+ * the whole of OdeModel.solve_ODE (models/blackbox_ode.py:36-47):
+ *     c  = z W1[:,1:]^T + b1                               (first layer of Dynamics on the constants, :99-106)
+ *     x0 = sigmoid(Wb relu(Wa z + ba) + bb)                (latent_to_ode_net, :19-22, :32-34)
+ * computed per trajectory inside the solver kernels (no (B,H) intermediates in HBM, no cuBLAS calls).
+ *   z (B,L);  W1 = dynamics_hidden.weight (H, L+1), b1 its bias;  Wa (H,L), ba (H), Wb (S,H), bb (S) =
+ *   latent_to_ode_net[0] / [2] -- pass all four as NULL and give y0 (B,S) instead when the caller computes the
+ *   initial state itself (the torchdiffeq.odeint entry, where y0 is an argument).
+ * Backward: grad_z (B,L) written (through c -- discrete mode only, SURVEY F5 -- and through x0 when the x0 net is
+ * fused); grad_y0 (B,S) written when the x0 net is NOT fused (else NULL); grad_params ACCUMULATED (caller
+ * zero-fills), flat
+ *     [ dw1t (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) | dW1[:,1:] (H*L) | db1 (H) |
+ *       dWa (H*L) | dba (H) | dWb (S*H) | dbb (S) ]           (the last four only when the x0 net is fused).
+ */
+int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S,
+                           const float* t, const float* z,
+                           const float* W1, const float* b1, const float* Wg, const float* bg,
+                           const float* Wd, const float* bd,
+                           const float* Wa, const float* ba, const float* Wb, const float* bb,
+                           const float* y0,
+                           float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                           void* stream);
+
+int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H, int S,
+                           const float* t, const float* z,
+                           const float* W1, const float* b1, const float* Wg, const float* bg,
+                           const float* Wd, const float* bd,
+                           const float* Wa, const float* ba, const float* Wb, const float* bb,
+                           const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                           const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
+                           float* grad_z, float* grad_y0, float* grad_params,
+                           void* stream);
+
+/*
  * Adaptive Dormand-Prince 5(4) forward solve; replaces torchdiffeq.odeint(func=OdeFunc, y0, t, method="dopri5",
  * rtol, atol) (models/blackbox_ode.py:44-45 with config.solver = "dopri5").  torchdiffeq semantics are kept:
  * ONE step size for the whole batch (error ratio = RMS over all B*S elements), float64 controller time,

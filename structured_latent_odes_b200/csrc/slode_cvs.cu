@@ -26,7 +26,11 @@ constexpr int kBlock = 256;
 constexpr int kMaxSub = 16;
 constexpr int NTH = 10;
 
-template <class R> struct Theta { R fmax, fmin, rmax, rmin, svm, ca, cv, k, pset, tau; };
+template <class R> struct Theta {
+  R fmax, fmin, rmax, rmin, svm, ca, cv, k, pset, tau;
+  R dF, dR, ica, icv, itau, rca, rcv;  // derived once per thread: f_max - f_min, r_max - r_min, 1/(100 ca),
+                                       // 1/(10 cv), 1/tau, 1/ca, 1/cv
+};
 
 template <class R> __device__ __forceinline__ R rexp(R x);
 template <> __device__ __forceinline__ float rexp<float>(float x) { return __expf(x); }
@@ -44,14 +48,14 @@ template <class R> __device__ __forceinline__ V4<R> axpy(R a, const V4<R>& x, co
 template <class R>
 __device__ __forceinline__ V4<R> rhs(const V4<R>& x, R ie, R rm, const Theta<R>& th) {
   const R pa = R(100) * x.v[0], pv = R(10) * x.v[1], s = x.v[2], sv = R(100) * x.v[3];
-  const R fhr = s * (th.fmax - th.fmin) + th.fmin;
-  const R r = s * (th.rmax - th.rmin) + th.rmin - rm;
+  const R fhr = fma(s, th.dF, th.fmin);
+  const R r = fma(s, th.dR, th.rmin) - rm;
   const R dva = sv * fhr - (pa - pv) / r;
   const R e = rexp<R>(-th.k * (pa - th.pset));
   V4<R> f;
-  f.v[0] = dva / (th.ca * R(100));
-  f.v[1] = (ie - dva) / (th.cv * R(10));
-  f.v[2] = (R(1) - R(1) / (R(1) + e) - s) / th.tau;
+  f.v[0] = dva * th.ica;
+  f.v[1] = (ie - dva) * th.icv;
+  f.v[2] = (R(1) - R(1) / (R(1) + e) - s) * th.itau;
   f.v[3] = ie * th.svm;
   return f;
 }
@@ -61,15 +65,15 @@ template <class R, bool PARAMS>
 __device__ __forceinline__ V4<R> vjp(const V4<R>& x, R ie, R rm, const Theta<R>& th, const V4<R>& g, R w, R& gie,
                                      R& grm, R (&gth)[NTH]) {
   const R pa = R(100) * x.v[0], pv = R(10) * x.v[1], s = x.v[2], sv = R(100) * x.v[3];
-  const R dF = th.fmax - th.fmin, dR = th.rmax - th.rmin;
-  const R fhr = s * dF + th.fmin;
-  const R r = s * dR + th.rmin - rm;
+  const R dF = th.dF, dR = th.dR;
+  const R fhr = fma(s, dF, th.fmin);
+  const R r = fma(s, dR, th.rmin) - rm;
   const R rinv = R(1) / r;
   const R q = (pa - pv) * rinv;
   const R dva = sv * fhr - q;
   const R e = rexp<R>(-th.k * (pa - th.pset));
   const R sg = R(1) / (R(1) + e);
-  const R ica = R(1) / (th.ca * R(100)), icv = R(1) / (th.cv * R(10)), itau = R(1) / th.tau;
+  const R ica = th.ica, icv = th.icv, itau = th.itau;
   const R g_dva = g.v[0] * ica - g.v[1] * icv;
   const R g_r = g_dva * q * rinv;          // d(-q)/dr = q/r
   const R g_fhr = g_dva * sv;
@@ -90,8 +94,8 @@ __device__ __forceinline__ V4<R> vjp(const V4<R>& x, R ie, R rm, const Theta<R>&
     gth[2] = fma(w, g_r * s, gth[2]);
     gth[3] = fma(w, g_r * (R(1) - s), gth[3]);
     gth[4] = fma(w, g.v[3] * ie, gth[4]);
-    gth[5] = fma(w, -g.v[0] * dva * ica / th.ca, gth[5]);
-    gth[6] = fma(w, -g.v[1] * (ie - dva) * icv / th.cv, gth[6]);
+    gth[5] = fma(w, -g.v[0] * dva * ica * th.rca, gth[5]);
+    gth[6] = fma(w, -g.v[1] * (ie - dva) * icv * th.rcv, gth[6]);
     gth[7] = fma(w, g_u * (-(pa - th.pset)), gth[7]);
     gth[8] = fma(w, g_u * th.k, gth[8]);
     gth[9] = fma(w, -g.v[2] * (R(1) - sg - s) * itau * itau, gth[9]);
@@ -236,6 +240,9 @@ template <class R> __device__ __forceinline__ Theta<R> load_theta(const R* th) {
   Theta<R> t;
   t.fmax = th[0]; t.fmin = th[1]; t.rmax = th[2]; t.rmin = th[3]; t.svm = th[4];
   t.ca = th[5]; t.cv = th[6]; t.k = th[7]; t.pset = th[8]; t.tau = th[9];
+  t.dF = t.fmax - t.fmin; t.dR = t.rmax - t.rmin;
+  t.ica = R(1) / (t.ca * R(100)); t.icv = R(1) / (t.cv * R(10)); t.itau = R(1) / t.tau;
+  t.rca = R(1) / t.ca; t.rcv = R(1) / t.cv;
   return t;
 }
 

@@ -595,7 +595,7 @@ dopri5_bwd_kernel(Dopri5BwdArgs p) {
     // sol[0] = y0
     lam = vadd<S>(lam, vscale2<S>(vload2<S>(gs0, gs1), live));
     if (started) {
-      sw.finish(sm, rec, gc0, gc1);
+      sw.finish(sm, rec, gc0, gc1, false);
     } else {
 #pragma unroll
       for (int j = 0; j < H; ++j) {

@@ -89,7 +89,7 @@ extern "C" int slode_mlp_fixed_fwd(int method, int64_t B, int T, int H, int S, c
   cudaStream_t stream = (cudaStream_t)stream_;
   PackGuard guard(stream);
   if (guard.status) return guard.status;
-  const FwdArgs a{method, B, T, t, c, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms};
+  const FwdArgs a{method, B, T, t, c, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, LatentSrc{}};
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->fwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_fwd_launches = 2;  // pack kernel + solver kernel
@@ -122,7 +122,7 @@ extern "C" int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H
   PackGuard guard(stream);
   if (guard.status) return guard.status;
   const BwdArgs a{method, mode,          B,  T,      t,        c,       w1t, Wg, Wd, sol, sol_stride_t, sol_stride_b,
-                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, grad_c, grad_w, stream, guard.sms};
+                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, grad_c, grad_w, stream, guard.sms, LatentSrc{}, nullptr};
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->bwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_bwd_launches = 2;
@@ -194,6 +194,107 @@ extern "C" int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S, const float*
   a.gsb = gsol_stride_b; a.gy0 = grad_y0; a.gc = grad_c; a.gw = grad_w;
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->dopri5_bwd(a, w, guard.staging, stream, guard.sms);
+  if (rc == SLODE_OK) g_bwd_launches = 2;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused entry points: the solve together with the two small nets in front of it
+// ---------------------------------------------------------------------------------------------------------
+static int check_latent(const char* who, int method, int L, const float* z, const float* W1, const float* b1,
+                        const float* Wa, const float* ba, const float* Wb, const float* bb, const float* y0or) {
+  if (method != SLODE_METHOD_EULER && method != SLODE_METHOD_MIDPOINT && method != SLODE_METHOD_RK4) {
+    set_error("%s: unknown method %d", who, method);
+    return SLODE_EINVAL;
+  }
+  if (L < 1 || !z || !W1 || !b1) {
+    set_error("%s: latent inputs missing (L=%d)", who, L);
+    return SLODE_EINVAL;
+  }
+  const int n = (Wa != nullptr) + (ba != nullptr) + (Wb != nullptr) + (bb != nullptr);
+  if (n != 0 && n != 4) {
+    set_error("%s: latent_to_ode_net weights must be given all together or not at all", who);
+    return SLODE_EINVAL;
+  }
+  if (n == 0 && !y0or) {
+    set_error("%s: neither latent_to_ode_net weights nor y0 / grad_y0 given", who);
+    return SLODE_EINVAL;
+  }
+  return SLODE_OK;
+}
+
+// W1[:,0] (stride L+1) -> contiguous copy in the device staging area (behind the packed weights)
+static int gather_w1t(const float* W1, int L, int H, float* dst, cudaStream_t stream) {
+  SLODE_CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(float), W1, sizeof(float) * (L + 1), sizeof(float), H,
+                                   cudaMemcpyDeviceToDevice, stream));
+  return SLODE_OK;
+}
+
+extern "C" int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S, const float* t, const float* z,
+                                      const float* W1, const float* b1, const float* Wg, const float* bg,
+                                      const float* Wd, const float* bd, const float* Wa, const float* ba,
+                                      const float* Wb, const float* bb, const float* y0, float* sol,
+                                      int64_t sol_stride_t, int64_t sol_stride_b, void* stream_) {
+  int rc = check_common("slode_latent_fixed_fwd", B, T, H, S);
+  if (rc) return rc;
+  if (B > 0) {
+    rc = check_latent("slode_latent_fixed_fwd", method, L, z, W1, b1, Wa, ba, Wb, bb, y0);
+    if (rc) return rc;
+  }
+  if (!t || !Wg || !bg || !Wd || !bd || (B > 0 && !sol)) {
+    set_error("slode_latent_fixed_fwd: null pointer");
+    return SLODE_EINVAL;
+  }
+  g_fwd_launches = 0;
+  if (B == 0) return SLODE_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PackGuard guard(stream);
+  if (guard.status) return guard.status;
+  float* w1t = guard.staging + 12288;
+  rc = gather_w1t(W1, L, H, w1t, stream);
+  if (rc) return rc;
+  const LatentSrc lat{z, L, W1, b1, Wa, ba, Wb, bb};
+  const FwdArgs a{method, B, T, t, nullptr, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, lat};
+  const PackSrc w{w1t, Wg, bg, Wd, bd};
+  rc = find_shape(H, S)->fwd(a, w, guard.staging);
+  if (rc == SLODE_OK) g_fwd_launches = 2;
+  return rc;
+}
+
+extern "C" int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H, int S, const float* t,
+                                      const float* z, const float* W1, const float* b1, const float* Wg,
+                                      const float* bg, const float* Wd, const float* bd, const float* Wa,
+                                      const float* ba, const float* Wb, const float* bb, const float* sol,
+                                      int64_t sol_stride_t, int64_t sol_stride_b, const float* grad_sol,
+                                      int64_t gsol_stride_t, int64_t gsol_stride_b, float* grad_z, float* grad_y0,
+                                      float* grad_params, void* stream_) {
+  int rc = check_common("slode_latent_fixed_bwd", B, T, H, S);
+  if (rc) return rc;
+  if (mode != SLODE_BWD_DISCRETE && mode != SLODE_BWD_TDE_ADJOINT) {
+    set_error("slode_latent_fixed_bwd: unknown mode %d", mode);
+    return SLODE_EINVAL;
+  }
+  if (B > 0) {
+    rc = check_latent("slode_latent_fixed_bwd", method, L, z, W1, b1, Wa, ba, Wb, bb, grad_y0);
+    if (rc) return rc;
+  }
+  if (!t || !Wg || !bg || !Wd || !bd || !grad_params || (B > 0 && (!sol || !grad_sol || !grad_z))) {
+    set_error("slode_latent_fixed_bwd: null pointer");
+    return SLODE_EINVAL;
+  }
+  g_bwd_launches = 0;
+  if (B == 0) return SLODE_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PackGuard guard(stream);
+  if (guard.status) return guard.status;
+  float* w1t = guard.staging + 12288;
+  rc = gather_w1t(W1, L, H, w1t, stream);
+  if (rc) return rc;
+  const LatentSrc lat{z, L, W1, b1, Wa, ba, Wb, bb};
+  const BwdArgs a{method, mode, B, T, t, nullptr, w1t, Wg, Wd, sol, sol_stride_t, sol_stride_b,
+                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, nullptr, grad_params, stream, guard.sms, lat, grad_z};
+  const PackSrc w{w1t, Wg, bg, Wd, bd};
+  rc = find_shape(H, S)->bwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_bwd_launches = 2;
   return rc;
 }

@@ -11,6 +11,16 @@ struct PackSrc {  // device pointers, torch Linear layouts
   const float *w1t, *Wg, *bg, *Wd, *bd;
 };
 
+// Optional fused prologue / epilogue.  With z given, the kernels compute
+// c = z W1[:,1:]^T + b1 themselves (and, backwards, dz, dW1[:,1:], db1); with the latent_to_ode_net weights given
+// as well, also x0 = sigmoid(Wb relu(Wa z + ba) + bb) (models/blackbox_ode.py:19-22,32-34) and its gradients.
+struct LatentSrc {
+  const float* z;                  // (B,L) row-major, or null: c / y0 are given instead
+  int L;
+  const float *W1, *b1;            // dynamics_hidden.weight (H, L+1) / bias (H)
+  const float *Wa, *ba, *Wb, *bb;  // latent_to_ode_net Linear(L,H) / Linear(H,S); null: y0 is given
+};
+
 struct FwdArgs {
   int method;
   int64_t B;
@@ -20,6 +30,7 @@ struct FwdArgs {
   int64_t st, sb;
   cudaStream_t stream;
   int sms;
+  LatentSrc lat;
 };
 
 struct BwdArgs {
@@ -33,6 +44,8 @@ struct BwdArgs {
   float *gy0, *gc, *gw;
   cudaStream_t stream;
   int sms;
+  LatentSrc lat;
+  float* gz;  // (B,L), fused mode only
 };
 
 // dopri5 forward (slode_dopri5_kernels.cuh); scratch pointers are filled in by the launcher

@@ -368,23 +368,162 @@ __device__ __forceinline__ PairIdx pair_index(int64_t tile, int64_t B) {
   return p;
 }
 
+// Sum K values (K a power of two <= 32) over the 32 lanes of the warp with ~K (not 5K) shuffles: in every round
+// each lane keeps half of its values and hands the other half to its partner, so after log2(K) rounds a lane
+// holds ONE value (index `slot`) summed over the lanes met so far; the remaining rounds are plain butterflies.
+// On return the lanes with (lane & (32/K - 1)) == 0 hold the warp totals of K distinct slots.
+template <int K>
+__device__ __forceinline__ float warp_sum_scatter(float (&v)[K], int lane, int& slot) {
+  int base = 0;
+  int n = K;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    if (n > 1) {
+      const int hn = n / 2;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int k = 0; k < K / 2; ++k) {
+        if (k < hn) {
+          const float mine = upper ? v[k + hn] : v[k];
+          const float give = upper ? v[k] : v[k + hn];
+          v[k] = mine + __shfl_xor_sync(0xffffffffu, give, off);
+        }
+      }
+      if (upper) base += hn;
+      n = hn;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+  slot = base;
+  return v[0];
+}
+// warp total of every slot added to dst(slot) (a shared-memory accumulator, or null to drop the slot)
+template <int K, class Dst>
+__device__ __forceinline__ void warp_reduce_to(float (&v)[K], int lane, Dst dst) {
+  int slot;
+  const float tot = warp_sum_scatter<K>(v, lane, slot);
+  if ((lane & (32 / K - 1)) == 0) {
+    float* p = dst(slot);
+    if (p) atomicAdd(p, tot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused prologue: c = z W1[:,1:]^T + b1 and x0 = latent_to_ode_net(z), weights staged in shared memory
+// ---------------------------------------------------------------------------------------------
+struct LatSmem {
+  float *Wz, *Wa, *b1, *ba, *Wb, *bb;  // Wz, Wa: [L][H] (transposed);  Wb: [H][S] (transposed)
+};
+__host__ __device__ inline int lat_floats(int L, int H, int S) { return 2 * L * H + 2 * H + H * S + S; }
+
+template <int H, int S>
+__device__ __forceinline__ LatSmem lat_stage(float* base, const LatentSrc& lat) {  // caller syncs afterwards
+  const int L = lat.L;
+  LatSmem ls;
+  ls.Wz = base;
+  ls.Wa = ls.Wz + L * H;
+  ls.b1 = ls.Wa + L * H;
+  ls.ba = ls.b1 + H;
+  ls.Wb = ls.ba + H;
+  ls.bb = ls.Wb + H * S;
+  const bool fx0 = lat.Wa != nullptr;
+  for (int i = threadIdx.x; i < L * H; i += kBlock) {
+    const int l = i / H, j = i % H;
+    ls.Wz[i] = lat.W1[j * (L + 1) + 1 + l];
+    ls.Wa[i] = fx0 ? lat.Wa[j * L + l] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < H; i += kBlock) {
+    ls.b1[i] = lat.b1[i];
+    ls.ba[i] = fx0 ? lat.ba[i] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < H * S; i += kBlock) ls.Wb[i] = fx0 ? lat.Wb[(i % S) * H + i / S] : 0.0f;
+  for (int i = threadIdx.x; i < S; i += kBlock) ls.bb[i] = fx0 ? lat.bb[i] : 0.0f;
+  return ls;
+}
+
+// hidden pre-activations of both small nets for the thread's two trajectories: c (dynamics) and ha (x0 net)
+template <int H, bool WANT_HA>
+__device__ __forceinline__ void lat_hidden(const LatSmem& ls, const LatentSrc& lat, const PairIdx& pi, f2 (&c2)[H],
+                                           f2 (&ha)[H]) {
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    c2[j] = bc(ls.b1[j]);
+    ha[j] = bc(ls.ba[j]);
+  }
+  const float* z0 = lat.z + pi.b0 * lat.L;
+  const float* z1 = lat.z + pi.b1 * lat.L;
+#pragma unroll 1
+  for (int l = 0; l < lat.L; ++l) {
+    const f2 zl = pk(__ldg(z0 + l), __ldg(z1 + l));
+    const float* wz = ls.Wz + l * H;
+    const float* wa = ls.Wa + l * H;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      c2[j] = fma2(bc(wz[j]), zl, c2[j]);
+      if (WANT_HA) ha[j] = fma2(bc(wa[j]), zl, ha[j]);
+    }
+  }
+}
+
+template <int H, int S>
+__device__ __forceinline__ Vec<S> lat_x0(const LatSmem& ls, const f2 (&ha)[H]) {
+  Vec<S> x;
+  f2 acc[S];
+#pragma unroll
+  SLODE_FOR_S acc[s] = bc(ls.bb[s]);
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    float p0, p1;
+    unpk(ha[j], p0, p1);
+    const f2 h = pk(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f));
+#pragma unroll
+    SLODE_FOR_S acc[s] = fma2(bc(ls.Wb[j * S + s]), h, acc[s]);
+  }
+#pragma unroll
+  SLODE_FOR_S {
+    float v0, v1;
+    unpk(mul2(acc[s], bc(kNegLog2e)), v0, v1);
+    x.v[s] = pk(sigmoid_from_scaled(v0), sigmoid_from_scaled(v1));
+  }
+  return x;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int H, int S, int METHOD>
 __global__ void __launch_bounds__(kBlock, SLODE_FWD_MINB)
 mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
-                     const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb) {
+                     const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, LatentSrc lat) {
+  extern __shared__ __align__(16) float fwd_dyn[];
+  LatSmem ls{};
+  if (lat.z) {
+    ls = lat_stage<H, S>(fwd_dyn, lat);
+    __syncthreads();
+  }
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
     f2 c2[H];
+    Vec<S> x;
+    if (lat.z) {
+      f2 ha[H];
+      if (lat.Wa) {
+        lat_hidden<H, true>(ls, lat, pi, c2, ha);
+        x = lat_x0<H, S>(ls, ha);
+      } else {
+        lat_hidden<H, false>(ls, lat, pi, c2, ha);
+        x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
+      }
+    } else {
 #pragma unroll
-    for (int j = 0; j < H; ++j) c2[j] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
+      for (int j = 0; j < H; ++j) c2[j] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
+      x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
+    }
     auto cj = [&](int j) { return c2[j]; };
     float* out0 = sol + pi.b0 * sb;
     float* out1 = sol + pi.b1 * sb;
-    Vec<S> x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
     vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
     float t0 = __ldg(tgrid);
     Vec<S> k1;
@@ -518,44 +657,13 @@ struct Sweep {
     }
   }
 
-  // Sum K values over the 32 lanes of the warp with ~K (not 5K) shuffles: in every round each lane keeps half
-  // of its values and hands the other half to its partner, so after 5 rounds lane L holds the warp total of
-  // value (L mod NV) for the values that are left.  Returns the lane's slot index; slot v of round-5 lives in
-  // v[0] of the lanes with (lane % 32) bit pattern selecting it.  Implemented for K <= 32 padded to a power of 2.
-  template <int K>
-  __device__ __forceinline__ static float warp_sum_scatter(float (&v)[K], int lane, int& slot) {
-    // K is a power of two >= 1
-    int base = 0;
-    int n = K;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      if (n > 1) {
-        const int hn = n / 2;
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int k = 0; k < K / 2; ++k) {
-          if (k < hn) {
-            const float mine = upper ? v[k + hn] : v[k];
-            const float give = upper ? v[k] : v[k + hn];
-            v[k] = mine + __shfl_xor_sync(0xffffffffu, give, off);
-          }
-        }
-        if (upper) base += hn;
-        n = hn;
-      } else {
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-      }
-    }
-    slot = base;
-    return v[0];
-  }
-
   // End of the sweep: for every hidden unit (uniform loop, all lanes busy) combine the recorded and the final
   // prefix sums into the sums over the evaluations where the unit was active,
   //     active throughout: final      turned off: record      turned on: final - record      never: 0
   // and turn them into dc_j (per trajectory), dw1t_j and dW_oj (warp reduction, one shared atomic per warp and
   // value).  The next unit's records are loaded while the current one is processed.
-  __device__ __forceinline__ void finish(BwdSmem<H, S>& sm, const float* __restrict__ rec, float* gc0, float* gc1) {
+  __device__ __forceinline__ void finish(BwdSmem<H, S>& sm, const float* __restrict__ rec, float* gc0, float* gc1,
+                                         bool gc_to_smem) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     constexpr int KR = (K2 + 1 <= 16) ? 16 : 32;  // values reduced per unit, padded to a power of two
@@ -625,18 +733,18 @@ struct Sweep {
       {
         float lo, hi;
         unpk(s1, lo, hi);
-        if (gc0) gc0[j] = lo;
-        if (gc1) gc1[j] = hi;
+        if (gc_to_smem) {
+          sm.c[j][tid] = s1;  // c_j is not needed any more: the fused epilogue picks dL/dc_j up from here
+        } else {
+          if (gc0) gc0[j] = lo;
+          if (gc1) gc1[j] = hi;
+        }
         unpk(s2, lo, hi);
         red[K2] = lo + hi;
       }
-      int slot;
-      const float tot = warp_sum_scatter<KR>(red, lane, slot);
-      // after the scatter-reduction the lanes 0, 32/KR, 2*32/KR, ... hold distinct slots; one lane per slot adds
-      if ((lane & (32 / KR - 1)) == 0 || KR == 32) {
-        if (slot < K2) atomicAdd(&sm.G[slot][j], tot);
-        else if (slot == K2) atomicAdd(&sm.gw1t[j], tot);
-      }
+      warp_reduce_to<KR>(red, lane, [&](int slot) -> float* {
+        return slot < K2 ? &sm.G[slot][j] : (slot == K2 ? &sm.gw1t[j] : nullptr);
+      });
     }
     // head biases: total of the cotangents over all evaluations
     {
@@ -649,12 +757,119 @@ struct Sweep {
         unpk(P[o], lo, hi);
         red[o] = lo + hi;
       }
-      int slot;
-      const float tot = warp_sum_scatter<KR>(red, lane, slot);
-      if (((lane & (32 / KR - 1)) == 0 || KR == 32) && slot < K2) atomicAdd(&sm.gb[slot], tot);
+      warp_reduce_to<KR>(red, lane, [&](int slot) -> float* { return slot < K2 ? &sm.gb[slot] : nullptr; });
     }
   }
 };
+
+// Fused epilogue of the reverse sweep (after Sweep::finish left dL/dc_j in sm.c): gradients of the two small
+// nets in front of the solve.
+//     dz_l     = sum_j dc_j W1z_jl (discrete mode only: odeint_adjoint gives z no gradient through the dynamics)
+//              + sum_j da_j Wa_jl,   da_j = [ha_j > 0] sum_s Wb_sj db_s,   db = dL/dx0 * x0 (1 - x0)
+//     dW1z_jl += dc_j z_l,  db1_j += dc_j,  dWa_jl += da_j z_l,  dba_j += da_j,  dWb_sj += db_s relu(ha_j),  dbb_s += db_s
+// The sums over trajectories go lane -> warp (scatter reduction) -> block accumulators in shared memory.
+template <int H, int S>
+__device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& ls, float* acc, const LatentSrc& lat,
+                                             const PairIdx& pi, bool discrete, const Vec<S>& lam, const Vec<S>& x0,
+                                             float* __restrict__ gz) {
+  static_assert(H <= 32, "one scatter reduction per group of H values");
+  constexpr int KR = (H <= 16) ? 16 : 32;
+  constexpr int KS = 16;
+  static_assert(S <= KS, "state dimension");
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int L = lat.L;
+  const bool fx0 = lat.Wa != nullptr;
+  float* gWz = acc;
+  float* gb1 = gWz + H * L;
+  float* gWa = gb1 + H;
+  float* gba = gWa + H * L;
+  float* gWb = gba + H;
+  float* gbb = gWb + S * H;
+  auto halves = [](f2 v) { float lo, hi; unpk(v, lo, hi); return lo + hi; };
+
+  f2 gcr[H], da[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    gcr[j] = sm.c[j][tid];
+    da[j] = 0ull;
+  }
+  if (fx0) {
+    f2 cdummy[H], ha[H];
+    lat_hidden<H, true>(ls, lat, pi, cdummy, ha);
+    Vec<S> db;
+#pragma unroll
+    SLODE_FOR_S db.v[s] = mul2(lam.v[s], fma2(neg2(x0.v[s]), x0.v[s], x0.v[s]));
+    f2 hr[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      float p0, p1;
+      unpk(ha[j], p0, p1);
+      hr[j] = pk(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f));
+      f2 a = 0ull;
+#pragma unroll
+      SLODE_FOR_S a = fma2(bc(ls.Wb[j * S + s]), db.v[s], a);
+      float a0, a1;
+      unpk(a, a0, a1);
+      da[j] = pk(p0 > 0.0f ? a0 : 0.0f, p1 > 0.0f ? a1 : 0.0f);
+    }
+#pragma unroll
+    SLODE_FOR_S {
+      float v[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(mul2(db.v[s], hr[k < H ? k : 0])) : 0.0f;
+      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gWb + s * H + slot : nullptr; });
+    }
+    {
+      float v[KS];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) v[k] = (k < S) ? halves(db.v[k < S ? k : 0]) : 0.0f;
+      warp_reduce_to<KS>(v, lane, [&](int slot) -> float* { return slot < S ? gbb + slot : nullptr; });
+    }
+    {
+      float v[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(da[k < H ? k : 0]) : 0.0f;
+      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gba + slot : nullptr; });
+    }
+  }
+  {
+    float v[KR];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(gcr[k < H ? k : 0]) : 0.0f;
+    warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gb1 + slot : nullptr; });
+  }
+  const float* z0 = lat.z + pi.b0 * L;
+  const float* z1 = lat.z + pi.b1 * L;
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const f2 zl = pk(__ldg(z0 + l), __ldg(z1 + l));
+    const float* wz = ls.Wz + l * H;
+    const float* wa = ls.Wa + l * H;
+    f2 dz = 0ull;
+    {
+      float v[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(mul2(gcr[k < H ? k : 0], zl)) : 0.0f;
+      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gWz + slot * L + l : nullptr; });
+    }
+    if (discrete) {
+#pragma unroll
+      for (int j = 0; j < H; ++j) dz = fma2(bc(wz[j]), gcr[j], dz);
+    }
+    if (fx0) {
+      float v[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(mul2(da[k < H ? k : 0], zl)) : 0.0f;
+      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gWa + slot * L + l : nullptr; });
+#pragma unroll
+      for (int j = 0; j < H; ++j) dz = fma2(bc(wa[j]), da[j], dz);
+    }
+    float d0, d1;
+    unpk(dz, d0, d1);
+    if (pi.ok0) gz[pi.b0 * L + l] = d0;
+    if (pi.ok1) gz[pi.b1 * L + l] = d1;
+  }
+}
 
 template <int H, int S, int METHOD, int MODE>
 __global__ void __launch_bounds__(kBlock, SLODE_BWD_MINB)
@@ -663,11 +878,22 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
                      const float* __restrict__ sol, int64_t st, int64_t sb,
                      const float* __restrict__ gsol, int64_t gst, int64_t gsb,
                      float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,
-                     float* __restrict__ flip_ws) {
+                     float* __restrict__ flip_ws, LatentSrc lat, float* __restrict__ grad_z) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem<H, S>& sm = *reinterpret_cast<BwdSmem<H, S>*>(smem_raw);
   constexpr int K2 = 2 * S;
   const int tid = threadIdx.x;
+  // fused mode: staged weights of the two small nets, then the block accumulators of their gradients
+  float* ext = reinterpret_cast<float*>(smem_raw + (sizeof(BwdSmem<H, S>) + 15) / 16 * 16);
+  LatSmem ls{};
+  float* lat_acc = nullptr;
+  int n_lat_acc = 0;
+  if (lat.z) {
+    ls = lat_stage<H, S>(ext, lat);
+    lat_acc = ext + lat_floats(lat.L, H, S);
+    n_lat_acc = lat.Wa ? lat_floats(lat.L, H, S) : (H * lat.L + H);
+    for (int i = tid; i < lat_floats(lat.L, H, S); i += kBlock) lat_acc[i] = 0.0f;
+  }
 
   for (int i = tid; i < H * K2; i += kBlock) {
     const int j = i / K2, o = i % K2;
@@ -689,9 +915,16 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     float* gc1 = pi.ok1 ? grad_c + pi.b1 * H : nullptr;
     // this thread's flip-record slots (re-used tile after tile)
     float* rec = flip_ws + ((size_t)blockIdx.x * kBlock + tid) * Sweep<H, S>::REC_PER_THREAD;
+    if (lat.z) {
+      f2 c2[H], ha[H];
+      lat_hidden<H, false>(ls, lat, pi, c2, ha);
 #pragma unroll
-    for (int j = 0; j < H; ++j)
-      sm.c[j][tid] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
+      for (int j = 0; j < H; ++j) sm.c[j][tid] = c2[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < H; ++j)
+        sm.c[j][tid] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
+    }
     auto cj = [&](int j) { return sm.c[j][tid]; };
     const float* xs0 = sol + pi.b0 * sb;
     const float* xs1 = sol + pi.b1 * sb;
@@ -863,16 +1096,25 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       t1 = t0;
     }
 
+    const bool fused = lat.z != nullptr;
     if (started) {
-      sw.finish(sm, rec, gc0, gc1);  // a masked-off half carries zero cotangents: it only adds zeros
+      sw.finish(sm, rec, gc0, gc1, fused);  // a masked-off half carries zero cotangents: it only adds zeros
     } else {  // T == 1: no evaluation at all
 #pragma unroll
       for (int j = 0; j < H; ++j) {
-        if (gc0) gc0[j] = 0.0f;
-        if (gc1) gc1[j] = 0.0f;
+        if (fused) {
+          sm.c[j][tid] = 0ull;
+        } else {
+          if (gc0) gc0[j] = 0.0f;
+          if (gc1) gc1[j] = 0.0f;
+        }
       }
     }
-    vstore2<S>(grad_y0 + pi.b0 * S, pi.ok0, grad_y0 + pi.b1 * S, pi.ok1, lam);
+    if (fused) {
+      const Vec<S> x0 = vload2<S>(xs0, xs1);
+      lat_epilogue<H, S>(sm, ls, lat_acc, lat, pi, MODE == SLODE_BWD_DISCRETE, lam, x0, grad_z);
+    }
+    if (!fused || !lat.Wa) vstore2<S>(grad_y0 + pi.b0 * S, pi.ok0, grad_y0 + pi.b1 * S, pi.ok1, lam);
   }
 
   __syncthreads();
@@ -887,6 +1129,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     const int base = (tid < S) ? (H + S * H + tid) : (H + S * H + S + S * H + (tid - S));
     atomicAdd(grad_w + base, sm.gb[tid]);
   }
+  // fused mode: [ dW1z (H*L) | db1 (H) | dWa (H*L) | dba (H) | dWb (S*H) | dbb (S) ] follow the five segments above
+  for (int i = tid; i < n_lat_acc; i += kBlock) atomicAdd(grad_w + (H + 2 * (S * H + S)) + i, lat_acc[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -895,16 +1139,16 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
 template <int H, int S, int METHOD>
 int launch_fwd(const FwdArgs& a) {
   auto kern = mlp_fixed_fwd_kernel<H, S, METHOD>;
-  static int blocks_per_sm = 0;  // per instantiation
-  if (blocks_per_sm == 0) {
-    int n = 0;
-    SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, 0));
-    blocks_per_sm = std::max(n, 1);
-  }
+  const size_t smem = a.lat.z ? sizeof(float) * lat_floats(a.lat.L, H, S) : 0;
+  if (smem > 48 * 1024)
+    SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks_per_sm = 0;
+  SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, smem));
+  blocks_per_sm = std::max(blocks_per_sm, 1);
   const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
   // whole waves of resident blocks; tiles are handed out grid-stride
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)a.sms * blocks_per_sm);
-  kern<<<grid, kBlock, 0, a.stream>>>(a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb);
+  kern<<<grid, kBlock, smem, a.stream>>>(a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb, a.lat);
   SLODE_CUDA_TRY(cudaGetLastError());
   return SLODE_OK;
 }
@@ -912,20 +1156,18 @@ int launch_fwd(const FwdArgs& a) {
 template <int H, int S, int METHOD, int MODE>
 int launch_bwd(const BwdArgs& a) {
   auto kern = mlp_fixed_bwd_kernel<H, S, METHOD, MODE>;
-  const size_t smem = sizeof(BwdSmem<H, S>);
-  static int blocks_per_sm = 0;  // per instantiation
-  if (blocks_per_sm == 0) {
-    SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int n = 0;
-    SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, smem));
-    blocks_per_sm = std::max(n, 1);
-  }
+  const size_t smem = (sizeof(BwdSmem<H, S>) + 15) / 16 * 16 +
+                      (a.lat.z ? 2 * sizeof(float) * lat_floats(a.lat.L, H, S) : 0);
+  SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks_per_sm = 0;
+  SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, smem));
+  blocks_per_sm = std::max(blocks_per_sm, 1);
   const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)a.sms * blocks_per_sm);
   float* ws = flip_workspace(sizeof(float) * (size_t)grid * kBlock * Sweep<H, S>::REC_PER_THREAD);
   if (!ws) return SLODE_ECUDA;
   kern<<<grid, kBlock, smem, a.stream>>>(a.B, a.T, a.t, a.c, a.w1t, a.Wg, a.Wd, a.sol, a.st, a.sb, a.gsol, a.gst,
-                                         a.gsb, a.gy0, a.gc, a.gw, ws);
+                                         a.gsb, a.gy0, a.gc, a.gw, ws, a.lat, a.gz);
   SLODE_CUDA_TRY(cudaGetLastError());
   return SLODE_OK;
 }

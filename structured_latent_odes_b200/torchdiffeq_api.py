@@ -210,6 +210,101 @@ class _MlpFixedSolve(torch.autograd.Function):
         return grad_y0, grad_c, gw1t, gWg, gbg, gWd, gbd, None, None, None, None
 
 
+class _LatentFixedSolve(torch.autograd.Function):
+    """The fused solve: c = z W1[:,1:]^T + b1 (and optionally x0 = latent_to_ode_net(z)) computed inside the solver
+    kernels, their gradients inside the reverse sweep.  ``x0net`` is (Wa, ba, Wb, bb) or four Nones (then y0 is an
+    input)."""
+
+    @staticmethod
+    def forward(ctx, z, y0, W1, b1, Wg, bg, Wd, bd, Wa, ba, Wb, bb, t, method_id, mode, layout):
+        B, L = z.shape
+        H = W1.shape[0]
+        S = Wg.shape[0]
+        T = t.numel()
+        fx0 = Wa is not None
+        zc = z.detach().to(torch.float32).contiguous()
+        w = [x.detach().contiguous() for x in (W1, b1, Wg, bg, Wd, bd)]
+        x0w = [x.detach().contiguous() for x in (Wa, ba, Wb, bb)] if fx0 else [None] * 4
+        y0c = None if fx0 else y0.detach().contiguous()
+        if layout == "bts":
+            sol = torch.empty((B, T, S), device=z.device, dtype=torch.float32).permute(1, 0, 2)
+        else:
+            sol = torch.empty((T, B, S), device=z.device, dtype=torch.float32)
+        with torch.cuda.device(z.device), _timed("fwd"):
+            rc = _cabi.lib().slode_latent_fixed_fwd(
+                method_id, B, T, L, H, S, _ptr(t), _ptr(zc), *[_ptr(x) for x in w], *[_ptr(x) for x in x0w], _ptr(y0c),
+                _ptr(sol), sol.stride(0), sol.stride(1), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_latent_fixed_fwd")
+        ctx.save_for_backward(zc, *w, t, sol, *(x0w if fx0 else []))
+        ctx.cfg = (method_id, mode, fx0)
+        return sol
+
+    @staticmethod
+    def backward(ctx, grad_sol):
+        method_id, mode, fx0 = ctx.cfg
+        zc, W1, b1, Wg, bg, Wd, bd, t, sol, *x0w = ctx.saved_tensors
+        if not fx0:
+            x0w = [None] * 4
+        T, B, S = sol.shape
+        H, L = W1.shape[0], zc.shape[1]
+        strides = _dense_tbs_strides(grad_sol)
+        if strides is None or grad_sol.dtype != torch.float32:
+            grad_sol = grad_sol.to(torch.float32).contiguous()
+            strides = (grad_sol.stride(0), grad_sol.stride(1))
+        dev = sol.device
+        grad_z = torch.empty((B, L), device=dev, dtype=torch.float32)
+        grad_y0 = None if fx0 else torch.empty((B, S), device=dev, dtype=torch.float32)
+        nbase = H + 2 * (S * H + S)
+        n = nbase + H * L + H + ((H * L + H + S * H + S) if fx0 else 0)
+        gp = torch.zeros(n, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev), _timed("bwd"):
+            rc = _cabi.lib().slode_latent_fixed_bwd(
+                method_id, mode, B, T, L, H, S, _ptr(t), _ptr(zc), _ptr(W1), _ptr(b1), _ptr(Wg), _ptr(bg), _ptr(Wd),
+                _ptr(bd), *[_ptr(x) for x in x0w], _ptr(sol), sol.stride(0), sol.stride(1), _ptr(grad_sol), strides[0],
+                strides[1], _ptr(grad_z), _ptr(grad_y0), _ptr(gp), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_latent_fixed_bwd")
+        o = 0
+
+        def take(*shape):
+            nonlocal o
+            k = 1
+            for d in shape:
+                k *= d
+            v = gp[o:o + k].view(*shape)
+            o += k
+            return v
+
+        gw1t, gWg, gbg, gWd, gbd = take(H), take(S, H), take(S), take(S, H), take(S)
+        gW1z, gb1 = take(H, L), take(H)
+        gW1 = torch.cat([gw1t[:, None], gW1z], dim=1)
+        gx0 = (take(H, L), take(H), take(S, H), take(S)) if fx0 else (None,) * 4
+        if mode == _cabi.BWD_TDE_ADJOINT and not fx0:
+            grad_z = None  # odeint_adjoint: the constants get no gradient through the dynamics (SURVEY F5)
+        return (grad_z, grad_y0, gW1, gb1, gWg, gbg, gWd, gbd, *gx0, None, None, None, None)
+
+
+def solve_latent(z, dynamics, x0_net, t, method, adjoint, layout="tbs"):
+    """Whole ``OdeModel.solve_ODE`` body in two kernels: returns ``(T,B,S)``.  ``x0_net`` is the reference's
+    ``latent_to_ode_net`` Sequential(Linear, ReLU, Linear, Sigmoid)."""
+    if method not in FIXED_METHODS:
+        raise NotImplementedError(method)
+    if not z.is_cuda:
+        raise RuntimeError("structured_latent_odes_b200 runs on CUDA tensors only (no CPU fallback); "
+                           f"got z on {z.device}")
+    hid, gro, deg = dynamics.dynamics_hidden, dynamics.dyanamics_growth, dynamics.dyanmics_degradation
+    la, lb = x0_net[0], x0_net[2]
+    H, S = hid.out_features, gro.out_features
+    if not _cabi.lib().slode_mlp_supported(H, S):
+        raise NotImplementedError(f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled kernel; available (H,S): "
+                                  f"{_cabi.supported_shapes()}. There is no generic fallback.")
+    if la.out_features != H or lb.in_features != H or lb.out_features != S or la.in_features != z.shape[1]:
+        raise ValueError("latent_to_ode_net layer sizes do not match the dynamics")
+    t = t.detach().to(device=z.device, dtype=torch.float32).contiguous()
+    mode = _cabi.BWD_TDE_ADJOINT if adjoint else _cabi.BWD_DISCRETE
+    return _LatentFixedSolve.apply(z, None, hid.weight, hid.bias, gro.weight, gro.bias, deg.weight, deg.bias,
+                                   la.weight, la.bias, lb.weight, lb.bias, t, _cabi.METHODS[method], mode, layout)
+
+
 class SolverStats:
     """Bookkeeping of the last dopri5 solve on this process (``last_dopri5_stats``): accepted / rejected step
     counts, RHS evaluations per trajectory, and -- when ``options={"log_steps": True}`` -- the (t0, dt, accepted)
@@ -287,13 +382,9 @@ def _solve_blackbox(func, y0, t, method, mode, layout):
             f"{_cabi.supported_shapes()}. There is no generic fallback.")
     if z.device != y0.device or hid.weight.device != y0.device:
         raise RuntimeError("func tensors and y0 must live on the same CUDA device")
-    W1 = hid.weight
-    if mode == _cabi.BWD_TDE_ADJOINT:
-        z = z.detach()  # odeint_adjoint: constants are not in adjoint_params
-    # time-invariant part of the hidden pre-activation: a plain (B,L)x(L,H) GEMM -> cuBLAS
-    c = torch.addmm(hid.bias, z.to(torch.float32), W1[:, 1:].t())
-    return _MlpFixedSolve.apply(y0, c, W1[:, 0], gro.weight, gro.bias, deg.weight, deg.bias, t,
-                                _cabi.METHODS[method], mode, layout)
+    # the time-invariant part of the hidden pre-activation, c = z W1[:,1:]^T + b1, is computed inside the kernels
+    return _LatentFixedSolve.apply(z, y0, hid.weight, hid.bias, gro.weight, gro.bias, deg.weight, deg.bias,
+                                   None, None, None, None, t, _cabi.METHODS[method], mode, layout)
 
 
 class _MlpDopri5Solve(torch.autograd.Function):

@@ -17,7 +17,7 @@ def test_raw_pointer_call_matches_the_python_api():
     p = U.make_product(o)
     B, T, L, H, S = 300, 86, 15, 25, 5
     z = torch.randn(B, L, device="cuda")
-    want = p.solve_ODE(z).permute(1, 0, 2).contiguous()
+    want = p.solve_ODE(z).detach().permute(1, 0, 2).contiguous()
     d = p.dynamics
     W1 = d.dynamics_hidden.weight.detach()
     c = torch.addmm(d.dynamics_hidden.bias.detach(), z, W1[:, 1:].t()).contiguous()
@@ -34,5 +34,18 @@ def test_raw_pointer_call_matches_the_python_api():
                                 sol.data_ptr(), B * S, S, ctypes.c_void_p(s.cuda_stream))
     assert rc == 0, L_.slode_last_error()
     s.synchronize()
-    assert torch.equal(sol, want)
+    # the Python API runs the FUSED entry point (c and x0 computed inside the kernel): same numbers to rounding
+    assert U.rel_err(sol, want) < 1e-6
     assert L_.slode_query(_cabi.Q_FWD_LAUNCHES) >= 1
+    # the fused entry point with raw pointers: bit-identical to the Python API
+    n0, n2 = p.latent_to_ode_net[0], p.latent_to_ode_net[2]
+    sol2 = torch.empty(T, B, S, device="cuda")
+    rc = L_.slode_latent_fixed_fwd(_cabi.METHOD_RK4, B, T, L, H, S, p.times.data_ptr(), z.data_ptr(),
+                                   W1.contiguous().data_ptr(), d.dynamics_hidden.bias.detach().data_ptr(),
+                                   Wg.data_ptr(), bg.data_ptr(), Wd.data_ptr(), bd.data_ptr(),
+                                   n0.weight.detach().data_ptr(), n0.bias.detach().data_ptr(),
+                                   n2.weight.detach().data_ptr(), n2.bias.detach().data_ptr(), None,
+                                   sol2.data_ptr(), B * S, S, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, L_.slode_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(sol2, want)
