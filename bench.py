@@ -48,17 +48,19 @@ def algorithmic_flops(method: str, T: int, H: int, S: int):
     evals = {"euler": steps, "midpoint": 2 * steps, "rk4": 3 * steps + 1}[method]
     mlp = 2 * H + 4 * H * S + 2 * S
     combine = {"euler": 2 * S, "midpoint": 4 * S, "rk4": 16 * S}[method]
-    fwd = evals * mlp + steps * (stages * 2 * S + combine)
+    prologue = 2 * L * H * 2 + 2 * H * S  # c = z W1z^T + b1, x0 net (once per trajectory)
+    fwd = evals * mlp + steps * (stages * 2 * S + combine) + prologue
     # per stage: cotangents of the head pre-activations (10S), P/Q prefix sums (8S), adjoint update (6S);
     # per hidden unit: two snapshots (gate flip + end of sweep) of 2 * (4*2S + 3*2S) flop.
-    bwd = fwd + steps * stages * 24 * S + H * 2 * (14 * 2 * S)
+    # ... plus the fused epilogue: dz and the outer products dc z^T, da z^T, db relu(ha)^T (once per trajectory)
+    bwd = fwd + steps * stages * 24 * S + H * 2 * (14 * 2 * S) + 2 * (4 * L * H + 2 * H * S)
     return float(fwd), float(bwd)
 
 
 def algorithmic_bytes(T: int, H: int, S: int):
-    """(forward, backward) HBM bytes per trajectory: fwd reads c (H) + y0 (S), writes sol (T*S);
-    bwd reads sol + grad_sol + c, writes grad_y0 + grad_c."""
-    return 4.0 * (H + S + T * S), 4.0 * (2 * T * S + H + S + H)
+    """(forward, backward) HBM bytes per trajectory of the fused path: fwd reads z (L), writes sol (T*S);
+    bwd reads sol + grad_sol + z, writes grad_z."""
+    return 4.0 * (L + T * S), 4.0 * (2 * T * S + 2 * L)
 
 
 # ---------------------------------------------------------------------------------------------------------
