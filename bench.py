@@ -183,7 +183,7 @@ def run_reference_arm(args):
 
 def workload_config(args, B_per_gpu, n):
     return {"workload": "configs[1] blackbox: 2^20 trajectories/GPU x 100 obs times, fp32 rk4(3/8) fwd+bwd",
-            "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L,
+            "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L, "sol_layout": getattr(args, "layout", "tbs"),
             "ode_hidden_dim": H, "ode_state_dim": S, "solver": args.method,
             "gradient": "odeint_adjoint emulation" if args.adjoint else "discrete adjoint (odeint + autograd parity)",
             "parallelism": f"trajectory-sharded x{n}, one flat all-reduce of parameter gradients",
@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8192, help="trajectories per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--layout", default="tbs", choices=["tbs", "bts"],
+                    help="storage of the resident step's solution: (T,B,S) torchdiffeq's, or (B,T,S) the decoder's")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -232,14 +234,17 @@ def main():
     torch.manual_seed(12)  # reference seed (config_cvs.py:28); identical weights on every rank
     model = slode.OdeModel()
     model.init_with_params(times=torch.arange(0.0, T, 1.0, device=dev), ode_state_dim=S, latent_dim=L,
-                           ode_hidden_dim=H, adjoint_solver=args.adjoint, solver=args.method, device=dev)
+                           ode_hidden_dim=H, adjoint_solver=args.adjoint, solver=args.method, device=dev,
+                           layout=args.layout)
     model = model.to(dev)
     params = [p for k, p in model.named_parameters()]
     reducer = sharding.FlatGradReducer(params)
 
     g = torch.Generator(device=dev).manual_seed(12 + rank)
     z = torch.randn(B, L, device=dev, generator=g)
-    G = torch.randn(T, B, S, device=dev, generator=g).permute(1, 0, 2)  # upstream dL/dsol, resident
+    # upstream dL/dsol, resident, in the same storage layout as the solution
+    G = (torch.randn(B, T, S, device=dev, generator=g) if args.layout == "bts"
+         else torch.randn(T, B, S, device=dev, generator=g).permute(1, 0, 2))
     launches = [0]
     lib = _cabi.lib()
 
@@ -281,17 +286,18 @@ def main():
     # ---- end to end: pinned host inputs -> loss + gradients back on the host --------------------------------
     gc = torch.Generator().manual_seed(100 + rank)
     z_host = torch.randn(B, L, generator=gc).pin_memory()
-    y_host = torch.rand(B, T, O, generator=gc).pin_memory()
+    y_host = torch.rand(B, O, T, generator=gc).pin_memory()   # observations as batch_to_device hands them over
     Wq = (torch.randn(O, S, generator=torch.Generator().manual_seed(7)) * 0.3).to(dev)
     nchunk = max(1, args.e2e_chunks)
     bounds = [sharding.shard_bounds(B, i, nchunk) for i in range(nchunk)]
     copy_stream = torch.cuda.Stream()
     out_host = torch.empty(1 + reducer.numel, dtype=torch.float32).pin_memory()
     zbuf = [torch.empty(bounds[0][1] - bounds[0][0], L, device=dev) for _ in range(2)]
-    ybuf = [torch.empty(bounds[0][1] - bounds[0][0], T, O, device=dev) for _ in range(2)]
+    ybuf = [torch.empty(bounds[0][1] - bounds[0][0], O, T, device=dev) for _ in range(2)]
 
     def step_e2e():
         """Chunked, double-buffered: chunk k+1 is copied on the copy stream while chunk k is solved."""
+        model.layout = "bts"  # the decoder heads read the solution (B,T,S)-contiguous
         model.zero_grad(set_to_none=True)
         main = torch.cuda.current_stream()
         loss_acc = torch.zeros((), device=dev)
@@ -319,7 +325,8 @@ def main():
             main.wait_event(ready[s])
             zc, yc = zbuf[s][: hi - lo], ybuf[s][: hi - lo]
             sol = model.solve_ODE(zc)
-            loss = ((sol @ Wq.t()) - yc).square().sum() / (B * T * O)
+            (mu,) = slode.decoder_heads(sol, (Wq,))          # q50 head, (n,O,T) like Decoder.forward
+            loss = (mu - yc).square().sum() / (B * T * O)
             loss.backward()
             loss_acc += loss.detach()
             ev = torch.cuda.Event()
@@ -333,6 +340,7 @@ def main():
     for _ in range(3):
         step_e2e()
     sync_all()
+    model.layout = args.layout
     e0.record()
     for _ in range(args.steps):
         step_e2e()
@@ -370,7 +378,7 @@ def main():
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t_e2e.item()) / args.steps,
-                    "what": f"pinned z (B,{L}) + observations (B,{T},{O}) -> solve -> q50 head + MSE -> backward -> "
+                    "what": f"pinned z (B,{L}) + observations (B,{O},{T}) -> solve -> q50 head (slode_heads) + MSE -> backward -> "
                             f"loss + {reducer.numel} parameter gradients on the host; {nchunk} double-buffered chunks"},
             "gpu_launches": n_launches,
             "roofline": {"bound": "fp32", "kernel": "mlp_fixed_bwd_kernel (reverse sweep, dominant)",

@@ -195,6 +195,26 @@ int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S,
                          float* grad_y0, float* grad_c, float* grad_w,
                          void* stream);
 
+/*
+ * Decoder heads on the latent trajectories; replaces, for all heads at once,
+ *     mu_q = Linear_q(solution).permute(0, 2, 1)            models/decoders.py:45-47 (Decoder: q50, q75, q25)
+ *     mean = output_mean(solution).permute(0, 2, 1)         models/decoders.py:86     (GaussianDecoder)
+ *   sol   element (t,b,s) at sol[t*sol_stride_t + b*sol_stride_b + s]
+ *   W     (NQ, O, S) contiguous: the NQ bias-free Linear(S -> O) weights stacked
+ *   mu    out, (NQ, B, O, T) contiguous: mu[q] is head q in the reference's (B, obs_dim, T) layout
+ * Backward: grad_mu (NQ,B,O,T) -> grad_sol (written, own strides) and grad_W (NQ,O,S) ACCUMULATED (caller
+ * zero-fills).  ode_state_dim in {4, 5, 8}, obs_dim <= 8, NQ <= 3.
+ */
+int slode_heads_fwd(int64_t B, int T, int S, int O, int NQ,
+                    const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                    const float* W, float* mu, void* stream);
+
+int slode_heads_bwd(int64_t B, int T, int S, int O, int NQ,
+                    const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                    const float* W, const float* grad_mu,
+                    float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
+                    float* grad_W, void* stream);
+
 /* element types of the CVS entry points */
 #define SLODE_F32 0
 #define SLODE_F64 1

@@ -1,0 +1,116 @@
+"""Host-side mirror of the reference's decoders (``models/decoders.py``) on top of the fused kernels.
+
+Same class names, constructor signature ``(config, times, latent_dim, device)``, attribute names
+(``ode_model``, ``output_q50`` / ``output_q75`` / ``output_q25`` / ``output_mean``, ``constant_std``), ``state_dict``
+keys and return tuples as the reference:
+
+  Decoder.forward(z)          -> solution_xt (B,T,S), mu_75, mu_50, mu_25, std   each (B, obs_dim, T)   :42-54
+  GaussianDecoder.forward(z)  -> solution_xt, mean, std                                                :84-91
+
+The latent solve runs in the fused solver kernels (``OdeModel.solve_ODE``), stored (B,T,S)-contiguous, and all
+heads are produced by ONE pass over the trajectories in their final (B,O,T) layout (``slode_heads_fwd`` / ``_bwd``)
+instead of one tiny-K matmul + permute per head.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _cabi
+from .blackbox_ode import OdeModel
+
+__all__ = ["Decoder", "GaussianDecoder", "decoder_heads"]
+
+
+class _Heads(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sol, W):
+        """sol: (B,T,S) view (any strides with unit stride in S); W: (NQ,O,S) -> mu (NQ,B,O,T)."""
+        B, T, S = sol.shape
+        NQ, O, _ = W.shape
+        if not sol.is_cuda:
+            raise RuntimeError("structured_latent_odes_b200 runs on CUDA tensors only (no CPU fallback)")
+        if sol.dtype != torch.float32 or (S > 1 and sol.stride(2) != 1):
+            sol = sol.to(torch.float32).contiguous()
+        Wc = W.detach().to(torch.float32).contiguous()
+        mu = torch.empty((NQ, B, O, T), device=sol.device, dtype=torch.float32)
+        with torch.cuda.device(sol.device):
+            rc = _cabi.lib().slode_heads_fwd(B, T, S, O, NQ, sol.data_ptr(), sol.stride(1), sol.stride(0), Wc.data_ptr(),
+                                             mu.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_heads_fwd")
+        ctx.save_for_backward(sol, Wc)
+        return mu
+
+    @staticmethod
+    def backward(ctx, grad_mu):
+        sol, Wc = ctx.saved_tensors
+        B, T, S = sol.shape
+        NQ, O, _ = Wc.shape
+        grad_mu = grad_mu.to(torch.float32).contiguous()
+        grad_sol = torch.empty((B, T, S), device=sol.device, dtype=torch.float32)
+        grad_W = torch.zeros_like(Wc)
+        with torch.cuda.device(sol.device):
+            rc = _cabi.lib().slode_heads_bwd(B, T, S, O, NQ, sol.data_ptr(), sol.stride(1), sol.stride(0), Wc.data_ptr(),
+                                             grad_mu.data_ptr(), grad_sol.data_ptr(), grad_sol.stride(1),
+                                             grad_sol.stride(0), grad_W.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_heads_bwd")
+        return grad_sol, grad_W
+
+
+def decoder_heads(solution, weights):
+    """``[Linear_q(solution).permute(0, 2, 1) for q]`` for bias-free ``Linear(S -> O)`` weights, in one kernel."""
+    W = torch.stack(list(weights), dim=0)
+    mu = _Heads.apply(solution, W)
+    return [mu[q] for q in range(W.shape[0])]
+
+
+def _make_ode_model(config, times, latent_dim, device):
+    m = OdeModel()
+    m.init_with_params(times=times, ode_state_dim=config.ode_state_dim, latent_dim=latent_dim,
+                       ode_hidden_dim=config.ode_hidden_dim, adjoint_solver=config.adjoint_solver, solver=config.solver,
+                       device=device, layout="bts")
+    return m
+
+
+class Decoder(nn.Module):
+    def __init__(self, config, times, latent_dim, device):
+        super().__init__()
+        self.times = times
+        self.ode_state_dim = config.ode_state_dim
+        self.obs_dim = config.obs_dim
+        self.latent_dim = latent_dim
+        self.ode_hidden_dim = config.ode_hidden_dim
+        self.ode_model = _make_ode_model(config, times, latent_dim, device)
+        self.output_q50 = nn.Sequential(nn.Linear(self.ode_state_dim, self.obs_dim, bias=False))
+        self.output_q75 = nn.Sequential(nn.Linear(self.ode_state_dim, self.obs_dim, bias=False))
+        self.output_q25 = nn.Sequential(nn.Linear(self.ode_state_dim, self.obs_dim, bias=False))
+        self.constant_std = nn.Parameter(torch.ones(self.obs_dim, len(self.times)) * config.constant_std,
+                                         requires_grad=True)
+
+    def forward(self, z):
+        solution = self.ode_model.solve_ODE(z=z)
+        mu_50, mu_75, mu_25 = decoder_heads(solution, (self.output_q50[0].weight, self.output_q75[0].weight,
+                                                       self.output_q25[0].weight))
+        std = torch.ones_like(mu_50) * nn.functional.softplus(self.constant_std)
+        return solution, mu_75, mu_50, mu_25, std
+
+
+class GaussianDecoder(nn.Module):
+    def __init__(self, config, times, latent_dim, device):
+        super().__init__()
+        self.times = times
+        self.ode_state_dim = config.ode_state_dim
+        self.obs_dim = config.obs_dim
+        self.latent_dim = latent_dim
+        self.ode_hidden_dim = config.ode_hidden_dim
+        self.ode_model = _make_ode_model(config, times, latent_dim, device)
+        self.output_mean = nn.Sequential(nn.Linear(self.ode_state_dim, self.obs_dim, bias=False))
+        self.constant_std = nn.Parameter(torch.ones(self.obs_dim, len(self.times)) * config.constant_std,
+                                         requires_grad=True)
+
+    def forward(self, z):
+        solution = self.ode_model.solve_ODE(z=z)
+        (mean,) = decoder_heads(solution, (self.output_mean[0].weight,))
+        std = torch.ones_like(mean) * nn.functional.softplus(self.constant_std)
+        return solution, mean, std

@@ -1,0 +1,88 @@
+"""Decoder mirrors (a9: the boundary consumer of the solve) against the oracle's QuantileHeads, which is itself
+pinned on the reference's real ``Decoder`` class (tests/test_oracle_golden.py)."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+import slode_testutil as U
+from oracle import shims, slode_port
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(shape, method, adjoint, O):
+    L, H, S, times = U.SHAPES[shape]
+    return shims._Munch(obs_dim=O, system_input_dim=0, ode_state_dim=S, ode_hidden_dim=H, adjoint_solver=adjoint,
+                        solver=method, constant_std=1e-2, seq_len=len(times))
+
+
+@pytest.mark.parametrize("shape,O,method,adjoint", [("cvs", 3, "midpoint", True), ("chal", 4, "rk4", False),
+                                                    ("proc", 4, "midpoint", True)])
+def test_decoder_matches_oracle_heads_and_gradients(shape, O, method, adjoint):
+    import structured_latent_odes_b200 as slode
+    L, H, S, times = U.SHAPES[shape]
+    o_ode = U.make_oracle(shape, method, adjoint)
+    torch.manual_seed(4)
+    heads = slode_port.QuantileHeads(o_ode, O, len(times))
+    dec = slode.Decoder(_cfg(shape, method, adjoint, O), times.cuda(), L, "cuda")
+    sd = {"ode_model." + k: v for k, v in o_ode.state_dict().items()}
+    sd.update({k: v for k, v in heads.state_dict().items() if not k.startswith("ode_model.")})
+    dec.load_state_dict(sd)
+    dec = dec.cuda()
+    g = torch.Generator().manual_seed(8)
+    B = 77
+    z = torch.randn(B, L, generator=g)
+    G = [torch.randn(B, O, len(times), generator=g) for _ in range(3)]
+
+    zo = z.clone().requires_grad_(True)
+    sol_o, q75_o, q50_o, q25_o, std_o = heads(zo)
+    (q75_o * G[0] + q50_o * G[1] + q25_o * G[2]).sum().backward()
+    zp = z.cuda().requires_grad_(True)
+    sol_p, q75_p, q50_p, q25_p, std_p = dec(zp)
+    assert q50_p.shape == (B, O, len(times)) and sol_p.shape == (B, len(times), S)
+    (q75_p * G[0].cuda() + q50_p * G[1].cuda() + q25_p * G[2].cuda()).sum().backward()
+    for a, b in ((sol_p, sol_o), (q75_p, q75_o), (q50_p, q50_o), (q25_p, q25_o), (std_p, std_o)):
+        assert U.rel_err(a, b) < 1e-5
+    assert U.rel_err(zp.grad, zo.grad) < 1e-5
+    go = dict(heads.named_parameters())
+    for k, p in dec.named_parameters():
+        if ".prod." in k or ".degr." in k or p.grad is None:
+            continue
+        ref = go[k].grad
+        assert ref is not None, k
+        assert U.rel_err(p.grad, ref) < 1e-5, (k, U.rel_err(p.grad, ref))
+
+
+def test_gaussian_decoder_and_raw_heads():
+    import structured_latent_odes_b200 as slode
+    L, H, S, times = U.SHAPES["cvs"]
+    dec = slode.GaussianDecoder(_cfg("cvs", "midpoint", True, 3), times.cuda(), L, "cuda").cuda()
+    z = torch.randn(33, L, device="cuda")
+    sol, mean, std = dec(z)
+    want = (sol @ dec.output_mean[0].weight.t()).permute(0, 2, 1)
+    assert U.rel_err(mean, want) < 1e-6 and std.shape == mean.shape
+    # heads on a (T,B,S)-contiguous solution (strided view) and ragged sizes
+    x = torch.randn(7, 130, 5, device="cuda").permute(1, 0, 2).requires_grad_(True)
+    W = [torch.randn(4, 5, device="cuda", requires_grad=True) for _ in range(2)]
+    mus = slode.decoder_heads(x, W)
+    ref = [(x @ w.t()).permute(0, 2, 1) for w in W]
+    G = [torch.randn_like(m) for m in mus]
+    gx, gw0, gw1 = torch.autograd.grad(sum((m * g).sum() for m, g in zip(mus, G)), [x] + W)
+    rx, rw0, rw1 = torch.autograd.grad(sum((m * g).sum() for m, g in zip(ref, G)), [x] + W)
+    for a, b in zip(mus + [gx, gw0, gw1], ref + [rx, rw0, rw1]):
+        assert U.rel_err(a, b) < 1e-5
+
+
+@pytest.mark.skipif(not shims.reference_available(), reason="/root/reference only exists in the build container")
+def test_state_dict_keys_equal_reference_decoder():
+    import structured_latent_odes_b200 as slode
+    _, dec_ref = shims.import_reference_blackbox()
+    L, H, S, times = U.SHAPES["cvs"]
+    cfg = _cfg("cvs", "midpoint", True, 3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = dec_ref.Decoder(config=cfg, latent_dim=L, times=times, device="cpu")
+        gref = dec_ref.GaussianDecoder(config=cfg, latent_dim=L, times=times, device="cpu")
+    assert sorted(ref.state_dict()) == sorted(slode.Decoder(cfg, times, L, "cpu").state_dict())
+    assert sorted(gref.state_dict()) == sorted(slode.GaussianDecoder(cfg, times, L, "cpu").state_dict())
