@@ -88,3 +88,13 @@ class QuantileHeads(nn.Module):
         mu = [head(sol).permute(0, 2, 1) for head in (self.output_q75, self.output_q50, self.output_q25)]
         std = torch.ones_like(mu[0]) * nn.functional.softplus(self.constant_std)
         return sol, mu[0], mu[1], mu[2], std
+
+
+class Decoder(QuantileHeads):
+    """``models/decoders.py::Decoder`` constructor signature over the CPU port (checker / CPU baseline of the
+    training step: ``structured_latent_odes_b200.training_cvs.MechanisticModel(decoder_cls=oracle Decoder)``)."""
+
+    def __init__(self, config, times, latent_dim, device="cpu"):
+        ode = OdeModel(times, config.ode_state_dim, latent_dim, config.ode_hidden_dim, config.adjoint_solver,
+                       config.solver)
+        super().__init__(ode, config.obs_dim, len(times), config.constant_std)
