@@ -14,7 +14,7 @@ CPU or eager fallback.
 """
 from .torchdiffeq_api import odeint, odeint_adjoint, install_as_torchdiffeq, is_blackbox_func  # noqa: F401
 from .blackbox_ode import OdeModel, OdeFunc, Dynamics  # noqa: F401
-from .decoders import Decoder, GaussianDecoder, decoder_heads  # noqa: F401
+from .decoders import Decoder, GaussianDecoder, decoder_heads, multiple_samples  # noqa: F401
 from .cvs_mechanistic import CvsMechanistic, generate_cvs_latents, observe as cvs_observe  # noqa: F401
 
 __version__ = "0.1.0"

@@ -19,7 +19,7 @@ from torch import nn
 from . import _cabi
 from .blackbox_ode import OdeModel
 
-__all__ = ["Decoder", "GaussianDecoder", "decoder_heads"]
+__all__ = ["Decoder", "GaussianDecoder", "decoder_heads", "multiple_samples"]
 
 
 class _Heads(torch.autograd.Function):
@@ -114,3 +114,26 @@ class GaussianDecoder(nn.Module):
         (mean,) = decoder_heads(solution, (self.output_mean[0].weight,))
         std = torch.ones_like(mean) * nn.functional.softplus(self.constant_std)
         return solution, mean, std
+
+
+@torch.no_grad()
+def multiple_samples(decoder, z_loc, z_scale, num_samples, generator=None):
+    """Posterior / prior predictive sampling in ONE launch.
+
+    The reference draws ``num_samples`` (200) latent samples one at a time and re-solves the whole set each time
+    (``training_challenge.py:174-195``, ``training_proc.py:205-223``: ``recon`` in a Python loop, results
+    concatenated on a new last axis).  Trajectories are independent, so the samples are folded into the batch axis
+    instead: ``z ~ Normal(z_loc, z_scale)`` for all (sample, series) pairs, one solve + one heads pass.
+
+    Returns ``{"mu_25", "mu_50", "mu_75"}`` of shape ``(B, obs_dim, T, num_samples)`` (the reference's layout) and
+    ``"z"`` of shape ``(num_samples, B, latent_dim)``.
+    """
+    B, L = z_loc.shape
+    eps = torch.randn((num_samples, B, L), device=z_loc.device, dtype=z_loc.dtype, generator=generator)
+    z = z_loc[None] + z_scale[None] * eps
+    out = decoder(z.reshape(num_samples * B, L))
+    names = ("mu_75", "mu_50", "mu_25") if len(out) == 5 else ("mu_50",)
+    res = {"z": z}
+    for name, mu in zip(names, out[1:1 + len(names)]):
+        res[name] = mu.reshape(num_samples, B, *mu.shape[1:]).permute(1, 2, 3, 0)
+    return res

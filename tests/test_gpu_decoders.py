@@ -86,3 +86,19 @@ def test_state_dict_keys_equal_reference_decoder():
         gref = dec_ref.GaussianDecoder(config=cfg, latent_dim=L, times=times, device="cpu")
     assert sorted(ref.state_dict()) == sorted(slode.Decoder(cfg, times, L, "cpu").state_dict())
     assert sorted(gref.state_dict()) == sorted(slode.GaussianDecoder(cfg, times, L, "cpu").state_dict())
+
+
+def test_multiple_samples_equals_the_reference_style_loop():
+    """f3: num_samples posterior draws in one launch == the reference's loop of separate solves on the same draws."""
+    import structured_latent_odes_b200 as slode
+    L, H, S, times = U.SHAPES["chal"]
+    dec = slode.Decoder(_cfg("chal", "midpoint", True, 4), times.cuda(), L, "cuda").cuda()
+    B, K = 35, 12
+    loc, scale = torch.randn(B, L, device="cuda"), 0.1 + torch.rand(B, L, device="cuda")
+    res = slode.multiple_samples(dec, loc, scale, K, generator=torch.Generator(device="cuda").manual_seed(1))
+    assert res["mu_50"].shape == (B, 4, len(times), K) and res["z"].shape == (K, B, L)
+    with torch.no_grad():
+        for k in (0, 5, K - 1):
+            _, q75, q50, q25, _ = dec(res["z"][k])
+            assert torch.equal(res["mu_50"][..., k], q50) and torch.equal(res["mu_75"][..., k], q75)
+            assert torch.equal(res["mu_25"][..., k], q25)
