@@ -565,7 +565,7 @@ dopri5_bwd_kernel(Dopri5BwdArgs p) {
       // k7 = f(t1, y1) enters the interpolant as f1 and y_mid
       gk[6] = vaxpy<S>(__fmul_rn(kDpCMid[6], fdt), gym, gf1);
       sw.add(ft1, gk[6], Y[6], A[5], D[5]);                       // same gates as the sweep's current ones
-      gy1 = vnfma<S>(gk[6], D[5], gy1);                            // through y1 inside k7
+      gy1 = vfma<S>(gk[6], D[5], gy1);                             // through y1 inside k7 (D holds -sigmoid)
       // y1 = y0 + dt sum_j b_j k_j,  y_mid = y0 + dt sum_j cmid_j k_j
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
@@ -579,7 +579,7 @@ dopri5_bwd_kernel(Dopri5BwdArgs p) {
       for (int i = 5; i >= 0; --i) {  // stage i+1 at time ts[i], state Y[i]
         if (i < 5) sw.events(rec, g[i]);
         sw.add(ts[i], gk[i], Y[i], A[i], D[i]);
-        const Vec<S> gY = vnmul<S>(gk[i], D[i]);
+        const Vec<S> gY = vmul<S>(gk[i], D[i]);
         gy0 = vadd<S>(gy0, gY);
         if (i > 0) {
 #pragma unroll

@@ -132,6 +132,13 @@ template <int S> __device__ __forceinline__ Vec<S> vaxpy(float c, const Vec<S>& 
   SLODE_FOR_S r.v[s] = fma2(cc, a.v[s], b.v[s]);
   return r;
 }
+// a*b + c
+template <int S> __device__ __forceinline__ Vec<S> vfma(const Vec<S>& a, const Vec<S>& b, const Vec<S>& c) {
+  Vec<S> r;
+#pragma unroll
+  SLODE_FOR_S r.v[s] = fma2(a.v[s], b.v[s], c.v[s]);
+  return r;
+}
 // c - a*b
 template <int S> __device__ __forceinline__ Vec<S> vnfma(const Vec<S>& a, const Vec<S>& b, const Vec<S>& c) {
   Vec<S> r;
@@ -259,8 +266,12 @@ struct Gate {
 // per SM sub-partition (profiles/microbench/ldcu_rate.cu): at one FFMA2 (2 cycles) per weight the weight stream
 // and the FMA pipe are exactly balanced and neither can be saturated; at NE >= 2 the kernel is FMA-bound.
 // cj(j) returns the pair (c_j of traj0, c_j of traj1).
+// Outputs: A = sigmoid(growth heads) and ND = MINUS sigmoid(degradation heads).  The sign costs nothing
+// (-D = rcp(-1 - e) instead of rcp(1 + e)) and removes every negation downstream: f = A + ND*x, the stage
+// adjoint dL/dY = gk*ND, D^2 - D = ND^2 + ND.  (fma.rn.f32x2 has no operand-negate form; a packed negation is
+// two LOP3 per pair.)
 template <int H, int S, int NE, bool MASK, int SLOT, class CLoad>
-__device__ __forceinline__ void mlp_eval(const float (&t)[NE], CLoad cj, Vec<S> (&A)[NE], Vec<S> (&D)[NE],
+__device__ __forceinline__ void mlp_eval(const float (&t)[NE], CLoad cj, Vec<S> (&A)[NE], Vec<S> (&ND)[NE],
                                          Gate<H> (&gate)[NE]) {
   using P = Pack<H, S>;
   constexpr int K2 = 2 * S;
@@ -327,24 +338,24 @@ __device__ __forceinline__ void mlp_eval(const float (&t)[NE], CLoad cj, Vec<S> 
       }
     }
   }
-  const f2 one = bc(1.0f);
+  const f2 one = bc(1.0f), minus_one = bc(-1.0f);
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
 #pragma unroll
     for (int o = 0; o < K2; ++o) {
       float v0, v1;
       unpk(acc[e][o], v0, v1);
-      const f2 ex = add2(pk(ex2_approx(v0), ex2_approx(v1)), one);
-      unpk(ex, v0, v1);
+      const f2 ex = pk(ex2_approx(v0), ex2_approx(v1));
+      unpk(o < S ? add2(ex, one) : sub2(minus_one, ex), v0, v1);
       const f2 sg = pk(rcp_approx(v0), rcp_approx(v1));
-      if (o < S) A[e].v[o] = sg; else D[e].v[o - S] = sg;
+      if (o < S) A[e].v[o] = sg; else ND[e].v[o - S] = sg;
     }
   }
 }
 
-// f = A - D*x
+// f = A - D*x = A + ND*x
 template <int S>
-__device__ __forceinline__ Vec<S> rhs(const Vec<S>& A, const Vec<S>& D, const Vec<S>& x) { return vnfma<S>(D, x, A); }
+__device__ __forceinline__ Vec<S> rhs(const Vec<S>& A, const Vec<S>& ND, const Vec<S>& x) { return vfma<S>(ND, x, A); }
 
 #ifndef SLODE_FWD_MINB
 #define SLODE_FWD_MINB 3
@@ -644,12 +655,12 @@ struct Sweep {
 
   // add the cotangents of the head pre-activations of one evaluation at time te:
   //   f = A - D*y with upstream gf:  d(pre_A) = gf*A(1-A),  d(pre_D) = -gf*y*D(1-D)
-  __device__ __forceinline__ void add(float te, const Vec<S>& gf, const Vec<S>& y, const Vec<S>& A, const Vec<S>& D) {
+  __device__ __forceinline__ void add(float te, const Vec<S>& gf, const Vec<S>& y, const Vec<S>& A, const Vec<S>& ND) {
     const f2 tt = bc(te);
 #pragma unroll
     SLODE_FOR_S {
       const f2 dg = mul2(gf.v[s], fma2(neg2(A.v[s]), A.v[s], A.v[s]));                 // gf * (A - A^2)
-      const f2 dd = mul2(mul2(gf.v[s], y.v[s]), fma2(D.v[s], D.v[s], neg2(D.v[s])));   // gf*y * (D^2 - D)
+      const f2 dd = mul2(mul2(gf.v[s], y.v[s]), fma2(ND.v[s], ND.v[s], ND.v[s]));      // gf*y * (D^2 - D), ND = -D
       P[s] = add2(P[s], dg);
       Q[s] = fma2(dg, tt, Q[s]);
       P[S + s] = add2(P[S + s], dd);
@@ -969,7 +980,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           const Vec<S> gk = vscale<S>(lam, dt);
           if (!started) { sw.init(g[0]); started = true; } else sw.events(rec, g[0]);
           sw.add(t0, gk, x, A[0], D[0]);
-          lam = vnfma<S>(gk, D[0], lam);
+          lam = vfma<S>(gk, D[0], lam);
         } else if (METHOD == SLODE_METHOD_MIDPOINT) {
           const float half_dt = 0.5f * dt;
           Vec<S> A[2], D[2];
@@ -980,12 +991,12 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> gk = vscale<S>(lam, dt);  // dL/dk2
           if (!started) { sw.init(g[1]); started = true; } else sw.events(rec, g[1]);
           sw.add(te[1], gk, ym, A[1], D[1]);
-          const Vec<S> gy = vnmul<S>(gk, D[1]);  // dL/dy_mid
+          const Vec<S> gy = vmul<S>(gk, D[1]);  // dL/dy_mid (D holds -sigmoid)
           lam = vadd<S>(lam, gy);
           gk = vscale<S>(gy, half_dt);  // dL/dk1
           sw.events(rec, g[0]);
           sw.add(t0, gk, x, A[0], D[0]);
-          lam = vnfma<S>(gk, D[0], lam);
+          lam = vfma<S>(gk, D[0], lam);
         } else {  // rk4 3/8: the three new evaluations (t0, ta, tb) are taken together
           const float dt3 = dt * kOneThird;
           Vec<S> A[3], D[3];
@@ -1004,7 +1015,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           const Vec<S> w = vscale<S>(lam, 0.125f * dt);
           // stage 4 (time t1, carried evaluation; its gates are the sweep's current ones): gk4 = w
           sw.add(t1, w, Y4, Ac, Dc);
-          Vec<S> gy = vnmul<S>(w, Dc);
+          Vec<S> gy = vmul<S>(w, Dc);
           lam = vadd<S>(lam, gy);
           Vec<S> gk1 = vaxpy<S>(dt, gy, w);
           Vec<S> gk2 = vaxpy<S>(-dt, gy, vscale<S>(w, 3.0f));
@@ -1012,20 +1023,20 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           // stage 3
           sw.events(rec, g[2]);
           sw.add(te[2], gk3, Y3, A[2], D[2]);
-          gy = vnmul<S>(gk3, D[2]);
+          gy = vmul<S>(gk3, D[2]);
           lam = vadd<S>(lam, gy);
           gk2 = vaxpy<S>(dt, gy, gk2);
           gk1 = vaxpy<S>(-dt3, gy, gk1);
           // stage 2
           sw.events(rec, g[1]);
           sw.add(te[1], gk2, Y2, A[1], D[1]);
-          gy = vnmul<S>(gk2, D[1]);
+          gy = vmul<S>(gk2, D[1]);
           lam = vadd<S>(lam, gy);
           gk1 = vaxpy<S>(dt3, gy, gk1);
           // stage 1 (time t0; its evaluation is the carried one of the next interval)
           sw.events(rec, g[0]);
           sw.add(t0, gk1, x, A[0], D[0]);
-          lam = vnfma<S>(gk1, D[0], lam);
+          lam = vfma<S>(gk1, D[0], lam);
           Ac = A[0];
           Dc = D[0];
         }
@@ -1043,7 +1054,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           const Vec<S> v = vscale<S>(lam, ds);
           if (!started) { sw.init(g[0]); started = true; } else sw.events(rec, g[0]);
           sw.add(t1, v, y, A[0], D[0]);
-          lam = vnfma<S>(v, D[0], lam);
+          lam = vfma<S>(v, D[0], lam);
         } else if (METHOD == SLODE_METHOD_MIDPOINT) {
           const float half = 0.5f * ds;
           Vec<S> A[2], D[2];
@@ -1051,39 +1062,40 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           const float te[2] = {t1, t1 - half};
           mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);  // the stage at t1 has weight 0: its gates are not used
           const Vec<S> ym = vaxpy<S>(-half, rhs<S>(A[0], D[0], y), y);  // y + half*(D1*y - A1)
-          const Vec<S> am = vaxpy<S>(-half, vmul<S>(lam, D[0]), lam);   // a + half*(-a*D1)
+          const Vec<S> am = vaxpy<S>(half, vmul<S>(lam, D[0]), lam);    // a + half*(-a*D1), D holds -sigmoid
           const Vec<S> v = vscale<S>(am, ds);
           if (!started) { sw.init(g[1]); started = true; } else sw.events(rec, g[1]);
           sw.add(te[1], v, ym, A[1], D[1]);
-          lam = vnfma<S>(v, D[1], lam);
+          lam = vfma<S>(v, D[1], lam);
         } else {  // rk4 3/8 on the augmented system; Ky = -f, Ka = -a*D; new evaluations at ta, tb, t0 together
           const float w8 = 0.125f * ds;
           Vec<S> A[3], D[3];
           Gate<H> g[3];
           const float te[3] = {t1 - ds * kOneThird, t1 - ds * kTwoThirds, t0};
           mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
+          // (A, D with D = -sigmoid) => f = A + D*y; the augmented step uses Ky = -f, Ka = -a*sigmoid = a*D
           // stage 1 at t1 (carried evaluation)
-          const Vec<S> ky1 = vsub<S>(vmul<S>(Dc, y), Ac);
-          const Vec<S> ka1 = vnmul<S>(lam, Dc);
+          const Vec<S> f1 = rhs<S>(Ac, Dc, y);
+          const Vec<S> ka1 = vmul<S>(lam, Dc);
           sw.add(t1, vscale<S>(lam, w8), y, Ac, Dc);
           // stage 2
-          Vec<S> ym = vaxpy<S>(ds * kOneThird, ky1, y);
+          Vec<S> ym = vaxpy<S>(-ds * kOneThird, f1, y);
           Vec<S> am = vaxpy<S>(ds * kOneThird, ka1, lam);
-          const Vec<S> ky2 = vsub<S>(vmul<S>(D[0], ym), A[0]);
-          const Vec<S> ka2 = vnmul<S>(am, D[0]);
+          const Vec<S> f2_ = rhs<S>(A[0], D[0], ym);
+          const Vec<S> ka2 = vmul<S>(am, D[0]);
           sw.events(rec, g[0]);
           sw.add(te[0], vscale<S>(am, 3.0f * w8), ym, A[0], D[0]);
           // stage 3
-          ym = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ky1, ky2), y);
+          ym = vaxpy<S>(-ds, vaxpy<S>(-kOneThird, f1, f2_), y);
           am = vaxpy<S>(ds, vaxpy<S>(-kOneThird, ka1, ka2), lam);
-          const Vec<S> ky3 = vsub<S>(vmul<S>(D[1], ym), A[1]);
-          const Vec<S> ka3 = vnmul<S>(am, D[1]);
+          const Vec<S> f3 = rhs<S>(A[1], D[1], ym);
+          const Vec<S> ka3 = vmul<S>(am, D[1]);
           sw.events(rec, g[1]);
           sw.add(te[1], vscale<S>(am, 3.0f * w8), ym, A[1], D[1]);
           // stage 4 at t0 (becomes the carried evaluation)
-          ym = vaxpy<S>(ds, vadd<S>(vsub<S>(ky1, ky2), ky3), y);
+          ym = vaxpy<S>(-ds, vadd<S>(vsub<S>(f1, f2_), f3), y);
           am = vaxpy<S>(ds, vadd<S>(vsub<S>(ka1, ka2), ka3), lam);
-          const Vec<S> ka4 = vnmul<S>(am, D[2]);
+          const Vec<S> ka4 = vmul<S>(am, D[2]);
           sw.events(rec, g[2]);
           sw.add(t0, vscale<S>(am, w8), ym, A[2], D[2]);
           const Vec<S> asum = vadd<S>(vaxpy<S>(3.0f, vadd<S>(ka2, ka3), ka1), ka4);
