@@ -500,6 +500,47 @@ __device__ __forceinline__ Vec<S> lat_x0(const LatSmem& ls, const f2 (&ha)[H]) {
   return x;
 }
 
+// Output stage of the forward kernel.  With (T,B,S) storage a warp's 64 trajectories are adjacent in memory and
+// plain stores coalesce.  With (B,T,S) storage (layout="bts", what the decoder reads) a trajectory's rows are
+// contiguous in TIME instead: four consecutive output times are staged in shared memory and written as one
+// run of 4*S floats per trajectory with 16-byte stores.
+constexpr int kStageT = 4;
+template <int S>
+struct OutStage {
+  float buf[kBlock][2][kStageT * S];
+};
+template <int S>
+__device__ __forceinline__ void out_put(OutStage<S>& os, bool time_major_rows, int k, int T, float* row0, bool ok0,
+                                        float* row1, bool ok1, const Vec<S>& x) {
+  // row0/row1: start of the trajectory's storage (element (k,s) at row + k*st + s)
+  if (!time_major_rows) return;
+  const int tid = threadIdx.x, slot = k & (kStageT - 1);
+#pragma unroll
+  SLODE_FOR_S {
+    float lo, hi;
+    unpk(x.v[s], lo, hi);
+    os.buf[tid][0][slot * S + s] = lo;
+    os.buf[tid][1][slot * S + s] = hi;
+  }
+  if (slot == kStageT - 1 || k == T - 1) {
+    const int n = (slot + 1) * S;            // floats staged
+    const int k0 = k - slot;                 // first staged output time
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* dst = (h ? row1 : row0) + (int64_t)k0 * S;
+      if (!(h ? ok1 : ok0)) continue;
+      const float* src = os.buf[tid][h];
+      if (n == kStageT * S && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (kStageT * S) % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < kStageT * S / 4; ++q)
+          reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(src)[q];
+      } else {
+        for (int q = 0; q < n; ++q) dst[q] = src[q];
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -508,6 +549,8 @@ __global__ void __launch_bounds__(kBlock, SLODE_FWD_MINB)
 mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                      const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, LatentSrc lat) {
   extern __shared__ __align__(16) float fwd_dyn[];
+  __shared__ __align__(16) OutStage<S> ostage;
+  const bool rows_in_time = (st == S);  // (B,T,S)-contiguous storage
   LatSmem ls{};
   if (lat.z) {
     ls = lat_stage<H, S>(fwd_dyn, lat);
@@ -535,7 +578,10 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     auto cj = [&](int j) { return c2[j]; };
     float* out0 = sol + pi.b0 * sb;
     float* out1 = sol + pi.b1 * sb;
-    vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
+    float* const row0 = out0;
+    float* const row1 = out1;
+    if (rows_in_time) out_put<S>(ostage, true, 0, T, row0, pi.ok0, row1, pi.ok1, x);
+    else vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
     float t0 = __ldg(tgrid);
     Vec<S> k1;
     if (METHOD == SLODE_METHOD_RK4) {  // k1 of the first step; afterwards carried over from the step before
@@ -580,7 +626,8 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       }
       out0 += st;
       out1 += st;
-      vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
+      if (rows_in_time) out_put<S>(ostage, true, i + 1, T, row0, pi.ok0, row1, pi.ok1, x);
+      else vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
       t0 = t1;
     }
   }
