@@ -251,9 +251,7 @@ def main():
     def step_resident():
         model.zero_grad(set_to_none=True)
         sol = model.solve_ODE(z)
-        launches[0] += lib.slode_query(_cabi.Q_FWD_LAUNCHES)
         sol.backward(G)
-        launches[0] += lib.slode_query(_cabi.Q_BWD_LAUNCHES)
         reducer.reduce()
 
     def sync_all():
@@ -265,7 +263,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     sync_all()
-    launches[0] = 0
+    launches[0] = lib.slode_query(_cabi.Q_TOTAL_LAUNCHES)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks, KernelTimer() as kt:
         sync_all()
@@ -281,7 +279,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total = float(tmax.item())
     value = world * B * (T - 1) * args.steps / (ms_total * 1e-3)
-    n_launches = launches[0]
+    n_launches = lib.slode_query(_cabi.Q_TOTAL_LAUNCHES) - launches[0]
 
     # ---- end to end: pinned host inputs -> loss + gradients back on the host --------------------------------
     gc = torch.Generator().manual_seed(100 + rank)

@@ -66,8 +66,9 @@ extern "C" {
 #define SLODE_Q_MAX_STATE 3      /* largest S */
 #define SLODE_Q_N_SHAPES 4       /* number of compiled (H,S) pairs */
 #define SLODE_Q_SHAPE_BASE 100   /* 100+2i -> H of pair i, 101+2i -> S of pair i */
-#define SLODE_Q_FWD_LAUNCHES 10  /* kernels launched by the last fwd call on this thread */
+#define SLODE_Q_FWD_LAUNCHES 10  /* kernels launched by the last forward entry-point call of the process */
 #define SLODE_Q_BWD_LAUNCHES 11
+#define SLODE_Q_TOTAL_LAUNCHES 12 /* kernels launched by this library since it was loaded (all threads) */
 
 int slode_query(int what);
 const char* slode_last_error(void);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -35,9 +36,16 @@ struct PackGuard {
 // the library, valid while the caller holds a PackGuard (which serialises the kernels that use it).
 float* flip_workspace(size_t bytes);
 
-// thread-local launch counters reported by slode_query
-extern thread_local int g_fwd_launches;
-extern thread_local int g_bwd_launches;
+// launch counters reported by slode_query: kernels launched by the last forward / backward entry-point call of
+// the process (autograd runs backward calls on its own thread, so these are process-wide), and the running total
+struct LaunchCount {
+  std::atomic<int> last{0};
+  LaunchCount& operator=(int v);
+  operator int() const { return last.load(); }
+};
+extern LaunchCount g_fwd_launches;
+extern LaunchCount g_bwd_launches;
+extern std::atomic<long long> g_total_launches;
 
 // ---------------------------------------------------------------------------------------------
 // device side

@@ -169,6 +169,7 @@ extern "C" int slode_heads_fwd(int64_t B, int T, int S, int O, int NQ, const flo
   if (S == 4) GO(4); else if (S == 5) GO(5); else GO(8);
 #undef GO
   SLODE_CUDA_TRY(cudaGetLastError());
+  g_fwd_launches = 1;
   return SLODE_OK;
 }
 
@@ -191,5 +192,6 @@ extern "C" int slode_heads_bwd(int64_t B, int T, int S, int O, int NQ, const flo
   if (S == 4) GO(4); else if (S == 5) GO(5); else GO(8);
 #undef GO
   SLODE_CUDA_TRY(cudaGetLastError());
+  g_bwd_launches = 1;
   return SLODE_OK;
 }

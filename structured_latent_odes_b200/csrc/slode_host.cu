@@ -9,8 +9,14 @@
 namespace slode {
 
 static thread_local char g_err[512] = "";
-thread_local int g_fwd_launches = 0;
-thread_local int g_bwd_launches = 0;
+LaunchCount g_fwd_launches;
+LaunchCount g_bwd_launches;
+std::atomic<long long> g_total_launches{0};
+LaunchCount& LaunchCount::operator=(int v) {
+  last.store(v);
+  if (v > 0) g_total_launches.fetch_add(v);
+  return *this;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -62,6 +62,7 @@ extern "C" int slode_query(int what) {
     case SLODE_Q_N_SHAPES: return kNumShapes;
     case SLODE_Q_FWD_LAUNCHES: return g_fwd_launches;
     case SLODE_Q_BWD_LAUNCHES: return g_bwd_launches;
+    case SLODE_Q_TOTAL_LAUNCHES: return (int)(g_total_launches.load() & 0x7fffffff);
   }
   if (what >= SLODE_Q_SHAPE_BASE && what < SLODE_Q_SHAPE_BASE + 2 * kNumShapes) {
     const int i = (what - SLODE_Q_SHAPE_BASE) / 2;
