@@ -121,5 +121,9 @@ if __name__ == "__main__":
     for ns in (1, 200, 4096):
         for method in ("midpoint", "rk4"):
             blackbox(f"configs[3] proc 312 wells x {ns} samples", 312 * ns, 100, 50, 25, 8, method, method == "midpoint", times=tt)
+    for Hw in (16, 32, 64):  # configs[4]: hidden-width sweep on the FMA path (compiled widths)
+        Sw = 4 if Hw == 16 else 5
+        for B in (1 << 10, 1 << 16, big):
+            blackbox(f"configs[4] width sweep H={Hw}", B, 100, 15, Hw, Sw, "rk4", False)
     blackbox("configs[1] blackbox rk4 (bench.py workload)", big, 100, 15, 25, 5, "rk4", False)
     blackbox("configs[1] blackbox midpoint adjoint", big, 100, 15, 25, 5, "midpoint", True)

@@ -93,7 +93,7 @@ typedef int (*dopri5_fwd_fn)(const Dopri5Args&, const PackSrc&, float* staging, 
 typedef int (*dopri5_bwd_fn)(const Dopri5BwdArgs&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 
 // (25,5): CVS / challenge configs; (25,8): proc config; the rest serve tests and the width sweep.
-#define SLODE_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5)
+#define SLODE_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5) X(64, 5)
 
 #define SLODE_DECLARE_SHAPE(H, S)                                         \
   int mlp_fwd_##H##_##S(const FwdArgs&, const PackSrc&, float* staging);  \

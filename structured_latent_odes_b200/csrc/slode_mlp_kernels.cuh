@@ -551,31 +551,42 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   extern __shared__ __align__(16) float fwd_dyn[];
   __shared__ __align__(16) OutStage<S> ostage;
   const bool rows_in_time = (st == S);  // (B,T,S)-contiguous storage
+  // wide hidden layers: the per-trajectory c_j do not fit in registers next to the accumulators -> shared memory
+  constexpr bool C_IN_SMEM = H > 32;
+  f2 (*csm)[kBlock] = reinterpret_cast<f2 (*)[kBlock]>(fwd_dyn);
+  float* lat_base = fwd_dyn + (C_IN_SMEM ? 2 * H * kBlock : 0);
   LatSmem ls{};
   if (lat.z) {
-    ls = lat_stage<H, S>(fwd_dyn, lat);
+    ls = lat_stage<H, S>(lat_base, lat);
     __syncthreads();
   }
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
-    f2 c2[H];
+    f2 c2[C_IN_SMEM ? 1 : H];
     Vec<S> x;
-    if (lat.z) {
-      f2 ha[H];
-      if (lat.Wa) {
-        lat_hidden<H, true>(ls, lat, pi, c2, ha);
-        x = lat_x0<H, S>(ls, ha);
+    {
+      f2 ctmp[H];
+      if (lat.z) {
+        f2 ha[H];
+        if (lat.Wa) {
+          lat_hidden<H, true>(ls, lat, pi, ctmp, ha);
+          x = lat_x0<H, S>(ls, ha);
+        } else {
+          lat_hidden<H, false>(ls, lat, pi, ctmp, ha);
+          x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
+        }
       } else {
-        lat_hidden<H, false>(ls, lat, pi, c2, ha);
+#pragma unroll
+        for (int j = 0; j < H; ++j) ctmp[j] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
         x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
       }
-    } else {
 #pragma unroll
-      for (int j = 0; j < H; ++j) c2[j] = pk(ld_stream(cin + pi.b0 * H + j), ld_stream(cin + pi.b1 * H + j));
-      x = vload2<S>(y0 + pi.b0 * S, y0 + pi.b1 * S);
+      for (int j = 0; j < H; ++j) {
+        if (C_IN_SMEM) csm[j][threadIdx.x] = ctmp[j]; else c2[C_IN_SMEM ? 0 : j] = ctmp[j];
+      }
     }
-    auto cj = [&](int j) { return c2[j]; };
+    auto cj = [&](int j) { return C_IN_SMEM ? csm[j][threadIdx.x] : c2[C_IN_SMEM ? 0 : j]; };
     float* out0 = sol + pi.b0 * sb;
     float* out1 = sol + pi.b1 * sb;
     float* const row0 = out0;
@@ -826,12 +837,27 @@ struct Sweep {
 //              + sum_j da_j Wa_jl,   da_j = [ha_j > 0] sum_s Wb_sj db_s,   db = dL/dx0 * x0 (1 - x0)
 //     dW1z_jl += dc_j z_l,  db1_j += dc_j,  dWa_jl += da_j z_l,  dba_j += da_j,  dWb_sj += db_s relu(ha_j),  dbb_s += db_s
 // The sums over trajectories go lane -> warp (scatter reduction) -> block accumulators in shared memory.
+// reduce vals(k), k in [0,H), over the warp's lanes and both trajectories into dst(k) (shared accumulators)
+template <int H, class Val, class Dst>
+__device__ __forceinline__ void reduce_units(int lane, Val val, Dst dst) {
+  constexpr int KR = (H <= 16) ? 16 : 32;
+#pragma unroll
+  for (int base = 0; base < H; base += KR) {
+    float v[KR];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+      float lo = 0.0f, hi = 0.0f;
+      if (base + k < H) unpk(val(base + k), lo, hi);
+      v[k] = lo + hi;
+    }
+    warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return base + slot < H ? dst(base + slot) : nullptr; });
+  }
+}
+
 template <int H, int S>
 __device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& ls, float* acc, const LatentSrc& lat,
                                              const PairIdx& pi, bool discrete, const Vec<S>& lam, const Vec<S>& x0,
                                              float* __restrict__ gz) {
-  static_assert(H <= 32, "one scatter reduction per group of H values");
-  constexpr int KR = (H <= 16) ? 16 : 32;
   constexpr int KS = 16;
   static_assert(S <= KS, "state dimension");
   const int tid = threadIdx.x, lane = tid & 31;
@@ -843,7 +869,6 @@ __device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& l
   float* gba = gWa + H * L;
   float* gWb = gba + H;
   float* gbb = gWb + S * H;
-  auto halves = [](f2 v) { float lo, hi; unpk(v, lo, hi); return lo + hi; };
 
   f2 gcr[H], da[H];
 #pragma unroll
@@ -872,30 +897,21 @@ __device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& l
     }
 #pragma unroll
     SLODE_FOR_S {
-      float v[KR];
-#pragma unroll
-      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(mul2(db.v[s], hr[k < H ? k : 0])) : 0.0f;
-      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gWb + s * H + slot : nullptr; });
+      reduce_units<H>(lane, [&](int k) { return mul2(db.v[s], hr[k]); }, [&](int k) { return gWb + s * H + k; });
     }
     {
       float v[KS];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) v[k] = (k < S) ? halves(db.v[k < S ? k : 0]) : 0.0f;
+      for (int k = 0; k < KS; ++k) {
+        float lo = 0.0f, hi = 0.0f;
+        if (k < S) unpk(db.v[k < S ? k : 0], lo, hi);
+        v[k] = lo + hi;
+      }
       warp_reduce_to<KS>(v, lane, [&](int slot) -> float* { return slot < S ? gbb + slot : nullptr; });
     }
-    {
-      float v[KR];
-#pragma unroll
-      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(da[k < H ? k : 0]) : 0.0f;
-      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gba + slot : nullptr; });
-    }
+    reduce_units<H>(lane, [&](int k) { return da[k]; }, [&](int k) { return gba + k; });
   }
-  {
-    float v[KR];
-#pragma unroll
-    for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(gcr[k < H ? k : 0]) : 0.0f;
-    warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gb1 + slot : nullptr; });
-  }
+  reduce_units<H>(lane, [&](int k) { return gcr[k]; }, [&](int k) { return gb1 + k; });
   const float* z0 = lat.z + pi.b0 * L;
   const float* z1 = lat.z + pi.b1 * L;
 #pragma unroll 1
@@ -904,21 +920,13 @@ __device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& l
     const float* wz = ls.Wz + l * H;
     const float* wa = ls.Wa + l * H;
     f2 dz = 0ull;
-    {
-      float v[KR];
-#pragma unroll
-      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(mul2(gcr[k < H ? k : 0], zl)) : 0.0f;
-      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gWz + slot * L + l : nullptr; });
-    }
+    reduce_units<H>(lane, [&](int k) { return mul2(gcr[k], zl); }, [&](int k) { return gWz + k * L + l; });
     if (discrete) {
 #pragma unroll
       for (int j = 0; j < H; ++j) dz = fma2(bc(wz[j]), gcr[j], dz);
     }
     if (fx0) {
-      float v[KR];
-#pragma unroll
-      for (int k = 0; k < KR; ++k) v[k] = (k < H) ? halves(mul2(da[k < H ? k : 0], zl)) : 0.0f;
-      warp_reduce_to<KR>(v, lane, [&](int slot) -> float* { return slot < H ? gWa + slot * L + l : nullptr; });
+      reduce_units<H>(lane, [&](int k) { return mul2(da[k], zl); }, [&](int k) { return gWa + k * L + l; });
 #pragma unroll
       for (int j = 0; j < H; ++j) dz = fma2(bc(wa[j]), da[j], dz);
     }
@@ -1198,7 +1206,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
 template <int H, int S, int METHOD>
 int launch_fwd(const FwdArgs& a) {
   auto kern = mlp_fixed_fwd_kernel<H, S, METHOD>;
-  const size_t smem = a.lat.z ? sizeof(float) * lat_floats(a.lat.L, H, S) : 0;
+  const size_t smem = (a.lat.z ? sizeof(float) * lat_floats(a.lat.L, H, S) : 0) +
+                      (H > 32 ? sizeof(f2) * H * kBlock : 0);
   if (smem > 48 * 1024)
     SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;

@@ -21,6 +21,7 @@ SHAPES = {
     "proc": (50, 25, 8, proc_like_times()),
     "small": (6, 16, 4, torch.linspace(0.0, 3.0, 17)),
     "h32": (15, 32, 5, torch.arange(0.0, 40.0, 1.0)),
+    "h64": (15, 64, 5, torch.arange(0.0, 30.0, 1.0)),
 }
 
 

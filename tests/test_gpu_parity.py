@@ -39,7 +39,7 @@ def _compare(shape, method, adjoint, B, layout="tbs", seed=3):
 
 @pytest.mark.parametrize("adjoint", [False, True])
 @pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
-@pytest.mark.parametrize("shape", ["cvs", "proc", "small", "h32"])
+@pytest.mark.parametrize("shape", ["cvs", "proc", "small", "h32", "h64"])
 def test_fixed_grid_matches_oracle(shape, method, adjoint):
     _compare(shape, method, adjoint, B=200)
 
