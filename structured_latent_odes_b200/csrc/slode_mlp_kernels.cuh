@@ -545,7 +545,7 @@ __device__ __forceinline__ void out_put(OutStage<S>& os, bool time_major_rows, i
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int H, int S, int METHOD>
-__global__ void __launch_bounds__(kBlock, SLODE_FWD_MINB)
+__global__ void __launch_bounds__(kBlock, ((S >= 8 && METHOD == SLODE_METHOD_RK4) ? 2 : SLODE_FWD_MINB))  // S=8 rk4: 48 accumulator pairs
 mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                      const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, LatentSrc lat) {
   extern __shared__ __align__(16) float fwd_dyn[];
