@@ -72,7 +72,7 @@ class ClockSampler:
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
             0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int, period=0.05):
+    def __init__(self, index: int, period=0.01):
         self.samples, self.reasons, self.power = [], set(), []
         self.stop_flag = threading.Event()
         self.period = period
