@@ -126,7 +126,15 @@ int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
  * zero-fills), flat
  *     [ dw1t (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) | dW1[:,1:] (H*L) | db1 (H) |
  *       dWa (H*L) | dba (H) | dWb (S*H) | dbb (S) ]           (the last four only when the x0 net is fused).
+ *
+ * eval_ckpt (optional, may be NULL): slode_eval_ckpt_floats(method, B, T, S) floats.  When given, the forward stores
+ * the growth / degradation sigmoids of every MLP evaluation of the solve there (120 B per trajectory and rk4 step at
+ * S = 5) and the DISCRETE reverse sweep reads them back instead of re-evaluating the MLP (it then only recomputes the
+ * hidden-layer gates): trades 12.5 GB of HBM per 2^20 x 100 solve for ~60 % of the reverse sweep's arithmetic.  The
+ * odeint_adjoint mode evaluates at its own stage times and ignores it.
  */
+int64_t slode_eval_ckpt_floats(int method, int64_t B, int T, int S);
+
 int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S,
                            const float* t, const float* z,
                            const float* W1, const float* b1, const float* Wg, const float* bg,
@@ -134,7 +142,7 @@ int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S,
                            const float* Wa, const float* ba, const float* Wb, const float* bb,
                            const float* y0,
                            float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
-                           void* stream);
+                           float* eval_ckpt, void* stream);
 
 int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H, int S,
                            const float* t, const float* z,
@@ -144,7 +152,7 @@ int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H,
                            const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
                            const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
                            float* grad_z, float* grad_y0, float* grad_params,
-                           void* stream);
+                           const float* eval_ckpt, void* stream);
 
 /*
  * Adaptive Dormand-Prince 5(4) forward solve; replaces torchdiffeq.odeint(func=OdeFunc, y0, t, method="dopri5",

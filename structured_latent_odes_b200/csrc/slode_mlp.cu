@@ -90,7 +90,7 @@ extern "C" int slode_mlp_fixed_fwd(int method, int64_t B, int T, int H, int S, c
   cudaStream_t stream = (cudaStream_t)stream_;
   PackGuard guard(stream);
   if (guard.status) return guard.status;
-  const FwdArgs a{method, B, T, t, c, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, LatentSrc{}};
+  const FwdArgs a{method, B, T, t, c, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, LatentSrc{}, nullptr};
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->fwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_fwd_launches = 2;  // pack kernel + solver kernel
@@ -123,7 +123,7 @@ extern "C" int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H
   PackGuard guard(stream);
   if (guard.status) return guard.status;
   const BwdArgs a{method, mode,          B,  T,      t,        c,       w1t, Wg, Wd, sol, sol_stride_t, sol_stride_b,
-                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, grad_c, grad_w, stream, guard.sms, LatentSrc{}, nullptr};
+                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, grad_c, grad_w, stream, guard.sms, LatentSrc{}, nullptr, nullptr};
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->bwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_bwd_launches = 2;
@@ -235,7 +235,7 @@ extern "C" int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H
                                       const float* W1, const float* b1, const float* Wg, const float* bg,
                                       const float* Wd, const float* bd, const float* Wa, const float* ba,
                                       const float* Wb, const float* bb, const float* y0, float* sol,
-                                      int64_t sol_stride_t, int64_t sol_stride_b, void* stream_) {
+                                      int64_t sol_stride_t, int64_t sol_stride_b, float* eval_ckpt, void* stream_) {
   int rc = check_common("slode_latent_fixed_fwd", B, T, H, S);
   if (rc) return rc;
   if (B > 0) {
@@ -255,7 +255,7 @@ extern "C" int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H
   rc = gather_w1t(W1, L, H, w1t, stream);
   if (rc) return rc;
   const LatentSrc lat{z, L, W1, b1, Wa, ba, Wb, bb};
-  const FwdArgs a{method, B, T, t, nullptr, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, lat};
+  const FwdArgs a{method, B, T, t, nullptr, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, lat, eval_ckpt};
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->fwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_fwd_launches = 2;
@@ -268,7 +268,7 @@ extern "C" int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, in
                                       const float* ba, const float* Wb, const float* bb, const float* sol,
                                       int64_t sol_stride_t, int64_t sol_stride_b, const float* grad_sol,
                                       int64_t gsol_stride_t, int64_t gsol_stride_b, float* grad_z, float* grad_y0,
-                                      float* grad_params, void* stream_) {
+                                      float* grad_params, const float* eval_ckpt, void* stream_) {
   int rc = check_common("slode_latent_fixed_bwd", B, T, H, S);
   if (rc) return rc;
   if (mode != SLODE_BWD_DISCRETE && mode != SLODE_BWD_TDE_ADJOINT) {
@@ -293,9 +293,22 @@ extern "C" int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, in
   if (rc) return rc;
   const LatentSrc lat{z, L, W1, b1, Wa, ba, Wb, bb};
   const BwdArgs a{method, mode, B, T, t, nullptr, w1t, Wg, Wd, sol, sol_stride_t, sol_stride_b,
-                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, nullptr, grad_params, stream, guard.sms, lat, grad_z};
+                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, nullptr, grad_params, stream, guard.sms, lat, grad_z,
+                  mode == SLODE_BWD_DISCRETE ? eval_ckpt : nullptr};
   const PackSrc w{w1t, Wg, bg, Wd, bd};
   rc = find_shape(H, S)->bwd(a, w, guard.staging);
   if (rc == SLODE_OK) g_bwd_launches = 2;
   return rc;
+}
+
+extern "C" int64_t slode_eval_ckpt_floats(int method, int64_t B, int T, int S) {
+  if (B < 0 || T < 1 || S < 1) return -1;
+  int64_t nev;
+  switch (method) {
+    case SLODE_METHOD_EULER: nev = T - 1; break;
+    case SLODE_METHOD_MIDPOINT: nev = 2 * (int64_t)(T - 1); break;
+    case SLODE_METHOD_RK4: nev = 3 * (int64_t)(T - 1) + 1; break;
+    default: return -1;
+  }
+  return nev * ((B + 1) / 2) * (2 * (int64_t)S) * 2;
 }

@@ -31,6 +31,7 @@ struct FwdArgs {
   cudaStream_t stream;
   int sms;
   LatentSrc lat;
+  float* eval_ckpt;  // optional: every MLP evaluation (A, -D) of the solve, see slode_b200.h
 };
 
 struct BwdArgs {
@@ -46,6 +47,7 @@ struct BwdArgs {
   int sms;
   LatentSrc lat;
   float* gz;  // (B,L), fused mode only
+  const float* eval_ckpt;  // optional (discrete mode): the forward's evaluation checkpoints instead of recomputing
 };
 
 // dopri5 forward (slode_dopri5_kernels.cuh); scratch pointers are filled in by the launcher

@@ -353,6 +353,75 @@ __device__ __forceinline__ void mlp_eval(const float (&t)[NE], CLoad cj, Vec<S> 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// evaluation checkpoints: the (A, -D) of every MLP evaluation of a solve, in the threads' own pair layout
+//   element (evaluation e, head output k, trajectory pair p) = one f2 at ckpt[(e * 2S + k) * npairs + p]
+// (output-major: for a fixed k the 32 threads of a warp write / read 256 contiguous bytes)
+// Evaluation order: euler e = i (time t_i); midpoint e = 2i (t_i), 2i+1 (t_i + dt/2); rk4 e = 0 (t_0) and
+// 3i+1, 3i+2, 3i+3 = (t_i + dt/3, t_i + 2dt/3, t_{i+1}).  120 B per trajectory and rk4 step at S = 5: writing
+// them costs the forward ~5 clk/SM per trajectory-step of HBM time, re-computing them costs the reverse sweep
+// >= 6.4 clk/SM of FMA time at PEAK (13 measured) -- on 180 GB of HBM3e the checkpoint is the better trade.
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void ckpt_store(f2* __restrict__ ckpt, int64_t e, int64_t npairs, int64_t pair,
+                                           const Vec<S>& A, const Vec<S>& ND) {
+  f2* p = ckpt + e * (2 * S) * npairs + pair;
+#pragma unroll
+  SLODE_FOR_S {
+    p[s * npairs] = A.v[s];
+    p[(S + s) * npairs] = ND.v[s];
+  }
+}
+template <int S>
+__device__ __forceinline__ void ckpt_load(const f2* __restrict__ ckpt, int64_t e, int64_t npairs, int64_t pair,
+                                          Vec<S>& A, Vec<S>& ND) {
+  const f2* p = ckpt + e * (2 * S) * npairs + pair;
+#pragma unroll
+  SLODE_FOR_S {
+    A.v[s] = __ldg(p + s * npairs);
+    ND.v[s] = __ldg(p + (S + s) * npairs);
+  }
+}
+
+// relu gates of NE evaluation times from the hidden layer alone (the reverse sweep with checkpoints needs the
+// gates for the prefix-sum bookkeeping but not the heads)
+template <int H, int NE, class CLoad>
+__device__ __forceinline__ void gates_only(const float* __restrict__ w1t_smem, const float (&t)[NE], CLoad cj,
+                                           Gate<H> (&gate)[NE]) {
+  constexpr int NW = Gate<H>::NW;
+  uint32_t neg[NE][2][NW];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) neg[e][0][w] = neg[e][1][w] = 0u;
+  }
+  f2 tt[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) tt[e] = bc(t[e]);
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    const f2 c = cj(j);
+    const f2 w1 = bc(w1t_smem[j]);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      float p0, p1;
+      unpk(fma2(w1, tt[e], c), p0, p1);
+      neg[e][0][j / 32] = __funnelshift_l(__float_as_uint(p0), neg[e][0][j / 32], 1);
+      neg[e][1][j / 32] = __funnelshift_l(__float_as_uint(p1), neg[e][1][j / 32], 1);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
+      const uint32_t low = (nw == 32) ? 0xffffffffu : ((1u << nw) - 1u);
+      gate[e].w[0][w] = (~neg[e][0][w]) & low;
+      gate[e].w[1][w] = (~neg[e][1][w]) & low;
+    }
+  }
+}
+
 // f = A - D*x = A + ND*x
 template <int S>
 __device__ __forceinline__ Vec<S> rhs(const Vec<S>& A, const Vec<S>& ND, const Vec<S>& x) { return vfma<S>(ND, x, A); }
@@ -547,8 +616,10 @@ __device__ __forceinline__ void out_put(OutStage<S>& os, bool time_major_rows, i
 template <int H, int S, int METHOD>
 __global__ void __launch_bounds__(kBlock, ((S >= 8 && METHOD == SLODE_METHOD_RK4) ? 2 : SLODE_FWD_MINB))  // S=8 rk4: 48 accumulator pairs
 mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
-                     const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, LatentSrc lat) {
+                     const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, LatentSrc lat,
+                     f2* __restrict__ eval_ckpt) {
   extern __shared__ __align__(16) float fwd_dyn[];
+  const int64_t npairs = (B + 1) / 2;
   __shared__ __align__(16) OutStage<S> ostage;
   const bool rows_in_time = (st == S);  // (B,T,S)-contiguous storage
   // wide hidden layers: the per-trajectory c_j do not fit in registers next to the accumulators -> shared memory
@@ -563,6 +634,8 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
+    const int64_t pair = tile * kBlock + threadIdx.x;
+    const bool save = eval_ckpt != nullptr && pi.ok0;
     f2 c2[C_IN_SMEM ? 1 : H];
     Vec<S> x;
     {
@@ -600,6 +673,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       Gate<H> ng[1];
       const float te[1] = {t0};
       mlp_eval<H, S, 1, false, 1>(te, cj, A, D, ng);
+      if (save) ckpt_store<S>(eval_ckpt, 0, npairs, pair, A[0], D[0]);
       k1 = rhs<S>(A[0], D[0], x);
     }
 
@@ -612,6 +686,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Gate<H> ng[1];
         const float te[1] = {t0};
         mlp_eval<H, S, 1, false, 0>(te, cj, A, D, ng);
+        if (save) ckpt_store<S>(eval_ckpt, i, npairs, pair, A[0], D[0]);
         x = vaxpy<S>(dt, rhs<S>(A[0], D[0], x), x);
       } else if (METHOD == SLODE_METHOD_MIDPOINT) {
         const float half_dt = 0.5f * dt;
@@ -619,6 +694,10 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Gate<H> ng[2];
         const float te[2] = {t0, t0 + half_dt};
         mlp_eval<H, S, 2, false, 0>(te, cj, A, D, ng);
+        if (save) {
+          ckpt_store<S>(eval_ckpt, 2 * (int64_t)i, npairs, pair, A[0], D[0]);
+          ckpt_store<S>(eval_ckpt, 2 * (int64_t)i + 1, npairs, pair, A[1], D[1]);
+        }
         const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A[0], D[0], x), x);
         x = vaxpy<S>(dt, rhs<S>(A[1], D[1], ym), x);
       } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func); the three new evaluations are taken together
@@ -626,6 +705,10 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Gate<H> ng[3];
         const float te[3] = {t0 + dt * kOneThird, t0 + dt * kTwoThirds, t1};
         mlp_eval<H, S, 3, false, 0>(te, cj, A, D, ng);
+        if (save) {
+#pragma unroll
+          for (int e = 0; e < 3; ++e) ckpt_store<S>(eval_ckpt, 3 * (int64_t)i + 1 + e, npairs, pair, A[e], D[e]);
+        }
         Vec<S> y = vaxpy<S>(dt * kOneThird, k1, x);
         const Vec<S> k2 = rhs<S>(A[0], D[0], y);
         y = vaxpy<S>(dt, vaxpy<S>(-kOneThird, k1, k2), x);
@@ -937,14 +1020,17 @@ __device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& l
   }
 }
 
-template <int H, int S, int METHOD, int MODE>
+template <int H, int S, int METHOD, int MODE, bool CKPT>
 __global__ void __launch_bounds__(kBlock, SLODE_BWD_MINB)
 mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                      const float* __restrict__ w1t, const float* __restrict__ Wg, const float* __restrict__ Wd,
                      const float* __restrict__ sol, int64_t st, int64_t sb,
                      const float* __restrict__ gsol, int64_t gst, int64_t gsb,
                      float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,
-                     float* __restrict__ flip_ws, LatentSrc lat, float* __restrict__ grad_z) {
+                     float* __restrict__ flip_ws, LatentSrc lat, float* __restrict__ grad_z,
+                     const f2* __restrict__ eval_ckpt) {
+  static_assert(!CKPT || MODE == SLODE_BWD_DISCRETE, "evaluation checkpoints serve the discrete sweep");
+  const int64_t npairs = (B + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem<H, S>& sm = *reinterpret_cast<BwdSmem<H, S>*>(smem_raw);
   constexpr int K2 = 2 * S;
@@ -976,6 +1062,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
+    // (checkpoints of a fully masked-off thread do not exist: it reads pair 0's, its cotangents are zero anyway)
+    const int64_t pair = pi.ok0 ? tile * kBlock + tid : 0;
     // a masked-off half aliases trajectory B-1 (owned by another half): it must never touch grad_c
     float* gc0 = pi.ok0 ? grad_c + pi.b0 * H : nullptr;
     float* gc1 = pi.ok1 ? grad_c + pi.b1 * H : nullptr;
@@ -1007,7 +1095,12 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       Vec<S> A[1], D[1];
       Gate<H> g[1];
       const float te[1] = {t1};
-      mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
+      if (CKPT) {
+        ckpt_load<S>(eval_ckpt, 3 * (int64_t)(T - 1), npairs, pair, A[0], D[0]);
+        gates_only<H, 1>(sm.w1t, te, cj, g);
+      } else {
+        mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
+      }
       Ac = A[0];
       Dc = D[0];
       sw.init(g[0]);
@@ -1031,7 +1124,12 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[1], D[1];
           Gate<H> g[1];
           const float te[1] = {t0};
-          mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
+          if (CKPT) {
+            ckpt_load<S>(eval_ckpt, i, npairs, pair, A[0], D[0]);
+            gates_only<H, 1>(sm.w1t, te, cj, g);
+          } else {
+            mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
+          }
           const Vec<S> gk = vscale<S>(lam, dt);
           if (!started) { sw.init(g[0]); started = true; } else sw.events(rec, g[0]);
           sw.add(t0, gk, x, A[0], D[0]);
@@ -1041,7 +1139,13 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[2], D[2];
           Gate<H> g[2];
           const float te[2] = {t0, t0 + half_dt};
-          mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
+          if (CKPT) {
+            ckpt_load<S>(eval_ckpt, 2 * (int64_t)i, npairs, pair, A[0], D[0]);
+            ckpt_load<S>(eval_ckpt, 2 * (int64_t)i + 1, npairs, pair, A[1], D[1]);
+            gates_only<H, 2>(sm.w1t, te, cj, g);
+          } else {
+            mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
+          }
           const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A[0], D[0], x), x);
           Vec<S> gk = vscale<S>(lam, dt);  // dL/dk2
           if (!started) { sw.init(g[1]); started = true; } else sw.events(rec, g[1]);
@@ -1057,7 +1161,13 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[3], D[3];
           Gate<H> g[3];
           const float te[3] = {t0, t0 + dt * kOneThird, t0 + dt * kTwoThirds};
-          mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
+          if (CKPT) {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) ckpt_load<S>(eval_ckpt, 3 * (int64_t)i + e, npairs, pair, A[e], D[e]);
+            gates_only<H, 3>(sm.w1t, te, cj, g);
+          } else {
+            mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
+          }
           Vec<S> Y2, Y3, Y4;
           {
             const Vec<S> k1 = rhs<S>(A[0], D[0], x);
@@ -1216,14 +1326,15 @@ int launch_fwd(const FwdArgs& a) {
   const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
   // whole waves of resident blocks; tiles are handed out grid-stride
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)a.sms * blocks_per_sm);
-  kern<<<grid, kBlock, smem, a.stream>>>(a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb, a.lat);
+  kern<<<grid, kBlock, smem, a.stream>>>(a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb, a.lat,
+                                         reinterpret_cast<f2*>(a.eval_ckpt));
   SLODE_CUDA_TRY(cudaGetLastError());
   return SLODE_OK;
 }
 
-template <int H, int S, int METHOD, int MODE>
+template <int H, int S, int METHOD, int MODE, bool CKPT>
 int launch_bwd(const BwdArgs& a) {
-  auto kern = mlp_fixed_bwd_kernel<H, S, METHOD, MODE>;
+  auto kern = mlp_fixed_bwd_kernel<H, S, METHOD, MODE, CKPT>;
   const size_t smem = (sizeof(BwdSmem<H, S>) + 15) / 16 * 16 +
                       (a.lat.z ? 2 * sizeof(float) * lat_floats(a.lat.L, H, S) : 0);
   SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1235,7 +1346,8 @@ int launch_bwd(const BwdArgs& a) {
   float* ws = flip_workspace(sizeof(float) * (size_t)grid * kBlock * Sweep<H, S>::REC_PER_THREAD);
   if (!ws) return SLODE_ECUDA;
   kern<<<grid, kBlock, smem, a.stream>>>(a.B, a.T, a.t, a.c, a.w1t, a.Wg, a.Wd, a.sol, a.st, a.sb, a.gsol, a.gst,
-                                         a.gsb, a.gy0, a.gc, a.gw, ws, a.lat, a.gz);
+                                         a.gsb, a.gy0, a.gc, a.gw, ws, a.lat, a.gz,
+                                         reinterpret_cast<const f2*>(a.eval_ckpt));
   SLODE_CUDA_TRY(cudaGetLastError());
   return SLODE_OK;
 }
@@ -1255,8 +1367,10 @@ template <int H, int S>
 int bwd_shape(const BwdArgs& a) {
 #define SLODE_BWD_CASE(M)                                                                            \
   case M:                                                                                            \
-    return (a.mode == SLODE_BWD_DISCRETE) ? launch_bwd<H, S, M, SLODE_BWD_DISCRETE>(a)               \
-                                          : launch_bwd<H, S, M, SLODE_BWD_TDE_ADJOINT>(a);
+    if (a.mode == SLODE_BWD_DISCRETE)                                                                \
+      return a.eval_ckpt ? launch_bwd<H, S, M, SLODE_BWD_DISCRETE, true>(a)                          \
+                         : launch_bwd<H, S, M, SLODE_BWD_DISCRETE, false>(a);                        \
+    return launch_bwd<H, S, M, SLODE_BWD_TDE_ADJOINT, false>(a);
   switch (a.method) {
     SLODE_BWD_CASE(SLODE_METHOD_EULER)
     SLODE_BWD_CASE(SLODE_METHOD_MIDPOINT)

@@ -28,6 +28,9 @@ from . import _cabi
 __all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_func", "KernelTimer"]
 
 FIXED_METHODS = ("euler", "midpoint", "rk4")
+# Store the MLP evaluations of a forward solve for its discrete reverse sweep (12.5 GB per 2^20 x 100 rk4 solve at
+# S = 5; the sweep then skips ~60 % of its arithmetic).  Set to False to re-evaluate instead (no extra memory).
+EVAL_CHECKPOINTS = True
 
 
 class KernelTimer:
@@ -218,6 +221,8 @@ class _LatentFixedSolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, y0, W1, b1, Wg, bg, Wd, bd, Wa, ba, Wb, bb, t, method_id, mode, layout):
         B, L = z.shape
+        # evaluation checkpoints for the discrete reverse sweep (see slode_b200.h): only when a backward can follow
+        want_ckpt = (mode == _cabi.BWD_DISCRETE and EVAL_CHECKPOINTS and any(ctx.needs_input_grad))
         H = W1.shape[0]
         S = Wg.shape[0]
         T = t.numel()
@@ -230,12 +235,17 @@ class _LatentFixedSolve(torch.autograd.Function):
             sol = torch.empty((B, T, S), device=z.device, dtype=torch.float32).permute(1, 0, 2)
         else:
             sol = torch.empty((T, B, S), device=z.device, dtype=torch.float32)
+        ckpt = None
+        if want_ckpt and B > 0 and T > 1:
+            n = _cabi.lib().slode_eval_ckpt_floats(method_id, B, T, S)
+            ckpt = torch.empty(n, device=z.device, dtype=torch.float32)
         with torch.cuda.device(z.device), _timed("fwd"):
             rc = _cabi.lib().slode_latent_fixed_fwd(
                 method_id, B, T, L, H, S, _ptr(t), _ptr(zc), *[_ptr(x) for x in w], *[_ptr(x) for x in x0w], _ptr(y0c),
-                _ptr(sol), sol.stride(0), sol.stride(1), torch.cuda.current_stream().cuda_stream)
+                _ptr(sol), sol.stride(0), sol.stride(1), _ptr(ckpt), torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "slode_latent_fixed_fwd")
         ctx.save_for_backward(zc, *w, t, sol, *(x0w if fx0 else []))
+        ctx.ckpt = ckpt
         ctx.cfg = (method_id, mode, fx0)
         return sol
 
@@ -261,8 +271,10 @@ class _LatentFixedSolve(torch.autograd.Function):
             rc = _cabi.lib().slode_latent_fixed_bwd(
                 method_id, mode, B, T, L, H, S, _ptr(t), _ptr(zc), _ptr(W1), _ptr(b1), _ptr(Wg), _ptr(bg), _ptr(Wd),
                 _ptr(bd), *[_ptr(x) for x in x0w], _ptr(sol), sol.stride(0), sol.stride(1), _ptr(grad_sol), strides[0],
-                strides[1], _ptr(grad_z), _ptr(grad_y0), _ptr(gp), torch.cuda.current_stream().cuda_stream)
+                strides[1], _ptr(grad_z), _ptr(grad_y0), _ptr(gp), _ptr(ctx.ckpt),
+                torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "slode_latent_fixed_bwd")
+        ctx.ckpt = None  # 120 B per trajectory-step: release it as soon as the sweep has been enqueued
         o = 0
 
         def take(*shape):

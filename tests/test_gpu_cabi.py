@@ -45,7 +45,8 @@ def test_raw_pointer_call_matches_the_python_api():
                                    Wg.data_ptr(), bg.data_ptr(), Wd.data_ptr(), bd.data_ptr(),
                                    n0.weight.detach().data_ptr(), n0.bias.detach().data_ptr(),
                                    n2.weight.detach().data_ptr(), n2.bias.detach().data_ptr(), None,
-                                   sol2.data_ptr(), B * S, S, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                   sol2.data_ptr(), B * S, S, None,
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, L_.slode_last_error()
     torch.cuda.synchronize()
     assert torch.equal(sol2, want)
