@@ -57,10 +57,24 @@ def algorithmic_flops(method: str, T: int, H: int, S: int):
     return float(fwd), float(bwd)
 
 
-def algorithmic_bytes(T: int, H: int, S: int):
+def algorithmic_bytes(T: int, H: int, S: int, method: str = "rk4", ckpt: bool = False):
     """(forward, backward) HBM bytes per trajectory of the fused path: fwd reads z (L), writes sol (T*S);
-    bwd reads sol + grad_sol + z, writes grad_z."""
-    return 4.0 * (L + T * S), 4.0 * (2 * T * S + 2 * L)
+    bwd reads sol + grad_sol + z, writes grad_z.  With evaluation checkpoints the forward also writes, and the
+    reverse sweep reads, 2S floats per MLP evaluation."""
+    evals = {"euler": T - 1, "midpoint": 2 * (T - 1), "rk4": 3 * (T - 1) + 1}[method]
+    ck = 4.0 * evals * 2 * S if ckpt else 0.0
+    return 4.0 * (L + T * S) + ck, 4.0 * (2 * T * S + 2 * L) + ck
+
+
+def checkpointed_bwd_flops(method: str, T: int, H: int, S: int):
+    """Reverse sweep with evaluation checkpoints: hidden-layer gates (2H per evaluation), stage recompute from the
+    stored sigmoids, adjoint recurrences, prefix sums, epilogue -- no head products."""
+    steps = T - 1
+    stages = {"euler": 1, "midpoint": 2, "rk4": 4}[method]
+    evals = {"euler": steps, "midpoint": 2 * steps, "rk4": 3 * steps + 1}[method]
+    combine = {"euler": 2 * S, "midpoint": 4 * S, "rk4": 16 * S}[method]
+    return float(evals * 2 * H + steps * (stages * 2 * S + combine) + steps * stages * 24 * S + H * 2 * (14 * 2 * S)
+                 + 2 * (4 * L * H + 2 * H * S))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -186,6 +200,8 @@ def workload_config(args, B_per_gpu, n):
             "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L, "sol_layout": getattr(args, "layout", "tbs"),
             "ode_hidden_dim": H, "ode_state_dim": S, "solver": args.method,
             "gradient": "odeint_adjoint emulation" if args.adjoint else "discrete adjoint (odeint + autograd parity)",
+            "reverse_sweep": ("recomputes the MLP evaluations" if (getattr(args, "no_eval_ckpt", False) or args.adjoint)
+                              else "reads the forward's evaluation checkpoints (12.5 GB per 2^20 x 100 solve)"),
             "parallelism": f"trajectory-sharded x{n}, one flat all-reduce of parameter gradients",
             "l2": "inputs larger than L2 (sol / grad_sol are 2.1 GB each per GPU vs 126 MB L2)"}
 
@@ -202,6 +218,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8192, help="trajectories per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--no-eval-ckpt", action="store_true",
+                    help="reverse sweep re-evaluates the MLP instead of reading the forward's evaluation checkpoints")
     ap.add_argument("--layout", default="tbs", choices=["tbs", "bts"],
                     help="storage of the resident step's solution: (T,B,S) torchdiffeq's, or (B,T,S) the decoder's")
     args = ap.parse_args()
@@ -215,6 +233,9 @@ def main():
     import structured_latent_odes_b200 as slode
     from structured_latent_odes_b200 import _cabi, sharding
     from structured_latent_odes_b200.torchdiffeq_api import KernelTimer
+    from structured_latent_odes_b200 import torchdiffeq_api as _api_cfg
+    if args.no_eval_ckpt:
+        _api_cfg.EVAL_CHECKPOINTS = False
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -352,8 +373,12 @@ def main():
     d2h = out_host.numel() * 4
 
     if rank == 0:
+        from structured_latent_odes_b200 import torchdiffeq_api as _api
+        ckpt = bool(_api.EVAL_CHECKPOINTS) and not args.adjoint
         ff, fb = algorithmic_flops(args.method, T, H, S)
-        bf, bb = algorithmic_bytes(T, H, S)
+        if ckpt:
+            fb = checkpointed_bwd_flops(args.method, T, H, S)
+        bf, bb = algorithmic_bytes(T, H, S, args.method, ckpt)
         fwd_ms = sum(ktimes["fwd"]) / max(len(ktimes["fwd"]), 1)
         bwd_ms = sum(ktimes["bwd"]) / max(len(ktimes["bwd"]), 1)
         peaks = {}
@@ -362,9 +387,9 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
+        traffic_map = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"bwd_{args.method}_{int(args.adjoint)}")
+            traffic_map = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
         achieved_b = B * fb / (bwd_ms * 1e-3) / 1e12
@@ -379,20 +404,37 @@ def main():
                     "what": f"pinned z (B,{L}) + observations (B,{O},{T}) -> solve -> q50 head (slode_heads) + MSE -> backward -> "
                             f"loss + {reducer.numel} parameter gradients on the host; {nchunk} double-buffered chunks"},
             "gpu_launches": n_launches,
-            "roofline": {"bound": "fp32", "kernel": "mlp_fixed_bwd_kernel (reverse sweep, dominant)",
-                         "achieved": achieved_b, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved_b / FP32_PEAK_TFLOPS, "traffic": traffic,
-                         "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz; FFMA2 micro-benchmark measured 74.0 "
-                                        "(profiles/r01/fp32_pipes_microbench.jsonl); MEASURED_PEAKS.json has no fp32 entry",
-                         "algorithmic_flop_per_launch": B * fb, "ms_per_launch": bwd_ms,
-                         "hbm": {"achieved": B * bb / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": B * bb / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "measured" if peaks else "fallback"}},
-            "roofline_fwd": {"bound": "fp32", "kernel": "mlp_fixed_fwd_kernel", "achieved": achieved_f,
-                             "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_f / FP32_PEAK_TFLOPS,
-                             "algorithmic_flop_per_launch": B * ff, "ms_per_launch": fwd_ms,
-                             "hbm": {"achieved": B * bf / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": B * bf / (fwd_ms * 1e-3) / 1e9 / hbm_peak}},
         }
+        hbm_src = "measured" if peaks else "fallback"
+        rl_b = {"kernel": "mlp_fixed_bwd_kernel (reverse sweep" + (", evaluation checkpoints)" if ckpt else ")"),
+                "ms_per_launch": bwd_ms, "algorithmic_flop_per_launch": B * fb, "algorithmic_bytes_per_launch": B * bb,
+                "fp32": {"achieved": achieved_b, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_b / FP32_PEAK_TFLOPS},
+                "hbm": {"achieved": B * bb / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": B * bb / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}}
+        rl_f = {"kernel": "mlp_fixed_fwd_kernel", "ms_per_launch": fwd_ms, "algorithmic_flop_per_launch": B * ff,
+                "algorithmic_bytes_per_launch": B * bf,
+                "fp32": {"achieved": achieved_f, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_f / FP32_PEAK_TFLOPS},
+                "hbm": {"achieved": B * bf / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": B * bf / (fwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}}
+        fp32_src = ("148 SM x 128 lanes x 2 x 1.965 GHz; FFMA2 micro-benchmark measured 74.0 "
+                    "(profiles/r01/fp32_pipes_microbench.jsonl); MEASURED_PEAKS.json has no fp32 entry")
+
+        def flat(r, traffic_key):
+            """contract shape: the roofline that binds the kernel on top, the other one beside it"""
+            bound = "hbm" if r["hbm"]["frac"] >= r["fp32"]["frac"] else "fp32"
+            top = r[bound]
+            out = {"bound": bound, "kernel": r["kernel"], "achieved": top["achieved"], "peak": top["peak"],
+                   "unit": top["unit"], "frac": top["frac"], "traffic": traffic_map.get(traffic_key),
+                   "peak_source": top.get("peak_source", fp32_src) if bound == "hbm" else fp32_src,
+                   "ms_per_launch": r["ms_per_launch"], "algorithmic_flop_per_launch": r["algorithmic_flop_per_launch"],
+                   "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"]}
+            out["fp32" if bound == "hbm" else "hbm"] = r["fp32" if bound == "hbm" else "hbm"]
+            return out
+
+        tag = f"{args.method}_{int(args.adjoint)}" + ("_ckpt" if ckpt else "")
+        dominant_is_bwd = bwd_ms >= fwd_ms
+        line["roofline"] = flat(rl_b if dominant_is_bwd else rl_f, ("bwd_" if dominant_is_bwd else "fwd_") + tag)
+        line["roofline_other"] = flat(rl_f if dominant_is_bwd else rl_b, ("fwd_" if dominant_is_bwd else "bwd_") + tag)
         if not args.no_cpu_baseline and world == 1:
             reps = 3
             times, cores = time_cpu_reference(args.method, args.adjoint, args.ref_batch, reps)

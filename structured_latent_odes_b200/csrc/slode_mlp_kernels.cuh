@@ -383,6 +383,14 @@ __device__ __forceinline__ void ckpt_load(const f2* __restrict__ ckpt, int64_t e
   }
 }
 
+// pull one evaluation's checkpoint (2S pairs, one cache line per (output, warp)) towards L1 an iteration ahead
+template <int S>
+__device__ __forceinline__ void ckpt_prefetch(const f2* __restrict__ ckpt, int64_t e, int64_t npairs, int64_t pair) {
+  const f2* p = ckpt + e * (2 * S) * npairs + pair;
+#pragma unroll
+  for (int k = 0; k < 2 * S; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k * npairs));
+}
+
 // relu gates of NE evaluation times from the hidden layer alone (the reverse sweep with checkpoints needs the
 // gates for the prefix-sum bookkeeping but not the heads)
 template <int H, int NE, class CLoad>
@@ -1116,6 +1124,12 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         vprefetch<S>(xs1 + (int64_t)(i - 1) * st);
         vprefetch<S>(gs0 + (int64_t)(i - 1) * gst);
         vprefetch<S>(gs1 + (int64_t)(i - 1) * gst);
+        if (CKPT) {
+          constexpr int per_step = (METHOD == SLODE_METHOD_RK4) ? 3 : (METHOD == SLODE_METHOD_MIDPOINT ? 2 : 1);
+#pragma unroll
+          for (int e = 0; e < per_step; ++e)
+            ckpt_prefetch<S>(eval_ckpt, (int64_t)per_step * (i - 1) + e, npairs, pair);
+        }
       }
 
       if (MODE == SLODE_BWD_DISCRETE) {
