@@ -129,7 +129,7 @@ int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
  *
  * eval_ckpt (optional, may be NULL): slode_eval_ckpt_floats(method, B, T, S) floats.  When given, the forward stores
  * the growth / degradation sigmoids of every MLP evaluation of the solve there (120 B per trajectory and rk4 step at
- * S = 5) and the DISCRETE reverse sweep reads them back instead of re-evaluating the MLP (it then only recomputes the
+ * S = 5, stored per tile of 256 trajectories) and the DISCRETE reverse sweep reads them back instead of re-evaluating the MLP (it then only recomputes the
  * hidden-layer gates): trades 12.5 GB of HBM per 2^20 x 100 solve for ~60 % of the reverse sweep's arithmetic.  The
  * odeint_adjoint mode evaluates at its own stage times and ignores it.
  */

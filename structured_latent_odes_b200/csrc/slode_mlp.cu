@@ -310,5 +310,6 @@ extern "C" int64_t slode_eval_ckpt_floats(int method, int64_t B, int T, int S) {
     case SLODE_METHOD_RK4: nev = 3 * (int64_t)(T - 1) + 1; break;
     default: return -1;
   }
-  return nev * ((B + 1) / 2) * (2 * (int64_t)S) * 2;
+  const int64_t tiles = ((B + 1) / 2 + 127) / 128;  // tile-major: every tile of 128 trajectory pairs owns nev * 2S KB
+  return tiles * nev * (2 * (int64_t)S) * 128 * 2;
 }

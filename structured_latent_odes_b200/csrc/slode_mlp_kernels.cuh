@@ -355,40 +355,44 @@ __device__ __forceinline__ void mlp_eval(const float (&t)[NE], CLoad cj, Vec<S> 
 
 // ---------------------------------------------------------------------------------------------
 // evaluation checkpoints: the (A, -D) of every MLP evaluation of a solve, in the threads' own pair layout
-//   element (evaluation e, head output k, trajectory pair p) = one f2 at ckpt[(e * 2S + k) * npairs + p]
-// (output-major: for a fixed k the 32 threads of a warp write / read 256 contiguous bytes)
+//   element (tile, evaluation e, head output k, thread) = one f2 at ckpt[((tile * n_evals + e) * 2S + k) * 128 + thread]
+// Tile-major: the 256 trajectories of a tile own one contiguous region (n_evals x 2S KB) that the forward fills
+// front to back and the reverse sweep streams back to front -- whole DRAM pages, 256 contiguous bytes per warp and
+// (evaluation, output).
 // Evaluation order: euler e = i (time t_i); midpoint e = 2i (t_i), 2i+1 (t_i + dt/2); rk4 e = 0 (t_0) and
 // 3i+1, 3i+2, 3i+3 = (t_i + dt/3, t_i + 2dt/3, t_{i+1}).  120 B per trajectory and rk4 step at S = 5: writing
 // them costs the forward ~5 clk/SM per trajectory-step of HBM time, re-computing them costs the reverse sweep
 // >= 6.4 clk/SM of FMA time at PEAK (13 measured) -- on 180 GB of HBM3e the checkpoint is the better trade.
 // ---------------------------------------------------------------------------------------------
+template <int METHOD>
+__host__ __device__ constexpr int64_t ckpt_evals(int T) {
+  return METHOD == SLODE_METHOD_RK4 ? 3 * (int64_t)(T - 1) + 1 : (METHOD == SLODE_METHOD_MIDPOINT ? 2 * (int64_t)(T - 1) : T - 1);
+}
 template <int S>
-__device__ __forceinline__ void ckpt_store(f2* __restrict__ ckpt, int64_t e, int64_t npairs, int64_t pair,
-                                           const Vec<S>& A, const Vec<S>& ND) {
-  f2* p = ckpt + e * (2 * S) * npairs + pair;
+__device__ __forceinline__ void ckpt_store(f2* __restrict__ tile_base, int64_t e, const Vec<S>& A, const Vec<S>& ND) {
+  f2* p = tile_base + e * (2 * S) * kBlock + threadIdx.x;
 #pragma unroll
   SLODE_FOR_S {
-    p[s * npairs] = A.v[s];
-    p[(S + s) * npairs] = ND.v[s];
+    p[s * kBlock] = A.v[s];
+    p[(S + s) * kBlock] = ND.v[s];
   }
 }
 template <int S>
-__device__ __forceinline__ void ckpt_load(const f2* __restrict__ ckpt, int64_t e, int64_t npairs, int64_t pair,
-                                          Vec<S>& A, Vec<S>& ND) {
-  const f2* p = ckpt + e * (2 * S) * npairs + pair;
+__device__ __forceinline__ void ckpt_load(const f2* __restrict__ tile_base, int64_t e, Vec<S>& A, Vec<S>& ND) {
+  const f2* p = tile_base + e * (2 * S) * kBlock + threadIdx.x;
 #pragma unroll
   SLODE_FOR_S {
-    A.v[s] = __ldg(p + s * npairs);
-    ND.v[s] = __ldg(p + (S + s) * npairs);
+    A.v[s] = __ldg(p + s * kBlock);
+    ND.v[s] = __ldg(p + (S + s) * kBlock);
   }
 }
 
 // pull one evaluation's checkpoint (2S pairs, one cache line per (output, warp)) towards L1 an iteration ahead
 template <int S>
-__device__ __forceinline__ void ckpt_prefetch(const f2* __restrict__ ckpt, int64_t e, int64_t npairs, int64_t pair) {
-  const f2* p = ckpt + e * (2 * S) * npairs + pair;
+__device__ __forceinline__ void ckpt_prefetch(const f2* __restrict__ tile_base, int64_t e) {
+  const f2* p = tile_base + e * (2 * S) * kBlock + threadIdx.x;
 #pragma unroll
-  for (int k = 0; k < 2 * S; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k * npairs));
+  for (int k = 0; k < 2 * S; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k * kBlock));
 }
 
 // relu gates of NE evaluation times from the hidden layer alone (the reverse sweep with checkpoints needs the
@@ -627,7 +631,6 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
                      const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, LatentSrc lat,
                      f2* __restrict__ eval_ckpt) {
   extern __shared__ __align__(16) float fwd_dyn[];
-  const int64_t npairs = (B + 1) / 2;
   __shared__ __align__(16) OutStage<S> ostage;
   const bool rows_in_time = (st == S);  // (B,T,S)-contiguous storage
   // wide hidden layers: the per-trajectory c_j do not fit in registers next to the accumulators -> shared memory
@@ -642,8 +645,9 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
-    const int64_t pair = tile * kBlock + threadIdx.x;
-    const bool save = eval_ckpt != nullptr && pi.ok0;
+    // every thread stores (tail threads their duplicate of trajectory B-1): the tile's region holds finite numbers
+    const bool save = eval_ckpt != nullptr;
+    f2* const ck = eval_ckpt + tile * ckpt_evals<METHOD>(T) * (2 * S) * kBlock;
     f2 c2[C_IN_SMEM ? 1 : H];
     Vec<S> x;
     {
@@ -681,7 +685,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       Gate<H> ng[1];
       const float te[1] = {t0};
       mlp_eval<H, S, 1, false, 1>(te, cj, A, D, ng);
-      if (save) ckpt_store<S>(eval_ckpt, 0, npairs, pair, A[0], D[0]);
+      if (save) ckpt_store<S>(ck, 0, A[0], D[0]);
       k1 = rhs<S>(A[0], D[0], x);
     }
 
@@ -694,7 +698,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Gate<H> ng[1];
         const float te[1] = {t0};
         mlp_eval<H, S, 1, false, 0>(te, cj, A, D, ng);
-        if (save) ckpt_store<S>(eval_ckpt, i, npairs, pair, A[0], D[0]);
+        if (save) ckpt_store<S>(ck, i, A[0], D[0]);
         x = vaxpy<S>(dt, rhs<S>(A[0], D[0], x), x);
       } else if (METHOD == SLODE_METHOD_MIDPOINT) {
         const float half_dt = 0.5f * dt;
@@ -703,8 +707,8 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         const float te[2] = {t0, t0 + half_dt};
         mlp_eval<H, S, 2, false, 0>(te, cj, A, D, ng);
         if (save) {
-          ckpt_store<S>(eval_ckpt, 2 * (int64_t)i, npairs, pair, A[0], D[0]);
-          ckpt_store<S>(eval_ckpt, 2 * (int64_t)i + 1, npairs, pair, A[1], D[1]);
+          ckpt_store<S>(ck, 2 * (int64_t)i, A[0], D[0]);
+          ckpt_store<S>(ck, 2 * (int64_t)i + 1, A[1], D[1]);
         }
         const Vec<S> ym = vaxpy<S>(half_dt, rhs<S>(A[0], D[0], x), x);
         x = vaxpy<S>(dt, rhs<S>(A[1], D[1], ym), x);
@@ -715,7 +719,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         mlp_eval<H, S, 3, false, 0>(te, cj, A, D, ng);
         if (save) {
 #pragma unroll
-          for (int e = 0; e < 3; ++e) ckpt_store<S>(eval_ckpt, 3 * (int64_t)i + 1 + e, npairs, pair, A[e], D[e]);
+          for (int e = 0; e < 3; ++e) ckpt_store<S>(ck, 3 * (int64_t)i + 1 + e, A[e], D[e]);
         }
         Vec<S> y = vaxpy<S>(dt * kOneThird, k1, x);
         const Vec<S> k2 = rhs<S>(A[0], D[0], y);
@@ -1038,7 +1042,6 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
                      float* __restrict__ flip_ws, LatentSrc lat, float* __restrict__ grad_z,
                      const f2* __restrict__ eval_ckpt) {
   static_assert(!CKPT || MODE == SLODE_BWD_DISCRETE, "evaluation checkpoints serve the discrete sweep");
-  const int64_t npairs = (B + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem<H, S>& sm = *reinterpret_cast<BwdSmem<H, S>*>(smem_raw);
   constexpr int K2 = 2 * S;
@@ -1070,8 +1073,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
-    // (checkpoints of a fully masked-off thread do not exist: it reads pair 0's, its cotangents are zero anyway)
-    const int64_t pair = pi.ok0 ? tile * kBlock + tid : 0;
+    const f2* const ck = CKPT ? eval_ckpt + tile * ckpt_evals<METHOD>(T) * (2 * S) * kBlock : nullptr;
     // a masked-off half aliases trajectory B-1 (owned by another half): it must never touch grad_c
     float* gc0 = pi.ok0 ? grad_c + pi.b0 * H : nullptr;
     float* gc1 = pi.ok1 ? grad_c + pi.b1 * H : nullptr;
@@ -1104,7 +1106,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       Gate<H> g[1];
       const float te[1] = {t1};
       if (CKPT) {
-        ckpt_load<S>(eval_ckpt, 3 * (int64_t)(T - 1), npairs, pair, A[0], D[0]);
+        ckpt_load<S>(ck, 3 * (int64_t)(T - 1), A[0], D[0]);
         gates_only<H, 1>(sm.w1t, te, cj, g);
       } else {
         mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
@@ -1128,7 +1130,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           constexpr int per_step = (METHOD == SLODE_METHOD_RK4) ? 3 : (METHOD == SLODE_METHOD_MIDPOINT ? 2 : 1);
 #pragma unroll
           for (int e = 0; e < per_step; ++e)
-            ckpt_prefetch<S>(eval_ckpt, (int64_t)per_step * (i - 1) + e, npairs, pair);
+            ckpt_prefetch<S>(ck, (int64_t)per_step * (i - 1) + e);
         }
       }
 
@@ -1139,7 +1141,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Gate<H> g[1];
           const float te[1] = {t0};
           if (CKPT) {
-            ckpt_load<S>(eval_ckpt, i, npairs, pair, A[0], D[0]);
+            ckpt_load<S>(ck, i, A[0], D[0]);
             gates_only<H, 1>(sm.w1t, te, cj, g);
           } else {
             mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
@@ -1154,8 +1156,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Gate<H> g[2];
           const float te[2] = {t0, t0 + half_dt};
           if (CKPT) {
-            ckpt_load<S>(eval_ckpt, 2 * (int64_t)i, npairs, pair, A[0], D[0]);
-            ckpt_load<S>(eval_ckpt, 2 * (int64_t)i + 1, npairs, pair, A[1], D[1]);
+            ckpt_load<S>(ck, 2 * (int64_t)i, A[0], D[0]);
+            ckpt_load<S>(ck, 2 * (int64_t)i + 1, A[1], D[1]);
             gates_only<H, 2>(sm.w1t, te, cj, g);
           } else {
             mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
@@ -1177,7 +1179,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           const float te[3] = {t0, t0 + dt * kOneThird, t0 + dt * kTwoThirds};
           if (CKPT) {
 #pragma unroll
-            for (int e = 0; e < 3; ++e) ckpt_load<S>(eval_ckpt, 3 * (int64_t)i + e, npairs, pair, A[e], D[e]);
+            for (int e = 0; e < 3; ++e) ckpt_load<S>(ck, 3 * (int64_t)i + e, A[e], D[e]);
             gates_only<H, 3>(sm.w1t, te, cj, g);
           } else {
             mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
