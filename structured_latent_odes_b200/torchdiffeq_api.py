@@ -25,7 +25,8 @@ from torch import nn
 
 from . import _cabi
 
-__all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_func", "KernelTimer"]
+__all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_func", "KernelTimer", "solve_latent",
+           "solve_fixed_from_c"]
 
 FIXED_METHODS = ("euler", "midpoint", "rk4")
 # Store the MLP evaluations of a forward solve for its discrete reverse sweep (12.5 GB per 2^20 x 100 rk4 solve at
@@ -211,6 +212,16 @@ class _MlpFixedSolve(torch.autograd.Function):
         gWd = grad_w[o:o + S * H].view(S, H); o += S * H
         gbd = grad_w[o:o + S]
         return grad_y0, grad_c, gw1t, gWg, gbg, gWd, gbd, None, None, None, None
+
+
+def solve_fixed_from_c(y0, c, w1t, Wg, bg, Wd, bd, t, method, adjoint=False, layout="tbs"):
+    """The solve from precomputed ``c = z W1[:,1:]^T + b1`` (B,H) and ``y0`` (B,S): the ``slode_mlp_fixed_*`` entry
+    points, for hosts that already hold those (gradients flow to ``y0``, ``c`` and the five weight tensors)."""
+    if method not in FIXED_METHODS:
+        raise NotImplementedError(method)
+    t = t.detach().to(device=y0.device, dtype=torch.float32).contiguous()
+    mode = _cabi.BWD_TDE_ADJOINT if adjoint else _cabi.BWD_DISCRETE
+    return _MlpFixedSolve.apply(y0, c, w1t, Wg, bg, Wd, bd, t, _cabi.METHODS[method], mode, layout)
 
 
 class _LatentFixedSolve(torch.autograd.Function):

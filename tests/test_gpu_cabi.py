@@ -50,3 +50,33 @@ def test_raw_pointer_call_matches_the_python_api():
     assert rc == 0, L_.slode_last_error()
     torch.cuda.synchronize()
     assert torch.equal(sol2, want)
+
+
+@pytest.mark.parametrize("method,adjoint", [("rk4", False), ("midpoint", True), ("euler", False)])
+def test_c_based_entry_points_match_the_fused_path(method, adjoint):
+    """slode_mlp_fixed_fwd / _bwd (precomputed c and y0, gradients to c / y0 / weights) against the fused
+    slode_latent_fixed_* path through autograd: same trajectories and the same gradients for every parameter."""
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    o = U.make_oracle("cvs", method, adjoint)
+    p = U.make_product(o)
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(150, 15, generator=g).cuda()
+    G = torch.randn(150, 86, 5, generator=g).cuda()
+    sol_f, gz_f, gr_f = U.run_fwd_bwd(p, z, G)
+    p.zero_grad()
+    zz = z.clone().requires_grad_(True)
+    d = p.dynamics
+    W1 = d.dynamics_hidden.weight
+    zc = zz.detach() if adjoint else zz   # odeint_adjoint: no gradient to z through the dynamics
+    c = torch.addmm(d.dynamics_hidden.bias, zc, W1[:, 1:].t())
+    y0 = p.initialize_state(zz)
+    sol = api.solve_fixed_from_c(y0, c, W1[:, 0], d.dyanamics_growth.weight, d.dyanamics_growth.bias,
+                                 d.dyanmics_degradation.weight, d.dyanmics_degradation.bias, p.times, method,
+                                 adjoint=adjoint).permute(1, 0, 2)
+    (sol * G).sum().backward()
+    assert U.rel_err(sol, sol_f) < 2e-6
+    assert U.rel_err(zz.grad, gz_f) < 1e-5
+    for k, v in p.named_parameters():
+        if ".prod." in k or ".degr." in k:
+            continue
+        assert U.rel_err(v.grad, gr_f[k]) < 1e-5, k
