@@ -355,10 +355,11 @@ __device__ __forceinline__ void mlp_eval(const float (&t)[NE], CLoad cj, Vec<S> 
 
 // ---------------------------------------------------------------------------------------------
 // evaluation checkpoints: the (A, -D) of every MLP evaluation of a solve, in the threads' own pair layout
-//   element (tile, evaluation e, head output k, thread) = one f2 at ckpt[((tile * n_evals + e) * 2S + k) * 128 + thread]
-// Tile-major: the 256 trajectories of a tile own one contiguous region (n_evals x 2S KB) that the forward fills
-// front to back and the reverse sweep streams back to front -- whole DRAM pages, 256 contiguous bytes per warp and
-// (evaluation, output).
+//   element (tile, warp w, evaluation e, head output k, lane) = one f2 at
+//       ckpt[(((tile * 4 + w) * n_evals + e) * 2S + k) * 32 + lane]
+// Warp-major: the 64 trajectories of a warp own one contiguous stream (n_evals x 2S x 256 B) that the forward
+// fills front to back and the reverse sweep consumes back to front -- one interval's evaluations are ONE contiguous
+// run (7.5 KB for rk4 at S = 5), which the sweep fetches with a single bulk copy per warp and interval.
 // Evaluation order: euler e = i (time t_i); midpoint e = 2i (t_i), 2i+1 (t_i + dt/2); rk4 e = 0 (t_0) and
 // 3i+1, 3i+2, 3i+3 = (t_i + dt/3, t_i + 2dt/3, t_{i+1}).  120 B per trajectory and rk4 step at S = 5: writing
 // them costs the forward ~5 clk/SM per trajectory-step of HBM time, re-computing them costs the reverse sweep
@@ -368,31 +369,36 @@ template <int METHOD>
 __host__ __device__ constexpr int64_t ckpt_evals(int T) {
   return METHOD == SLODE_METHOD_RK4 ? 3 * (int64_t)(T - 1) + 1 : (METHOD == SLODE_METHOD_MIDPOINT ? 2 * (int64_t)(T - 1) : T - 1);
 }
+// start of the calling warp's checkpoint stream
 template <int S>
-__device__ __forceinline__ void ckpt_store(f2* __restrict__ tile_base, int64_t e, const Vec<S>& A, const Vec<S>& ND) {
-  f2* p = tile_base + e * (2 * S) * kBlock + threadIdx.x;
+__device__ __forceinline__ int64_t ckpt_warp_offset(int64_t tile, int64_t n_evals) {
+  return ((tile * (kBlock / 32) + (threadIdx.x >> 5)) * n_evals) * (2 * S) * 32;
+}
+template <int S>
+__device__ __forceinline__ void ckpt_store(f2* __restrict__ warp_base, int64_t e, const Vec<S>& A, const Vec<S>& ND) {
+  f2* p = warp_base + e * (2 * S) * 32 + (threadIdx.x & 31);
 #pragma unroll
   SLODE_FOR_S {
-    p[s * kBlock] = A.v[s];
-    p[(S + s) * kBlock] = ND.v[s];
+    p[s * 32] = A.v[s];
+    p[(S + s) * 32] = ND.v[s];
   }
 }
 template <int S>
-__device__ __forceinline__ void ckpt_load(const f2* __restrict__ tile_base, int64_t e, Vec<S>& A, Vec<S>& ND) {
-  const f2* p = tile_base + e * (2 * S) * kBlock + threadIdx.x;
+__device__ __forceinline__ void ckpt_load(const f2* __restrict__ warp_base, int64_t e, Vec<S>& A, Vec<S>& ND) {
+  const f2* p = warp_base + e * (2 * S) * 32 + (threadIdx.x & 31);
 #pragma unroll
   SLODE_FOR_S {
-    A.v[s] = __ldg(p + s * kBlock);
-    ND.v[s] = __ldg(p + (S + s) * kBlock);
+    A.v[s] = __ldg(p + s * 32);
+    ND.v[s] = __ldg(p + (S + s) * 32);
   }
 }
 
 // pull one evaluation's checkpoint (2S pairs, one cache line per (output, warp)) towards L1 an iteration ahead
 template <int S>
-__device__ __forceinline__ void ckpt_prefetch(const f2* __restrict__ tile_base, int64_t e) {
-  const f2* p = tile_base + e * (2 * S) * kBlock + threadIdx.x;
+__device__ __forceinline__ void ckpt_prefetch(const f2* __restrict__ warp_base, int64_t e) {
+  const f2* p = warp_base + e * (2 * S) * 32 + (threadIdx.x & 31);
 #pragma unroll
-  for (int k = 0; k < 2 * S; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k * kBlock));
+  for (int k = 0; k < 2 * S; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k * 32));
 }
 
 // relu gates of NE evaluation times from the hidden layer alone (the reverse sweep with checkpoints needs the
@@ -430,6 +436,51 @@ __device__ __forceinline__ void gates_only(const float* __restrict__ w1t_smem, c
       const uint32_t low = (nw == 32) ? 0xffffffffu : ((1u << nw) - 1u);
       gate[e].w[0][w] = (~neg[e][0][w]) & low;
       gate[e].w[1][w] = (~neg[e][1][w]) & low;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-warp bulk-copy (TMA, 1-D) staging of the checkpoints: lane 0 streams the evaluations of the interval two
+// ahead into the warp's own shared-memory stage while the warp works; completion arrives on the warp's mbarrier.
+// No block-wide barrier is involved (a first version that shared the stages across the block lost more to the
+// barrier than the copies hid).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1 << 26)) __trap();  // a lost copy must not hang the GPU
+  }
+}
+template <int S, int NE>
+__device__ __forceinline__ void stage_read(const f2* __restrict__ st, Vec<S> (&A)[NE], Vec<S> (&ND)[NE]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+#pragma unroll
+    SLODE_FOR_S {
+      A[e].v[s] = st[(e * 2 * S + s) * 32 + lane];
+      ND[e].v[s] = st[(e * 2 * S + S + s) * 32 + lane];
     }
   }
 }
@@ -647,7 +698,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     const PairIdx pi = pair_index(tile, B);
     // every thread stores (tail threads their duplicate of trajectory B-1): the tile's region holds finite numbers
     const bool save = eval_ckpt != nullptr;
-    f2* const ck = eval_ckpt + tile * ckpt_evals<METHOD>(T) * (2 * S) * kBlock;
+    f2* const ck = eval_ckpt + ckpt_warp_offset<S>(tile, ckpt_evals<METHOD>(T));
     f2 c2[C_IN_SMEM ? 1 : H];
     Vec<S> x;
     {
@@ -1046,8 +1097,24 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   BwdSmem<H, S>& sm = *reinterpret_cast<BwdSmem<H, S>*>(smem_raw);
   constexpr int K2 = 2 * S;
   const int tid = threadIdx.x;
+  // checkpointed sweep (S <= 5): per-warp double-buffered stages filled by bulk copies
+  constexpr bool STAGED = CKPT && S <= 5;
+  constexpr int per_step = (METHOD == SLODE_METHOD_RK4) ? 3 : (METHOD == SLODE_METHOD_MIDPOINT ? 2 : 1);
+  constexpr int kStageF2 = per_step * K2 * 32;                           // f2 per warp and interval
+  constexpr int kWarps = kBlock / 32;
+  constexpr size_t kStageBytes = STAGED ? (size_t)kWarps * 2 * kStageF2 * sizeof(f2) + kWarps * 2 * sizeof(uint64_t) : 0;
+  unsigned char* stage_raw = smem_raw + (sizeof(BwdSmem<H, S>) + 15) / 16 * 16;
+  const int warp = tid >> 5, lane = tid & 31;
+  f2* const wstage = reinterpret_cast<f2*>(stage_raw) + (size_t)warp * 2 * kStageF2;   // this warp's two stages
+  uint64_t* const wbars = reinterpret_cast<uint64_t*>(stage_raw + (size_t)kWarps * 2 * kStageF2 * sizeof(f2)) + warp * 2;
+  uint32_t uses0 = 0u, uses1 = 0u;  // completed fills of each stage (its mbarrier's phase parity)
+  if (STAGED && lane == 0) {
+    mbar_init(&wbars[0], 1);
+    mbar_init(&wbars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // fused mode: staged weights of the two small nets, then the block accumulators of their gradients
-  float* ext = reinterpret_cast<float*>(smem_raw + (sizeof(BwdSmem<H, S>) + 15) / 16 * 16);
+  float* ext = reinterpret_cast<float*>(stage_raw + (kStageBytes + 15) / 16 * 16);
   LatSmem ls{};
   float* lat_acc = nullptr;
   int n_lat_acc = 0;
@@ -1073,7 +1140,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
-    const f2* const ck = CKPT ? eval_ckpt + tile * ckpt_evals<METHOD>(T) * (2 * S) * kBlock : nullptr;
+    const f2* const ck = CKPT ? eval_ckpt + ckpt_warp_offset<S>(tile, ckpt_evals<METHOD>(T)) : nullptr;
     // a masked-off half aliases trajectory B-1 (owned by another half): it must never touch grad_c
     float* gc0 = pi.ok0 ? grad_c + pi.b0 * H : nullptr;
     float* gc1 = pi.ok1 ? grad_c + pi.b1 * H : nullptr;
@@ -1097,6 +1164,17 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     const f2 live = pk(pi.ok0 ? 1.0f : 0.0f, pi.ok1 ? 1.0f : 0.0f);
     Vec<S> lam = vscale2<S>(vload2<S>(gs0 + (int64_t)(T - 1) * gst, gs1 + (int64_t)(T - 1) * gst), live);
 
+    // lane 0 streams interval n (counted from the end: i = T-2-n) of this warp into its stage n & 1
+    auto stage_issue = [&](int n) {
+      const int st_ = n & 1;
+      mbar_expect_tx(&wbars[st_], (uint32_t)(kStageF2 * sizeof(f2)));
+      bulk_g2s(wstage + st_ * kStageF2, ck + (int64_t)per_step * (T - 2 - n) * K2 * 32, (uint32_t)(kStageF2 * sizeof(f2)),
+               &wbars[st_]);
+    };
+    if (STAGED && lane == 0) {
+      if (T >= 2) stage_issue(0);
+      if (T >= 3) stage_issue(1);
+    }
     Sweep<H, S> sw;
     float t1 = __ldg(tgrid + T - 1);
     bool started = false;
@@ -1126,11 +1204,9 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         vprefetch<S>(xs1 + (int64_t)(i - 1) * st);
         vprefetch<S>(gs0 + (int64_t)(i - 1) * gst);
         vprefetch<S>(gs1 + (int64_t)(i - 1) * gst);
-        if (CKPT) {
-          constexpr int per_step = (METHOD == SLODE_METHOD_RK4) ? 3 : (METHOD == SLODE_METHOD_MIDPOINT ? 2 : 1);
+        if (CKPT && !STAGED) {
 #pragma unroll
-          for (int e = 0; e < per_step; ++e)
-            ckpt_prefetch<S>(ck, (int64_t)per_step * (i - 1) + e);
+          for (int e = 0; e < per_step; ++e) ckpt_prefetch<S>(ck, (int64_t)per_step * (i - 1) + e);
         }
       }
 
@@ -1140,8 +1216,16 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[1], D[1];
           Gate<H> g[1];
           const float te[1] = {t0};
+          if (STAGED) {
+              const int n_ = T - 2 - i, st_ = n_ & 1;
+              mbar_wait(&wbars[st_], (st_ ? uses1 : uses0) & 1u);
+              if (st_) ++uses1; else ++uses0;
+              stage_read<S, 1>(wstage + st_ * kStageF2, A, D);
+              __syncwarp();  // every lane has its copy: the warp's stage can be refilled
+              if (lane == 0 && n_ + 2 <= T - 2) stage_issue(n_ + 2);
+            }
           if (CKPT) {
-            ckpt_load<S>(ck, i, A[0], D[0]);
+            if (!STAGED) ckpt_load<S>(ck, i, A[0], D[0]);
             gates_only<H, 1>(sm.w1t, te, cj, g);
           } else {
             mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
@@ -1155,9 +1239,19 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[2], D[2];
           Gate<H> g[2];
           const float te[2] = {t0, t0 + half_dt};
+          if (STAGED) {
+              const int n_ = T - 2 - i, st_ = n_ & 1;
+              mbar_wait(&wbars[st_], (st_ ? uses1 : uses0) & 1u);
+              if (st_) ++uses1; else ++uses0;
+              stage_read<S, 2>(wstage + st_ * kStageF2, A, D);
+              __syncwarp();  // every lane has its copy: the warp's stage can be refilled
+              if (lane == 0 && n_ + 2 <= T - 2) stage_issue(n_ + 2);
+            }
           if (CKPT) {
-            ckpt_load<S>(ck, 2 * (int64_t)i, A[0], D[0]);
-            ckpt_load<S>(ck, 2 * (int64_t)i + 1, A[1], D[1]);
+            if (!STAGED) {
+              ckpt_load<S>(ck, 2 * (int64_t)i, A[0], D[0]);
+              ckpt_load<S>(ck, 2 * (int64_t)i + 1, A[1], D[1]);
+            }
             gates_only<H, 2>(sm.w1t, te, cj, g);
           } else {
             mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
@@ -1177,9 +1271,19 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[3], D[3];
           Gate<H> g[3];
           const float te[3] = {t0, t0 + dt * kOneThird, t0 + dt * kTwoThirds};
+          if (STAGED) {
+              const int n_ = T - 2 - i, st_ = n_ & 1;
+              mbar_wait(&wbars[st_], (st_ ? uses1 : uses0) & 1u);
+              if (st_) ++uses1; else ++uses0;
+              stage_read<S, 3>(wstage + st_ * kStageF2, A, D);
+              __syncwarp();  // every lane has its copy: the warp's stage can be refilled
+              if (lane == 0 && n_ + 2 <= T - 2) stage_issue(n_ + 2);
+            }
           if (CKPT) {
+            if (!STAGED) {
 #pragma unroll
-            for (int e = 0; e < 3; ++e) ckpt_load<S>(ck, 3 * (int64_t)i + e, A[e], D[e]);
+              for (int e = 0; e < 3; ++e) ckpt_load<S>(ck, 3 * (int64_t)i + e, A[e], D[e]);
+            }
             gates_only<H, 3>(sm.w1t, te, cj, g);
           } else {
             mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
@@ -1351,7 +1455,10 @@ int launch_fwd(const FwdArgs& a) {
 template <int H, int S, int METHOD, int MODE, bool CKPT>
 int launch_bwd(const BwdArgs& a) {
   auto kern = mlp_fixed_bwd_kernel<H, S, METHOD, MODE, CKPT>;
-  const size_t smem = (sizeof(BwdSmem<H, S>) + 15) / 16 * 16 +
+  constexpr int per_step = (METHOD == SLODE_METHOD_RK4) ? 3 : (METHOD == SLODE_METHOD_MIDPOINT ? 2 : 1);
+  const size_t stage_bytes =
+      (CKPT && S <= 5) ? ((size_t)(kBlock / 32) * 2 * per_step * 2 * S * 32 * sizeof(f2) + (kBlock / 32) * 2 * 8 + 15) / 16 * 16 : 0;
+  const size_t smem = (sizeof(BwdSmem<H, S>) + 15) / 16 * 16 + stage_bytes +
                       (a.lat.z ? 2 * sizeof(float) * lat_floats(a.lat.L, H, S) : 0);
   SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;
