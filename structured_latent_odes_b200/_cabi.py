@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libslode_b200.so")
+# SLODE_B200_LIB points at another build of the same library (kernel A/B measurements); there is still no fallback
+LIB_PATH = os.environ.get("SLODE_B200_LIB") or os.path.join(_HERE, "csrc", "libslode_b200.so")
 
 # slode_b200.h constants
 METHOD_EULER, METHOD_MIDPOINT, METHOD_RK4, METHOD_DOPRI5 = 0, 1, 2, 3

@@ -405,7 +405,7 @@ __device__ __forceinline__ void ckpt_prefetch(const f2* __restrict__ warp_base, 
 // gates for the prefix-sum bookkeeping but not the heads)
 template <int H, int NE, class CLoad>
 __device__ __forceinline__ void gates_only(const float* __restrict__ w1t_smem, const float (&t)[NE], CLoad cj,
-                                           Gate<H> (&gate)[NE]) {
+                                           Gate<H> (&gate)[NE], int w1t_stride = 1) {
   constexpr int NW = Gate<H>::NW;
   uint32_t neg[NE][2][NW];
 #pragma unroll
@@ -419,7 +419,7 @@ __device__ __forceinline__ void gates_only(const float* __restrict__ w1t_smem, c
 #pragma unroll
   for (int j = 0; j < H; ++j) {
     const f2 c = cj(j);
-    const f2 w1 = bc(w1t_smem[j]);
+    const f2 w1 = bc(w1t_smem[j * w1t_stride]);
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       float p0, p1;
@@ -485,10 +485,153 @@ __device__ __forceinline__ void stage_read(const f2* __restrict__ st, Vec<S> (&A
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Piecewise-linear evaluation of the heads.  The hidden layer sees only (t, z): along one trajectory the head
+// pre-activations are
+//     o_k(t) = b_k + sum_j W_kj relu(w1t_j t + c_j) = alpha_k t + beta_k,
+//     alpha_k = sum_{j active} W_kj w1t_j,   beta_k = b_k + sum_{j active} W_kj c_j,
+// with coefficients that change only when a relu gate flips -- at most once per unit over a monotone sweep of t.
+// The evaluator keeps (alpha, beta) of the thread's two trajectories in registers; one evaluation is the H gate
+// tests (one FFMA2 + two funnel shifts per unit), 2S FFMA2 and the 2S sigmoids instead of the dense
+// H x (2S + 1) FFMA2, and every flip costs one rank-one update read from shared memory (lanes flip different
+// units at different times: the update loop is divergent but short, <= H trips per trajectory and solve).
+// tb is a shared-memory copy of one slot of the packed weights (already scaled by -log2 e), cf the block's
+// c table [H][kBlock] of f2 viewed as floats.
+// ---------------------------------------------------------------------------------------------
+template <int H, int S>
+struct PlEval {
+  using P = Pack<H, S>;
+  static constexpr int K2 = 2 * S;
+  static constexpr int NW = Gate<H>::NW;
+  f2 al[K2], be[K2];
+  uint32_t cur[2][NW];
+
+  __device__ __forceinline__ void init(const float* __restrict__ tb, const float* __restrict__ cf, const Gate<H>& g) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < K2; ++k) {
+      al[k] = 0ull;
+      be[k] = bc(tb[k]);
+    }
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
+      const uint32_t g0 = g.w[0][w], g1 = g.w[1][w];
+#pragma unroll 1
+      for (int q = 0; q < nw; ++q) {
+        const int j = 32 * w + (nw - 1 - q);
+        const float* r = tb + P::KP + j * P::UNIT;
+        const f2 m = pk(((g0 >> q) & 1u) ? 1.0f : 0.0f, ((g1 >> q) & 1u) ? 1.0f : 0.0f);
+        const f2 u = mul2(bc(r[0]), m);
+        const f2 v = mul2(reinterpret_cast<const f2*>(cf)[j * kBlock + tid], m);
+#pragma unroll
+        for (int k = 0; k < K2; ++k) {
+          const f2 wk = bc(r[1 + k]);
+          al[k] = fma2(wk, u, al[k]);
+          be[k] = fma2(wk, v, be[k]);
+        }
+      }
+      cur[0][w] = g0;
+      cur[1][w] = g1;
+    }
+  }
+
+  // bring (alpha, beta) to the gate pattern g: one trip per flipped unit, both trajectories served per trip
+  __device__ __forceinline__ void update(const float* __restrict__ tb, const float* __restrict__ cf, const Gate<H>& g) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int nw = (w == NW - 1) ? (H - 32 * w) : 32;
+      const uint32_t g0 = g.w[0][w], g1 = g.w[1][w];
+      uint32_t d0 = g0 ^ cur[0][w], d1 = g1 ^ cur[1][w];
+      while (d0 | d1) {
+        const int q0 = d0 ? __ffs(d0) - 1 : 0, q1 = d1 ? __ffs(d1) - 1 : 0;
+        const float s0 = d0 ? (((g0 >> q0) & 1u) ? 1.0f : -1.0f) : 0.0f;
+        const float s1 = d1 ? (((g1 >> q1) & 1u) ? 1.0f : -1.0f) : 0.0f;
+        d0 &= d0 - 1;
+        d1 &= d1 - 1;
+        const int j0 = 32 * w + (nw - 1 - q0), j1 = 32 * w + (nw - 1 - q1);
+        const float* r0 = tb + P::KP + j0 * P::UNIT;
+        const float* r1 = tb + P::KP + j1 * P::UNIT;
+        float a0[P::UNIT], a1[P::UNIT];
+#pragma unroll
+        for (int k = 0; k < P::UNIT / 4; ++k) {
+          const float4 x0 = reinterpret_cast<const float4*>(r0)[k];
+          const float4 x1 = reinterpret_cast<const float4*>(r1)[k];
+          a0[4 * k] = x0.x; a0[4 * k + 1] = x0.y; a0[4 * k + 2] = x0.z; a0[4 * k + 3] = x0.w;
+          a1[4 * k] = x1.x; a1[4 * k + 1] = x1.y; a1[4 * k + 2] = x1.z; a1[4 * k + 3] = x1.w;
+        }
+        const float u0 = s0 * a0[0], u1 = s1 * a1[0];
+        const float v0 = s0 * cf[(j0 * kBlock + tid) * 2], v1 = s1 * cf[(j1 * kBlock + tid) * 2 + 1];
+#pragma unroll
+        for (int k = 0; k < K2; ++k) {
+          float lo, hi;
+          unpk(al[k], lo, hi);
+          al[k] = pk(fmaf(a0[1 + k], u0, lo), fmaf(a1[1 + k], u1, hi));
+          unpk(be[k], lo, hi);
+          be[k] = pk(fmaf(a0[1 + k], v0, lo), fmaf(a1[1 + k], v1, hi));
+        }
+      }
+      cur[0][w] = g0;
+      cur[1][w] = g1;
+    }
+  }
+
+  // A = sigmoid(growth heads), ND = -sigmoid(degradation heads) at time te (same conventions as mlp_eval)
+  __device__ __forceinline__ void eval(float te, Vec<S>& A, Vec<S>& ND) const {
+    const f2 tt = bc(te);
+    const f2 one = bc(1.0f), minus_one = bc(-1.0f);
+#pragma unroll
+    for (int o = 0; o < K2; ++o) {
+      float v0, v1;
+      unpk(fma2(al[o], tt, be[o]), v0, v1);
+      const f2 ex = pk(ex2_approx(v0), ex2_approx(v1));
+      unpk(o < S ? add2(ex, one) : sub2(minus_one, ex), v0, v1);
+      const f2 sg = pk(rcp_approx(v0), rcp_approx(v1));
+      if (o < S) A.v[o] = sg; else ND.v[o - S] = sg;
+    }
+  }
+};
+
+// NE evaluations through the piecewise-linear evaluator, visited in sweep order (REV: last index first) so that
+// the gate pattern moves monotonically; the first evaluation of a trajectory initialises the coefficients.
+template <int H, int S, int NE, bool REV, class CLoad>
+__device__ __forceinline__ void pl_evals(PlEval<H, S>& pl, bool& inited, const float* __restrict__ tb,
+                                         const float* __restrict__ cf, const float (&t)[NE], CLoad cj,
+                                         Vec<S> (&A)[NE], Vec<S> (&ND)[NE], Gate<H> (&gate)[NE]) {
+  using P = Pack<H, S>;
+  gates_only<H, NE>(tb + P::KP, t, cj, gate, P::UNIT);
+#pragma unroll
+  for (int n = 0; n < NE; ++n) {
+    const int e = REV ? NE - 1 - n : n;
+    if (!inited) {
+      pl.init(tb, cf, gate[e]);
+      inited = true;
+    } else {
+      pl.update(tb, cf, gate[e]);
+    }
+    pl.eval(t[e], A[e], ND[e]);
+  }
+}
+
+// copy slot 0 of the packed weights from constant to shared memory (dynamic unit indices need shared memory:
+// divergent constant-cache reads serialise)
+template <int H, int S>
+__device__ __forceinline__ void pl_stage_tables(float* __restrict__ tb) {
+  for (int i = threadIdx.x; i < Pack<H, S>::N; i += kBlock) tb[i] = SLODE_PACK_SYM[i];
+}
+
 // f = A - D*x = A + ND*x
 template <int S>
 __device__ __forceinline__ Vec<S> rhs(const Vec<S>& A, const Vec<S>& ND, const Vec<S>& x) { return vfma<S>(ND, x, A); }
 
+#ifndef SLODE_FWD_CSMEM
+#define SLODE_FWD_CSMEM 0
+#endif
+#ifndef SLODE_PL
+#define SLODE_PL 1  // fixed-grid kernels evaluate the heads piecewise-linearly (0: dense products from constant memory)
+#endif
 #ifndef SLODE_FWD_MINB
 #define SLODE_FWD_MINB 3
 #endif
@@ -685,14 +828,16 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   __shared__ __align__(16) OutStage<S> ostage;
   const bool rows_in_time = (st == S);  // (B,T,S)-contiguous storage
   // wide hidden layers: the per-trajectory c_j do not fit in registers next to the accumulators -> shared memory
-  constexpr bool C_IN_SMEM = H > 32;
+  constexpr bool PL = SLODE_PL != 0;  // piecewise-linear evaluation of the heads (PlEval)
+  constexpr bool C_IN_SMEM = PL || H > 32 || SLODE_FWD_CSMEM;
   f2 (*csm)[kBlock] = reinterpret_cast<f2 (*)[kBlock]>(fwd_dyn);
-  float* lat_base = fwd_dyn + (C_IN_SMEM ? 2 * H * kBlock : 0);
+  float* const tb = fwd_dyn + (C_IN_SMEM ? 2 * H * kBlock : 0);  // PL: shared copy of the packed weights
+  float* lat_base = tb + (PL ? Pack<H, S>::N : 0);
+  const float* const cf = fwd_dyn;
   LatSmem ls{};
-  if (lat.z) {
-    ls = lat_stage<H, S>(lat_base, lat);
-    __syncthreads();
-  }
+  if (PL) pl_stage_tables<H, S>(tb);
+  if (lat.z) ls = lat_stage<H, S>(lat_base, lat);
+  if (PL || lat.z) __syncthreads();
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const PairIdx pi = pair_index(tile, B);
@@ -731,11 +876,14 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     else vstore2<S>(out0, pi.ok0, out1, pi.ok1, x);
     float t0 = __ldg(tgrid);
     Vec<S> k1;
+    PlEval<H, S> pl;
+    bool pl_on = false;
     if (METHOD == SLODE_METHOD_RK4) {  // k1 of the first step; afterwards carried over from the step before
       Vec<S> A[1], D[1];
       Gate<H> ng[1];
       const float te[1] = {t0};
-      mlp_eval<H, S, 1, false, 1>(te, cj, A, D, ng);
+      if (PL) pl_evals<H, S, 1, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+      else mlp_eval<H, S, 1, false, 1>(te, cj, A, D, ng);
       if (save) ckpt_store<S>(ck, 0, A[0], D[0]);
       k1 = rhs<S>(A[0], D[0], x);
     }
@@ -748,7 +896,8 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Vec<S> A[1], D[1];
         Gate<H> ng[1];
         const float te[1] = {t0};
-        mlp_eval<H, S, 1, false, 0>(te, cj, A, D, ng);
+        if (PL) pl_evals<H, S, 1, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+        else mlp_eval<H, S, 1, false, 0>(te, cj, A, D, ng);
         if (save) ckpt_store<S>(ck, i, A[0], D[0]);
         x = vaxpy<S>(dt, rhs<S>(A[0], D[0], x), x);
       } else if (METHOD == SLODE_METHOD_MIDPOINT) {
@@ -756,7 +905,8 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Vec<S> A[2], D[2];
         Gate<H> ng[2];
         const float te[2] = {t0, t0 + half_dt};
-        mlp_eval<H, S, 2, false, 0>(te, cj, A, D, ng);
+        if (PL) pl_evals<H, S, 2, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+        else mlp_eval<H, S, 2, false, 0>(te, cj, A, D, ng);
         if (save) {
           ckpt_store<S>(ck, 2 * (int64_t)i, A[0], D[0]);
           ckpt_store<S>(ck, 2 * (int64_t)i + 1, A[1], D[1]);
@@ -767,7 +917,8 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Vec<S> A[3], D[3];
         Gate<H> ng[3];
         const float te[3] = {t0 + dt * kOneThird, t0 + dt * kTwoThirds, t1};
-        mlp_eval<H, S, 3, false, 0>(te, cj, A, D, ng);
+        if (PL) pl_evals<H, S, 3, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+        else mlp_eval<H, S, 3, false, 0>(te, cj, A, D, ng);
         if (save) {
 #pragma unroll
           for (int e = 0; e < 3; ++e) ckpt_store<S>(ck, 3 * (int64_t)i + 1 + e, A[e], D[e]);
@@ -1103,7 +1254,10 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   constexpr int kStageF2 = per_step * K2 * 32;                           // f2 per warp and interval
   constexpr int kWarps = kBlock / 32;
   constexpr size_t kStageBytes = STAGED ? (size_t)kWarps * 2 * kStageF2 * sizeof(f2) + kWarps * 2 * sizeof(uint64_t) : 0;
-  unsigned char* stage_raw = smem_raw + (sizeof(BwdSmem<H, S>) + 15) / 16 * 16;
+  constexpr bool PL = SLODE_PL != 0 && !CKPT;  // heads re-evaluated piecewise-linearly (PlEval)
+  float* const tb = reinterpret_cast<float*>(smem_raw + (sizeof(BwdSmem<H, S>) + 15) / 16 * 16);
+  const float* const cf = reinterpret_cast<const float*>(&sm.c[0][0]);
+  unsigned char* stage_raw = reinterpret_cast<unsigned char*>(tb + (PL ? Pack<H, S>::N : 0));
   const int warp = tid >> 5, lane = tid & 31;
   f2* const wstage = reinterpret_cast<f2*>(stage_raw) + (size_t)warp * 2 * kStageF2;   // this warp's two stages
   uint64_t* const wbars = reinterpret_cast<uint64_t*>(stage_raw + (size_t)kWarps * 2 * kStageF2 * sizeof(f2)) + warp * 2;
@@ -1135,6 +1289,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   }
   for (int i = tid; i < K2 * H; i += kBlock) (&sm.G[0][0])[i] = 0.0f;
   if (tid < K2) sm.gb[tid] = 0.0f;
+  if (PL) pl_stage_tables<H, S>(tb);
   __syncthreads();
 
   const int64_t ntiles = ((B + 1) / 2 + kBlock - 1) / kBlock;
@@ -1176,6 +1331,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       if (T >= 3) stage_issue(1);
     }
     Sweep<H, S> sw;
+    PlEval<H, S> pl;
+    bool pl_on = false;
     float t1 = __ldg(tgrid + T - 1);
     bool started = false;
     Vec<S> Ac, Dc;  // rk4: the evaluation at t1, carried over from the interval processed before
@@ -1187,7 +1344,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         ckpt_load<S>(ck, 3 * (int64_t)(T - 1), A[0], D[0]);
         gates_only<H, 1>(sm.w1t, te, cj, g);
       } else {
-        mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
+        if (PL) pl_evals<H, S, 1, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
+        else mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
       }
       Ac = A[0];
       Dc = D[0];
@@ -1227,6 +1385,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           if (CKPT) {
             if (!STAGED) ckpt_load<S>(ck, i, A[0], D[0]);
             gates_only<H, 1>(sm.w1t, te, cj, g);
+          } else if (PL) {
+            pl_evals<H, S, 1, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
           } else {
             mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
           }
@@ -1253,6 +1413,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
               ckpt_load<S>(ck, 2 * (int64_t)i + 1, A[1], D[1]);
             }
             gates_only<H, 2>(sm.w1t, te, cj, g);
+          } else if (PL) {
+            pl_evals<H, S, 2, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
           } else {
             mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
           }
@@ -1285,6 +1447,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
               for (int e = 0; e < 3; ++e) ckpt_load<S>(ck, 3 * (int64_t)i + e, A[e], D[e]);
             }
             gates_only<H, 3>(sm.w1t, te, cj, g);
+          } else if (PL) {
+            pl_evals<H, S, 3, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
           } else {
             mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
           }
@@ -1335,7 +1499,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[1], D[1];
           Gate<H> g[1];
           const float te[1] = {t1};
-          mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
+          if (PL) pl_evals<H, S, 1, false>(pl, pl_on, tb, cf, te, cj, A, D, g);
+          else mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
           const Vec<S> v = vscale<S>(lam, ds);
           if (!started) { sw.init(g[0]); started = true; } else sw.events(rec, g[0]);
           sw.add(t1, v, y, A[0], D[0]);
@@ -1345,7 +1510,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[2], D[2];
           Gate<H> g[2];
           const float te[2] = {t1, t1 - half};
-          mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);  // the stage at t1 has weight 0: its gates are not used
+          if (PL) pl_evals<H, S, 2, false>(pl, pl_on, tb, cf, te, cj, A, D, g);  // the stage at t1 has weight 0: its gates are not used
+          else mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
           const Vec<S> ym = vaxpy<S>(-half, rhs<S>(A[0], D[0], y), y);  // y + half*(D1*y - A1)
           const Vec<S> am = vaxpy<S>(half, vmul<S>(lam, D[0]), lam);    // a + half*(-a*D1), D holds -sigmoid
           const Vec<S> v = vscale<S>(am, ds);
@@ -1357,7 +1523,8 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[3], D[3];
           Gate<H> g[3];
           const float te[3] = {t1 - ds * kOneThird, t1 - ds * kTwoThirds, t0};
-          mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
+          if (PL) pl_evals<H, S, 3, false>(pl, pl_on, tb, cf, te, cj, A, D, g);
+          else mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
           // (A, D with D = -sigmoid) => f = A + D*y; the augmented step uses Ky = -f, Ka = -a*sigmoid = a*D
           // stage 1 at t1 (carried evaluation)
           const Vec<S> f1 = rhs<S>(Ac, Dc, y);
@@ -1437,8 +1604,9 @@ template <int H, int S, int METHOD>
 int launch_fwd(const FwdArgs& a) {
   auto kern = mlp_fixed_fwd_kernel<H, S, METHOD>;
   const size_t smem = (a.lat.z ? sizeof(float) * lat_floats(a.lat.L, H, S) : 0) +
-                      (H > 32 ? sizeof(f2) * H * kBlock : 0);
-  if (smem > 48 * 1024)
+                      ((SLODE_PL || H > 32 || SLODE_FWD_CSMEM) ? sizeof(f2) * H * kBlock : 0) +
+                      (SLODE_PL ? sizeof(float) * Pack<H, S>::N : 0);
+  if (smem > 16 * 1024)  // static (output stage) + dynamic may pass the 48 KB default
     SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;
   SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, smem));
@@ -1459,6 +1627,7 @@ int launch_bwd(const BwdArgs& a) {
   const size_t stage_bytes =
       (CKPT && S <= 5) ? ((size_t)(kBlock / 32) * 2 * per_step * 2 * S * 32 * sizeof(f2) + (kBlock / 32) * 2 * 8 + 15) / 16 * 16 : 0;
   const size_t smem = (sizeof(BwdSmem<H, S>) + 15) / 16 * 16 + stage_bytes +
+                      ((SLODE_PL && !CKPT) ? sizeof(float) * Pack<H, S>::N : 0) +
                       (a.lat.z ? 2 * sizeof(float) * lat_floats(a.lat.L, H, S) : 0);
   SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;

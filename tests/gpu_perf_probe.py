@@ -3,6 +3,9 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import structured_latent_odes_b200 as slode
+from structured_latent_odes_b200 import torchdiffeq_api as _api
+if os.environ.get("SLODE_NO_CKPT"):
+    _api.EVAL_CHECKPOINTS = False
 
 def run(B, T, L, H, S, method, adjoint, layout="tbs", reps=5):
     dev = "cuda"
