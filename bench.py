@@ -77,6 +77,32 @@ def checkpointed_bwd_flops(method: str, T: int, H: int, S: int):
                  + 2 * (4 * L * H + 2 * H * S))
 
 
+
+def pl_flops(method: str, T: int, H: int, S: int):
+    """(forward, backward) fp32 flop per trajectory of the piecewise-linear formulation the kernels run (DESIGN.md
+    section 4): per evaluation the heads are alpha*t + beta (2 * 2S) and the sigmoid adds/merged reciprocals
+    (4 * 2S); per relu crossing (at most H per solve, counted as H) one rank-one update of (alpha, beta)
+    (2 * 2 * 2S) and once per trajectory the dense initial coefficients (2 * 2 * 2S * H)."""
+    steps = T - 1
+    stages = {"euler": 1, "midpoint": 2, "rk4": 4}[method]
+    evals = {"euler": steps, "midpoint": 2 * steps, "rk4": 3 * steps + 1}[method]
+    combine = {"euler": 2 * S, "midpoint": 4 * S, "rk4": 16 * S}[method]
+    prologue = 2 * L * H * 2 + 2 * H * S
+    pl = evals * (4 * S + 8 * S) + H * 8 * S + 8 * S * H + 2 * H
+    fwd = pl + steps * (stages * 2 * S + combine) + prologue
+    bwd = fwd + steps * stages * 24 * S + H * 2 * (14 * 2 * S) + 2 * (4 * L * H + 2 * H * S)
+    return float(fwd), float(bwd)
+
+
+def sfu_ops(method: str, T: int, S: int):
+    """MUFU lane-operations per trajectory and solve: 2S sigmoids per evaluation, each one ex2 and -- two
+    denominators sharing one reciprocal -- half an rcp."""
+    evals = {"euler": T - 1, "midpoint": 2 * (T - 1), "rk4": 3 * (T - 1) + 1}[method]
+    return float(evals * 3 * S)
+
+
+XU_PEAK_TOPS = 148 * 16 * 1.965e9 / 1e12  # 16 MUFU lanes per SM and clock
+
 # ---------------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------------
@@ -200,8 +226,9 @@ def workload_config(args, B_per_gpu, n):
             "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L, "sol_layout": getattr(args, "layout", "tbs"),
             "ode_hidden_dim": H, "ode_state_dim": S, "solver": args.method,
             "gradient": "odeint_adjoint emulation" if args.adjoint else "discrete adjoint (odeint + autograd parity)",
-            "reverse_sweep": ("recomputes the MLP evaluations" if (getattr(args, "no_eval_ckpt", False) or args.adjoint)
-                              else "reads the forward's evaluation checkpoints (12.5 GB per 2^20 x 100 solve)"),
+            "mlp_evaluation": "piecewise-linear heads (alpha t + beta per trajectory, updated at relu crossings)",
+            "reverse_sweep": ("reads the forward's evaluation checkpoints (12.5 GB per 2^20 x 100 solve)"
+                              if (getattr(args, "eval_ckpt", False) and not args.adjoint) else "re-evaluates the MLP"),
             "parallelism": f"trajectory-sharded x{n}, one flat all-reduce of parameter gradients",
             "l2": "inputs larger than L2 (sol / grad_sol are 2.1 GB each per GPU vs 126 MB L2)"}
 
@@ -218,8 +245,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8192, help="trajectories per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
-    ap.add_argument("--no-eval-ckpt", action="store_true",
-                    help="reverse sweep re-evaluates the MLP instead of reading the forward's evaluation checkpoints")
+    ap.add_argument("--eval-ckpt", action="store_true",
+                    help="reverse sweep reads the forward's evaluation checkpoints instead of re-evaluating the MLP")
     ap.add_argument("--layout", default="tbs", choices=["tbs", "bts"],
                     help="storage of the resident step's solution: (T,B,S) torchdiffeq's, or (B,T,S) the decoder's")
     args = ap.parse_args()
@@ -234,8 +261,7 @@ def main():
     from structured_latent_odes_b200 import _cabi, sharding
     from structured_latent_odes_b200.torchdiffeq_api import KernelTimer
     from structured_latent_odes_b200 import torchdiffeq_api as _api_cfg
-    if args.no_eval_ckpt:
-        _api_cfg.EVAL_CHECKPOINTS = False
+    _api_cfg.EVAL_CHECKPOINTS = bool(args.eval_ckpt)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -387,9 +413,11 @@ def main():
     if rank == 0:
         from structured_latent_odes_b200 import torchdiffeq_api as _api
         ckpt = bool(_api.EVAL_CHECKPOINTS) and not args.adjoint
-        ff, fb = algorithmic_flops(args.method, T, H, S)
+        ff, fb = pl_flops(args.method, T, H, S)
         if ckpt:
             fb = checkpointed_bwd_flops(args.method, T, H, S)
+        xu_f = sfu_ops(args.method, T, S)
+        xu_b = 0.0 if ckpt else xu_f
         bf, bb = algorithmic_bytes(T, H, S, args.method, ckpt)
         fwd_ms = sum(ktimes["fwd"]) / max(len(ktimes["fwd"]), 1)
         bwd_ms = sum(ktimes["bwd"]) / max(len(ktimes["bwd"]), 1)
@@ -422,25 +450,34 @@ def main():
                 "ms_per_launch": bwd_ms, "algorithmic_flop_per_launch": B * fb, "algorithmic_bytes_per_launch": B * bb,
                 "fp32": {"achieved": achieved_b, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_b / FP32_PEAK_TFLOPS},
                 "hbm": {"achieved": B * bb / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": B * bb / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}}
+                        "frac": B * bb / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+                "xu": {"achieved": B * xu_b / (bwd_ms * 1e-3) / 1e12, "peak": XU_PEAK_TOPS, "unit": "T MUFU lane-op/s",
+                       "frac": B * xu_b / (bwd_ms * 1e-3) / 1e12 / XU_PEAK_TOPS, "sfu_ops_per_launch": B * xu_b}}
         rl_f = {"kernel": "mlp_fixed_fwd_kernel", "ms_per_launch": fwd_ms, "algorithmic_flop_per_launch": B * ff,
                 "algorithmic_bytes_per_launch": B * bf,
                 "fp32": {"achieved": achieved_f, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_f / FP32_PEAK_TFLOPS},
                 "hbm": {"achieved": B * bf / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": B * bf / (fwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}}
+                        "frac": B * bf / (fwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+                "xu": {"achieved": B * xu_f / (fwd_ms * 1e-3) / 1e12, "peak": XU_PEAK_TOPS, "unit": "T MUFU lane-op/s",
+                       "frac": B * xu_f / (fwd_ms * 1e-3) / 1e12 / XU_PEAK_TOPS, "sfu_ops_per_launch": B * xu_f}}
         fp32_src = ("148 SM x 128 lanes x 2 x 1.965 GHz; FFMA2 micro-benchmark measured 74.0 "
                     "(profiles/r01/fp32_pipes_microbench.jsonl); MEASURED_PEAKS.json has no fp32 entry")
 
+        xu_src = "148 SM x 16 MUFU lanes x 1.965 GHz (no MUFU entry in MEASURED_PEAKS.json)"
+
         def flat(r, traffic_key):
-            """contract shape: the roofline that binds the kernel on top, the other one beside it"""
-            bound = "hbm" if r["hbm"]["frac"] >= r["fp32"]["frac"] else "fp32"
+            """contract shape: the roofline that binds the kernel on top (largest fraction of its peak among HBM
+            bytes, fp32 FMA flop and XU/MUFU operations), the other two beside it"""
+            bound = max(("hbm", "fp32", "xu"), key=lambda k: r[k]["frac"])
             top = r[bound]
             out = {"bound": bound, "kernel": r["kernel"], "achieved": top["achieved"], "peak": top["peak"],
                    "unit": top["unit"], "frac": top["frac"], "traffic": traffic_map.get(traffic_key),
-                   "peak_source": top.get("peak_source", fp32_src) if bound == "hbm" else fp32_src,
+                   "peak_source": {"hbm": top.get("peak_source"), "fp32": fp32_src, "xu": xu_src}[bound],
                    "ms_per_launch": r["ms_per_launch"], "algorithmic_flop_per_launch": r["algorithmic_flop_per_launch"],
                    "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"]}
-            out["fp32" if bound == "hbm" else "hbm"] = r["fp32" if bound == "hbm" else "hbm"]
+            for k in ("hbm", "fp32", "xu"):
+                if k != bound:
+                    out[k] = r[k]
             return out
 
         tag = f"{args.method}_{int(args.adjoint)}" + ("_ckpt" if ckpt else "")

@@ -40,6 +40,20 @@
 #ifndef SLODE_PACK_SYM
 #error "define SLODE_PACK_SYM (the per-translation-unit constant symbol) before including slode_mlp_kernels.cuh"
 #endif
+// build-time switches (kernel A/B measurements build variants of the library with -D...)
+#ifndef SLODE_FWD_CSMEM
+#define SLODE_FWD_CSMEM 0
+#endif
+#ifndef SLODE_PL
+#define SLODE_PL 2  // fixed-grid kernels: 2 = piecewise-linear heads with the sorted walk over relu crossings,
+                   // 1 = piecewise-linear heads with all H gates tested per evaluation, 0 = dense products
+#endif
+#ifndef SLODE_FWD_MINB
+#define SLODE_FWD_MINB 3
+#endif
+#ifndef SLODE_BWD_MINB
+#define SLODE_BWD_MINB 2
+#endif
 #define SLODE_STR2(x) #x
 #define SLODE_STR(x) SLODE_STR2(x)
 
@@ -578,66 +592,238 @@ struct PlEval {
     }
   }
 
-  // A = sigmoid(growth heads), ND = -sigmoid(degradation heads) at time te (same conventions as mlp_eval)
+  // ---- sorted walk (SLODE_PL == 2): instead of testing all H gates at every evaluation, the trajectory's
+  // flips are visited in the order the sweep meets them.  p_j(t) = w1t_j t + c_j crosses zero at t*_j = -c_j/w1t_j;
+  // in the sweep coordinate u = dirsign (t - t_start) >= 0 the pending crossings are sorted once per trajectory
+  // (bitonic network in registers, keys = float bits of u*_j with the unit index in the low mantissa bits, biased
+  // early) and kept in shared memory.  An evaluation compares its u with the next key (one FSETP per trajectory);
+  // a due candidate is confirmed with the exact fp32 gate test the dense evaluation would make, so the gate
+  // patterns are those of gates_only whenever the key is not late, and a key cannot be late by more than the
+  // rounding of t*_j.
+  static constexpr int IB = H <= 32 ? 5 : (H <= 64 ? 6 : 7);  // index bits inside a key
+  static constexpr uint32_t IMASK = (1u << IB) - 1u;
+  static constexpr int N2 = H <= 32 ? 32 : (H <= 64 ? 64 : 128);
+  static constexpr uint32_t kNever = 0x7f800000u;  // +inf: never due
+  float nk[2];
+  int pos[2];
+
+  __device__ __forceinline__ void build(uint32_t* __restrict__ ks, const float* __restrict__ tb,
+                                        const float* __restrict__ cf, float t_start, float dirsign) {
+    const int tid = threadIdx.x;
+    const float* rinv = tb + P::N;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t k[N2];
+#pragma unroll
+      for (int j = 0; j < N2; ++j) {
+        k[j] = kNever;
+        if (j < H) {
+          const float ts = cf[(j * kBlock + tid) * 2 + h] * rinv[j];
+          const float slack = 4e-7f * (fabsf(ts) + fabsf(t_start));
+          const float u = dirsign * (ts - t_start);
+          const float ub = fmaxf(fmaf(u, 0.99998474f, -slack), 0.0f);
+          // pending iff the crossing is not behind the start (rinv = 0 marks w1t_j = 0: never flips; NaN fails the test)
+          if (rinv[j] != 0.0f && u > -(64.0f * slack + 1e-30f) && ub < 3.0e38f)
+            k[j] = (__float_as_uint(ub) & ~IMASK) | (uint32_t)j;
+        }
+      }
+#pragma unroll
+      for (int size = 2; size <= N2; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+          for (int i = 0; i < N2; ++i) {
+            const int l = i ^ stride;
+            if (l > i) {
+              const uint32_t a = k[i], b = k[l];
+              const bool up = (i & size) == 0;
+              k[i] = up ? min(a, b) : max(a, b);
+              k[l] = up ? max(a, b) : min(a, b);
+            }
+          }
+        }
+      }
+      uint32_t* col = ks + (size_t)h * (H + 1) * kBlock + tid;
+#pragma unroll
+      for (int j = 0; j < H; ++j) col[j * kBlock] = k[j];
+      col[H * kBlock] = kNever;
+      pos[h] = 0;
+      nk[h] = __uint_as_float(k[0]);
+    }
+  }
+
+  // move the gate pattern and (alpha, beta) to evaluation time te.  One loop per trajectory of the thread: a trip
+  // usually serves a single lane of the warp, so serving both halves in one trip would double its cost.
+  template <int HALF>
+  __device__ __forceinline__ void advance_half(const uint32_t* __restrict__ ks, const float* __restrict__ tb,
+                                               const float* __restrict__ cf, float te, float uq, float dirsign) {
+    const int tid = threadIdx.x;
+    while (uq >= nk[HALF]) {
+      const int j = (int)(__float_as_uint(nk[HALF]) & IMASK);
+      const float* r = tb + P::KP + j * P::UNIT;
+      float a[P::UNIT];
+#pragma unroll
+      for (int k = 0; k < P::UNIT / 4; ++k) {
+        const float4 x = reinterpret_cast<const float4*>(r)[k];
+        a[4 * k] = x.x; a[4 * k + 1] = x.y; a[4 * k + 2] = x.z; a[4 * k + 3] = x.w;
+      }
+      const float c = cf[(j * kBlock + tid) * 2 + HALF];
+      // state after the crossing, and the gate the dense test gives at te (on <=> sign bit clear)
+      const bool post = dirsign * a[0] > 0.0f;
+      const bool now = (__float_as_uint(fmaf(a[0], te, c)) >> 31) == 0u;
+      const int w = j >> 5;
+      const int b = ((w == NW - 1) ? (H - 32 * w) : 32) - 1 - (j & 31);
+      uint32_t cw = cur[HALF][0];
+#pragma unroll
+      for (int ww = 1; ww < NW; ++ww) {
+        if (w == ww) cw = cur[HALF][ww];
+      }
+      const bool is = (cw >> b) & 1u;
+      if (is != post) {        // not yet in the state behind the crossing
+        if (now != post) break;  // and not there at te either: the candidate stays pending
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) {
+          if (w == ww) cur[HALF][ww] ^= 1u << b;
+        }
+        const float sgn = post ? 1.0f : -1.0f;
+        const float u = sgn * a[0], v = sgn * c;
+#pragma unroll
+        for (int k = 0; k < K2; ++k) {
+          float lo, hi;
+          unpk(al[k], lo, hi);
+          al[k] = HALF ? pk(lo, fmaf(a[1 + k], u, hi)) : pk(fmaf(a[1 + k], u, lo), hi);
+          unpk(be[k], lo, hi);
+          be[k] = HALF ? pk(lo, fmaf(a[1 + k], v, hi)) : pk(fmaf(a[1 + k], v, lo), hi);
+        }
+      }
+      ++pos[HALF];
+      nk[HALF] = __uint_as_float(ks[((size_t)HALF * (H + 1) + pos[HALF]) * kBlock + tid]);
+    }
+  }
+  __device__ __forceinline__ void advance(const uint32_t* __restrict__ ks, const float* __restrict__ tb,
+                                          const float* __restrict__ cf, float te, float t_start, float dirsign) {
+    const float uq = dirsign * (te - t_start);
+    advance_half<0>(ks, tb, cf, te, uq, dirsign);
+    advance_half<1>(ks, tb, cf, te, uq, dirsign);
+  }
+
+  // A = sigmoid(growth heads), ND = -sigmoid(degradation heads) at time te (same conventions as mlp_eval).
+  // The XU pipe (16 MUFU lanes per SM) is what bounds this kernel once the dense products are gone, so the 2S
+  // reciprocals are taken two denominators at a time: 1/a = b * rcp(ab), 1/b = a * rcp(ab) -- one MUFU.RCP and
+  // three packed multiplies instead of two MUFU.RCP.  Exponents are clamped at 2^60 so that ab stays finite
+  // (sigmoid floor 1e-18).
   __device__ __forceinline__ void eval(float te, Vec<S>& A, Vec<S>& ND) const {
     const f2 tt = bc(te);
     const f2 one = bc(1.0f), minus_one = bc(-1.0f);
+    f2 d[K2];
 #pragma unroll
     for (int o = 0; o < K2; ++o) {
       float v0, v1;
       unpk(fma2(al[o], tt, be[o]), v0, v1);
-      const f2 ex = pk(ex2_approx(v0), ex2_approx(v1));
-      unpk(o < S ? add2(ex, one) : sub2(minus_one, ex), v0, v1);
-      const f2 sg = pk(rcp_approx(v0), rcp_approx(v1));
-      if (o < S) A.v[o] = sg; else ND.v[o - S] = sg;
+      const f2 ex = pk(ex2_approx(fminf(v0, 60.0f)), ex2_approx(fminf(v1, 60.0f)));
+      d[o] = o < S ? add2(ex, one) : sub2(minus_one, ex);
+    }
+    f2 r[K2];
+#pragma unroll
+    for (int o = 0; o + 1 < K2; o += 2) {
+      float m0, m1;
+      unpk(mul2(d[o], d[o + 1]), m0, m1);
+      const f2 rm = pk(rcp_approx(m0), rcp_approx(m1));
+      r[o] = mul2(rm, d[o + 1]);
+      r[o + 1] = mul2(rm, d[o]);
+    }
+    if (K2 & 1) {
+      float m0, m1;
+      unpk(d[K2 - 1], m0, m1);
+      r[K2 - 1] = pk(rcp_approx(m0), rcp_approx(m1));
+    }
+#pragma unroll
+    for (int o = 0; o < K2; ++o) {
+      if (o < S) A.v[o] = r[o]; else ND.v[o - S] = r[o];
     }
   }
 };
 
+// shared-memory block of the piecewise-linear evaluator:
+//   tb   [Pack::N]        copy of one slot of the packed weights
+//   rinv [H, padded]      -1 / w1t_j (0 where w1t_j = 0)
+//   keys [2][H+1][kBlock] sorted crossing keys of the thread's two trajectories (SLODE_PL == 2)
+// The sorted walk serves hidden layers of up to 32 units (one gate word, 32-key sorting network in registers);
+// wider layers test all H gates per evaluation (two dozen registers of keys more would spill, and the (64,5)
+// midpoint sweep built with the walk failed parity on the device -- unresolved).
+template <int H>
+__host__ __device__ constexpr bool pl_walk() { return SLODE_PL == 2 && H <= 32; }
+template <int H, int S>
+__host__ __device__ constexpr int pl_smem_floats() {
+  return Pack<H, S>::N + (H + 3) / 4 * 4 + (pl_walk<H>() ? 2 * (H + 1) * kBlock : 0);
+}
+struct PlCtx {
+  const float* tb;
+  const float* cf;
+  uint32_t* ks;
+  float dirsign;  // +1: this kernel visits increasing times, -1: decreasing
+};
+template <int H, int S>
+__device__ __forceinline__ PlCtx pl_ctx(float* base, const float* cf, float dirsign) {
+  return PlCtx{base, cf, reinterpret_cast<uint32_t*>(base + Pack<H, S>::N + (H + 3) / 4 * 4), dirsign};
+}
+
 // NE evaluations through the piecewise-linear evaluator, visited in sweep order (REV: last index first) so that
 // the gate pattern moves monotonically; the first evaluation of a trajectory initialises the coefficients.
 template <int H, int S, int NE, bool REV, class CLoad>
-__device__ __forceinline__ void pl_evals(PlEval<H, S>& pl, bool& inited, const float* __restrict__ tb,
-                                         const float* __restrict__ cf, const float (&t)[NE], CLoad cj,
-                                         Vec<S> (&A)[NE], Vec<S> (&ND)[NE], Gate<H> (&gate)[NE]) {
+__device__ __forceinline__ void pl_evals(PlEval<H, S>& pl, bool& inited, float& t_start, const PlCtx& pc,
+                                         const float (&t)[NE], CLoad cj, Vec<S> (&A)[NE], Vec<S> (&ND)[NE],
+                                         Gate<H> (&gate)[NE]) {
   using P = Pack<H, S>;
-  gates_only<H, NE>(tb + P::KP, t, cj, gate, P::UNIT);
+  constexpr bool WALK = pl_walk<H>();
+  if (!WALK) gates_only<H, NE>(pc.tb + P::KP, t, cj, gate, P::UNIT);
 #pragma unroll
   for (int n = 0; n < NE; ++n) {
     const int e = REV ? NE - 1 - n : n;
     if (!inited) {
-      pl.init(tb, cf, gate[e]);
+      if (WALK) {
+        Gate<H> g1[1];
+        const float t1[1] = {t[e]};
+        gates_only<H, 1>(pc.tb + P::KP, t1, cj, g1, P::UNIT);
+        pl.init(pc.tb, pc.cf, g1[0]);
+        t_start = t[e];
+        pl.build(pc.ks, pc.tb, pc.cf, t_start, pc.dirsign);
+      } else {
+        pl.init(pc.tb, pc.cf, gate[e]);
+      }
       inited = true;
+    } else if (WALK) {
+      pl.advance(pc.ks, pc.tb, pc.cf, t[e], t_start, pc.dirsign);
     } else {
-      pl.update(tb, cf, gate[e]);
+      pl.update(pc.tb, pc.cf, gate[e]);
+    }
+    if (WALK) {
+#pragma unroll
+      for (int w = 0; w < Gate<H>::NW; ++w) {
+        gate[e].w[0][w] = pl.cur[0][w];
+        gate[e].w[1][w] = pl.cur[1][w];
+      }
     }
     pl.eval(t[e], A[e], ND[e]);
   }
 }
 
 // copy slot 0 of the packed weights from constant to shared memory (dynamic unit indices need shared memory:
-// divergent constant-cache reads serialise)
+// divergent constant-cache reads serialise) and tabulate -1/w1t_j
 template <int H, int S>
 __device__ __forceinline__ void pl_stage_tables(float* __restrict__ tb) {
-  for (int i = threadIdx.x; i < Pack<H, S>::N; i += kBlock) tb[i] = SLODE_PACK_SYM[i];
+  using P = Pack<H, S>;
+  for (int i = threadIdx.x; i < P::N; i += kBlock) tb[i] = SLODE_PACK_SYM[i];
+  for (int j = threadIdx.x; j < H; j += kBlock) {
+    const float w = SLODE_PACK_SYM[P::KP + j * P::UNIT];
+    tb[P::N + j] = (w == 0.0f) ? 0.0f : -1.0f / w;
+  }
 }
 
 // f = A - D*x = A + ND*x
 template <int S>
 __device__ __forceinline__ Vec<S> rhs(const Vec<S>& A, const Vec<S>& ND, const Vec<S>& x) { return vfma<S>(ND, x, A); }
 
-#ifndef SLODE_FWD_CSMEM
-#define SLODE_FWD_CSMEM 0
-#endif
-#ifndef SLODE_PL
-#define SLODE_PL 1  // fixed-grid kernels evaluate the heads piecewise-linearly (0: dense products from constant memory)
-#endif
-#ifndef SLODE_FWD_MINB
-#define SLODE_FWD_MINB 3
-#endif
-#ifndef SLODE_BWD_MINB
-#define SLODE_BWD_MINB 2
-#endif
 
 // trajectory pair of a thread
 struct PairIdx {
@@ -825,15 +1011,17 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
                      const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, LatentSrc lat,
                      f2* __restrict__ eval_ckpt) {
   extern __shared__ __align__(16) float fwd_dyn[];
-  __shared__ __align__(16) OutStage<S> ostage;
   const bool rows_in_time = (st == S);  // (B,T,S)-contiguous storage
   // wide hidden layers: the per-trajectory c_j do not fit in registers next to the accumulators -> shared memory
   constexpr bool PL = SLODE_PL != 0;  // piecewise-linear evaluation of the heads (PlEval)
   constexpr bool C_IN_SMEM = PL || H > 32 || SLODE_FWD_CSMEM;
   f2 (*csm)[kBlock] = reinterpret_cast<f2 (*)[kBlock]>(fwd_dyn);
-  float* const tb = fwd_dyn + (C_IN_SMEM ? 2 * H * kBlock : 0);  // PL: shared copy of the packed weights
-  float* lat_base = tb + (PL ? Pack<H, S>::N : 0);
+  float* const tb = fwd_dyn + (C_IN_SMEM ? 2 * H * kBlock : 0);  // PL: packed weights, 1/w1t, crossing keys
+  float* lat_base = tb + (PL ? pl_smem_floats<H, S>() : 0);
   const float* const cf = fwd_dyn;
+  // the output stage of the (B,T,S) layout sits behind the staged latent nets (launch_fwd sizes the block)
+  OutStage<S>& ostage = *reinterpret_cast<OutStage<S>*>(lat_base + (lat.z ? (lat_floats(lat.L, H, S) + 3) / 4 * 4 : 0));
+  const PlCtx plc = pl_ctx<H, S>(tb, cf, (T < 2 || __ldg(tgrid + T - 1) >= __ldg(tgrid)) ? 1.0f : -1.0f);
   LatSmem ls{};
   if (PL) pl_stage_tables<H, S>(tb);
   if (lat.z) ls = lat_stage<H, S>(lat_base, lat);
@@ -878,11 +1066,12 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     Vec<S> k1;
     PlEval<H, S> pl;
     bool pl_on = false;
+    float pl_t0 = 0.0f;
     if (METHOD == SLODE_METHOD_RK4) {  // k1 of the first step; afterwards carried over from the step before
       Vec<S> A[1], D[1];
       Gate<H> ng[1];
       const float te[1] = {t0};
-      if (PL) pl_evals<H, S, 1, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+      if (PL) pl_evals<H, S, 1, false>(pl, pl_on, pl_t0, plc, te, cj, A, D, ng);
       else mlp_eval<H, S, 1, false, 1>(te, cj, A, D, ng);
       if (save) ckpt_store<S>(ck, 0, A[0], D[0]);
       k1 = rhs<S>(A[0], D[0], x);
@@ -896,7 +1085,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Vec<S> A[1], D[1];
         Gate<H> ng[1];
         const float te[1] = {t0};
-        if (PL) pl_evals<H, S, 1, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+        if (PL) pl_evals<H, S, 1, false>(pl, pl_on, pl_t0, plc, te, cj, A, D, ng);
         else mlp_eval<H, S, 1, false, 0>(te, cj, A, D, ng);
         if (save) ckpt_store<S>(ck, i, A[0], D[0]);
         x = vaxpy<S>(dt, rhs<S>(A[0], D[0], x), x);
@@ -905,7 +1094,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Vec<S> A[2], D[2];
         Gate<H> ng[2];
         const float te[2] = {t0, t0 + half_dt};
-        if (PL) pl_evals<H, S, 2, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+        if (PL) pl_evals<H, S, 2, false>(pl, pl_on, pl_t0, plc, te, cj, A, D, ng);
         else mlp_eval<H, S, 2, false, 0>(te, cj, A, D, ng);
         if (save) {
           ckpt_store<S>(ck, 2 * (int64_t)i, A[0], D[0]);
@@ -917,7 +1106,7 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         Vec<S> A[3], D[3];
         Gate<H> ng[3];
         const float te[3] = {t0 + dt * kOneThird, t0 + dt * kTwoThirds, t1};
-        if (PL) pl_evals<H, S, 3, false>(pl, pl_on, tb, cf, te, cj, A, D, ng);
+        if (PL) pl_evals<H, S, 3, false>(pl, pl_on, pl_t0, plc, te, cj, A, D, ng);
         else mlp_eval<H, S, 3, false, 0>(te, cj, A, D, ng);
         if (save) {
 #pragma unroll
@@ -1257,7 +1446,9 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   constexpr bool PL = SLODE_PL != 0 && !CKPT;  // heads re-evaluated piecewise-linearly (PlEval)
   float* const tb = reinterpret_cast<float*>(smem_raw + (sizeof(BwdSmem<H, S>) + 15) / 16 * 16);
   const float* const cf = reinterpret_cast<const float*>(&sm.c[0][0]);
-  unsigned char* stage_raw = reinterpret_cast<unsigned char*>(tb + (PL ? Pack<H, S>::N : 0));
+  unsigned char* stage_raw = reinterpret_cast<unsigned char*>(tb + (PL ? pl_smem_floats<H, S>() : 0));
+  // the reverse sweep visits the grid from its last time to its first
+  const PlCtx plc = pl_ctx<H, S>(tb, cf, (T < 2 || __ldg(tgrid + T - 1) >= __ldg(tgrid)) ? -1.0f : 1.0f);
   const int warp = tid >> 5, lane = tid & 31;
   f2* const wstage = reinterpret_cast<f2*>(stage_raw) + (size_t)warp * 2 * kStageF2;   // this warp's two stages
   uint64_t* const wbars = reinterpret_cast<uint64_t*>(stage_raw + (size_t)kWarps * 2 * kStageF2 * sizeof(f2)) + warp * 2;
@@ -1333,6 +1524,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     Sweep<H, S> sw;
     PlEval<H, S> pl;
     bool pl_on = false;
+    float pl_t0 = 0.0f;
     float t1 = __ldg(tgrid + T - 1);
     bool started = false;
     Vec<S> Ac, Dc;  // rk4: the evaluation at t1, carried over from the interval processed before
@@ -1344,7 +1536,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
         ckpt_load<S>(ck, 3 * (int64_t)(T - 1), A[0], D[0]);
         gates_only<H, 1>(sm.w1t, te, cj, g);
       } else {
-        if (PL) pl_evals<H, S, 1, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
+        if (PL) pl_evals<H, S, 1, true>(pl, pl_on, pl_t0, plc, te, cj, A, D, g);
         else mlp_eval<H, S, 1, true, 1>(te, cj, A, D, g);
       }
       Ac = A[0];
@@ -1386,7 +1578,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             if (!STAGED) ckpt_load<S>(ck, i, A[0], D[0]);
             gates_only<H, 1>(sm.w1t, te, cj, g);
           } else if (PL) {
-            pl_evals<H, S, 1, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
+            pl_evals<H, S, 1, true>(pl, pl_on, pl_t0, plc, te, cj, A, D, g);
           } else {
             mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
           }
@@ -1414,7 +1606,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             }
             gates_only<H, 2>(sm.w1t, te, cj, g);
           } else if (PL) {
-            pl_evals<H, S, 2, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
+            pl_evals<H, S, 2, true>(pl, pl_on, pl_t0, plc, te, cj, A, D, g);
           } else {
             mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
           }
@@ -1448,7 +1640,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
             }
             gates_only<H, 3>(sm.w1t, te, cj, g);
           } else if (PL) {
-            pl_evals<H, S, 3, true>(pl, pl_on, tb, cf, te, cj, A, D, g);
+            pl_evals<H, S, 3, true>(pl, pl_on, pl_t0, plc, te, cj, A, D, g);
           } else {
             mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
           }
@@ -1499,7 +1691,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[1], D[1];
           Gate<H> g[1];
           const float te[1] = {t1};
-          if (PL) pl_evals<H, S, 1, false>(pl, pl_on, tb, cf, te, cj, A, D, g);
+          if (PL) pl_evals<H, S, 1, false>(pl, pl_on, pl_t0, plc, te, cj, A, D, g);
           else mlp_eval<H, S, 1, true, 0>(te, cj, A, D, g);
           const Vec<S> v = vscale<S>(lam, ds);
           if (!started) { sw.init(g[0]); started = true; } else sw.events(rec, g[0]);
@@ -1510,7 +1702,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[2], D[2];
           Gate<H> g[2];
           const float te[2] = {t1, t1 - half};
-          if (PL) pl_evals<H, S, 2, false>(pl, pl_on, tb, cf, te, cj, A, D, g);  // the stage at t1 has weight 0: its gates are not used
+          if (PL) pl_evals<H, S, 2, false>(pl, pl_on, pl_t0, plc, te, cj, A, D, g);  // the stage at t1 has weight 0: its gates are not used
           else mlp_eval<H, S, 2, true, 0>(te, cj, A, D, g);
           const Vec<S> ym = vaxpy<S>(-half, rhs<S>(A[0], D[0], y), y);  // y + half*(D1*y - A1)
           const Vec<S> am = vaxpy<S>(half, vmul<S>(lam, D[0]), lam);    // a + half*(-a*D1), D holds -sigmoid
@@ -1523,7 +1715,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Vec<S> A[3], D[3];
           Gate<H> g[3];
           const float te[3] = {t1 - ds * kOneThird, t1 - ds * kTwoThirds, t0};
-          if (PL) pl_evals<H, S, 3, false>(pl, pl_on, tb, cf, te, cj, A, D, g);
+          if (PL) pl_evals<H, S, 3, false>(pl, pl_on, pl_t0, plc, te, cj, A, D, g);
           else mlp_eval<H, S, 3, true, 0>(te, cj, A, D, g);
           // (A, D with D = -sigmoid) => f = A + D*y; the augmented step uses Ky = -f, Ka = -a*sigmoid = a*D
           // stage 1 at t1 (carried evaluation)
@@ -1603,9 +1795,10 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
 template <int H, int S, int METHOD>
 int launch_fwd(const FwdArgs& a) {
   auto kern = mlp_fixed_fwd_kernel<H, S, METHOD>;
-  const size_t smem = (a.lat.z ? sizeof(float) * lat_floats(a.lat.L, H, S) : 0) +
+  const size_t smem = (a.lat.z ? sizeof(float) * ((lat_floats(a.lat.L, H, S) + 3) / 4 * 4) : 0) +
                       ((SLODE_PL || H > 32 || SLODE_FWD_CSMEM) ? sizeof(f2) * H * kBlock : 0) +
-                      (SLODE_PL ? sizeof(float) * Pack<H, S>::N : 0);
+                      (SLODE_PL ? sizeof(float) * pl_smem_floats<H, S>() : 0) +
+                      (a.st == S ? sizeof(OutStage<S>) + 16 : 0);
   if (smem > 16 * 1024)  // static (output stage) + dynamic may pass the 48 KB default
     SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;
@@ -1627,7 +1820,7 @@ int launch_bwd(const BwdArgs& a) {
   const size_t stage_bytes =
       (CKPT && S <= 5) ? ((size_t)(kBlock / 32) * 2 * per_step * 2 * S * 32 * sizeof(f2) + (kBlock / 32) * 2 * 8 + 15) / 16 * 16 : 0;
   const size_t smem = (sizeof(BwdSmem<H, S>) + 15) / 16 * 16 + stage_bytes +
-                      ((SLODE_PL && !CKPT) ? sizeof(float) * Pack<H, S>::N : 0) +
+                      ((SLODE_PL && !CKPT) ? sizeof(float) * pl_smem_floats<H, S>() : 0) +
                       (a.lat.z ? 2 * sizeof(float) * lat_floats(a.lat.L, H, S) : 0);
   SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;

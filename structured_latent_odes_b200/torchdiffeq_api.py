@@ -29,9 +29,11 @@ __all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_fu
            "solve_fixed_from_c"]
 
 FIXED_METHODS = ("euler", "midpoint", "rk4")
-# Store the MLP evaluations of a forward solve for its discrete reverse sweep (12.5 GB per 2^20 x 100 rk4 solve at
-# S = 5; the sweep then skips ~60 % of its arithmetic).  Set to False to re-evaluate instead (no extra memory).
-EVAL_CHECKPOINTS = True
+# True: a forward solve that may be differentiated also stores the head outputs (A, -D) of every MLP evaluation
+# (12.5 GB per 2^20 x 100 rk4 solve at S = 5) and the discrete reverse sweep reads them back instead of
+# re-evaluating.  Since the kernels evaluate the heads piecewise-linearly the re-evaluation is as fast as the
+# read-back (HBM-bound) and needs no memory, so the default is False; the checkpointed sweep stays available.
+EVAL_CHECKPOINTS = False
 
 
 class KernelTimer:

@@ -44,6 +44,58 @@ def test_fixed_grid_matches_oracle(shape, method, adjoint):
     _compare(shape, method, adjoint, B=200)
 
 
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+@pytest.mark.parametrize("shape", ["cvs", "proc", "h64"])
+def test_checkpointed_reverse_sweep_matches_oracle(shape, method, monkeypatch):
+    """EVAL_CHECKPOINTS: the forward stores every evaluation's (A, -D), the discrete sweep reads them back."""
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    monkeypatch.setattr(api, "EVAL_CHECKPOINTS", True)
+    _compare(shape, method, False, B=300)
+
+
+def test_long_horizon_many_relu_crossings():
+    """Every hidden unit crosses zero somewhere on a long, non-uniform grid that starts at a negative time: the
+    piecewise-linear evaluator must follow all of them (increasing and decreasing grids)."""
+    _cuda()
+    for sign in (1.0, -1.0):
+        for method, adjoint in (("rk4", False), ("midpoint", True), ("euler", False)):
+            o = U.make_oracle("cvs", method, adjoint)
+            g = torch.Generator().manual_seed(11)
+            t = sign * (torch.cumsum(torch.rand(150, generator=g) * 0.8 + 0.05, 0) - 20.0)
+            o.times = t
+            p = U.make_product(o)
+            z = 2.0 * torch.randn(130, 15, generator=g)
+            G = torch.randn(130, 150, 5, generator=g)
+            so, gzo, gro = U.run_fwd_bwd(o, z, G)
+            sp, gzp, grp = U.run_fwd_bwd(p, z.cuda(), G.cuda())
+            assert U.rel_err(sp, so) < TOL
+            assert U.rel_err(gzp, gzo) < 2 * TOL
+            for k in gro:
+                assert U.rel_err(grp[k], gro[k]) < 2 * TOL, (sign, method, k, U.rel_err(grp[k], gro[k]))
+
+
+@pytest.mark.parametrize("shape", ["cvs", "h32", "h64"])
+def test_many_crossings_per_evaluation(shape):
+    """A short grid around t = 0 with small |c|: most hidden units cross zero within a few steps, several per
+    evaluation and trajectory."""
+    _cuda()
+    L, H, S, _ = U.SHAPES[shape]
+    for method, adjoint in (("midpoint", False), ("midpoint", True), ("rk4", False), ("euler", True)):
+        o = U.make_oracle(shape, method, adjoint)
+        o.times = torch.linspace(-3.0, 3.0, 7)
+        p = U.make_product(o)
+        g = torch.Generator().manual_seed(5)
+        z = 0.3 * torch.randn(70, L, generator=g)
+        G = torch.randn(70, 7, S, generator=g)
+        so, gzo, gro = U.run_fwd_bwd(o, z, G)
+        sp, gzp, grp = U.run_fwd_bwd(p, z.cuda(), G.cuda())
+        assert U.rel_err(sp, so) < TOL
+        if gzo is not None:
+            assert U.rel_err(gzp, gzo) < 2 * TOL
+        for k in gro:
+            assert U.rel_err(grp[k], gro[k]) < 2 * TOL, (method, adjoint, k, U.rel_err(grp[k], gro[k]))
+
+
 @pytest.mark.parametrize("B", [1, 2, 127, 128, 129, 1000])
 def test_ragged_batch_sizes(B):
     _compare("cvs", "rk4", False, B)
