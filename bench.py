@@ -261,7 +261,7 @@ def main():
     from structured_latent_odes_b200 import _cabi, sharding
     from structured_latent_odes_b200.torchdiffeq_api import KernelTimer
     from structured_latent_odes_b200 import torchdiffeq_api as _api_cfg
-    _api_cfg.EVAL_CHECKPOINTS = bool(args.eval_ckpt)
+    _api_cfg.EVAL_CHECKPOINTS = bool(args.eval_ckpt)  # the library default (None) picks by state width
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -79,7 +79,10 @@ int slode_mlp_supported(int H, int S);
 /*
  * Forward fixed-grid solve; replaces torchdiffeq.odeint(func=OdeFunc, y0, t, method) for
  * method in {euler, midpoint, rk4} with grid == t (models/blackbox_ode.py:44-45).
- *   t    (T)    strictly monotone output times == solver grid
+ *   t    (T)    strictly monotone output times == solver grid (torchdiffeq asserts the same).  The kernels follow
+ *               every hidden unit's ReLU crossing along the sweep (the heads are piecewise linear in t along a
+ *               trajectory), which is only defined for a monotone grid; the Python entry points check it, a host
+ *               that binds this ABI directly must guarantee it -- a non-monotone t gives wrong results, not an error.
  *   c    (B,H)  row-major, see above;   y0 (B,S) row-major
  *   sol  out: element (i,b,s) at sol[i*sol_stride_t + b*sol_stride_b + s]; sol[0] = y0.
  *        (T,B,S)-contiguous (torchdiffeq's layout) is stride_t=B*S, stride_b=S;

@@ -1423,6 +1423,9 @@ __device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& l
   }
 }
 
+template <int S, bool CKPT>
+__host__ __device__ constexpr bool bwd_pl() { return SLODE_PL != 0 && !CKPT && S <= 5; }
+
 template <int H, int S, int METHOD, int MODE, bool CKPT>
 __global__ void __launch_bounds__(kBlock, SLODE_BWD_MINB)
 mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
@@ -1443,7 +1446,9 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
   constexpr int kStageF2 = per_step * K2 * 32;                           // f2 per warp and interval
   constexpr int kWarps = kBlock / 32;
   constexpr size_t kStageBytes = STAGED ? (size_t)kWarps * 2 * kStageF2 * sizeof(f2) + kWarps * 2 * sizeof(uint64_t) : 0;
-  constexpr bool PL = SLODE_PL != 0 && !CKPT;  // heads re-evaluated piecewise-linearly (PlEval)
+  // heads re-evaluated piecewise-linearly (PlEval).  Not for S > 5: (alpha, beta) next to the prefix sums P, Q are
+  // 8S more live registers, and at S = 8 the sweep spills (measured 20 ms against 12.7 ms for the proc shape)
+  constexpr bool PL = bwd_pl<S, CKPT>();
   float* const tb = reinterpret_cast<float*>(smem_raw + (sizeof(BwdSmem<H, S>) + 15) / 16 * 16);
   const float* const cf = reinterpret_cast<const float*>(&sm.c[0][0]);
   unsigned char* stage_raw = reinterpret_cast<unsigned char*>(tb + (PL ? pl_smem_floats<H, S>() : 0));
@@ -1820,7 +1825,7 @@ int launch_bwd(const BwdArgs& a) {
   const size_t stage_bytes =
       (CKPT && S <= 5) ? ((size_t)(kBlock / 32) * 2 * per_step * 2 * S * 32 * sizeof(f2) + (kBlock / 32) * 2 * 8 + 15) / 16 * 16 : 0;
   const size_t smem = (sizeof(BwdSmem<H, S>) + 15) / 16 * 16 + stage_bytes +
-                      ((SLODE_PL && !CKPT) ? sizeof(float) * pl_smem_floats<H, S>() : 0) +
+                      (bwd_pl<S, CKPT>() ? sizeof(float) * pl_smem_floats<H, S>() : 0) +
                       (a.lat.z ? 2 * sizeof(float) * lat_floats(a.lat.L, H, S) : 0);
   SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;

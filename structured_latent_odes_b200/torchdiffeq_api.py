@@ -29,11 +29,12 @@ __all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_fu
            "solve_fixed_from_c"]
 
 FIXED_METHODS = ("euler", "midpoint", "rk4")
-# True: a forward solve that may be differentiated also stores the head outputs (A, -D) of every MLP evaluation
-# (12.5 GB per 2^20 x 100 rk4 solve at S = 5) and the discrete reverse sweep reads them back instead of
-# re-evaluating.  Since the kernels evaluate the heads piecewise-linearly the re-evaluation is as fast as the
-# read-back (HBM-bound) and needs no memory, so the default is False; the checkpointed sweep stays available.
-EVAL_CHECKPOINTS = False
+# Evaluation checkpoints: a forward solve that may be differentiated also stores the head outputs (A, -D) of every
+# MLP evaluation (2S floats each: 12.5 GB per 2^20 x 100 rk4 solve at S = 5) and the discrete reverse sweep reads
+# them back instead of re-evaluating.  None = automatic: off for S <= 5, where the sweep re-evaluates the heads
+# piecewise-linearly as fast as it could read them (and needs no memory), on for wider states, where it would
+# have to redo the dense products.  True / False force it.
+EVAL_CHECKPOINTS = None
 
 
 class KernelTimer:
@@ -235,9 +236,10 @@ class _LatentFixedSolve(torch.autograd.Function):
     def forward(ctx, z, y0, W1, b1, Wg, bg, Wd, bd, Wa, ba, Wb, bb, t, method_id, mode, layout):
         B, L = z.shape
         # evaluation checkpoints for the discrete reverse sweep (see slode_b200.h): only when a backward can follow
-        want_ckpt = (mode == _cabi.BWD_DISCRETE and EVAL_CHECKPOINTS and any(ctx.needs_input_grad))
         H = W1.shape[0]
         S = Wg.shape[0]
+        use_ckpt = (S > 5) if EVAL_CHECKPOINTS is None else bool(EVAL_CHECKPOINTS)
+        want_ckpt = (mode == _cabi.BWD_DISCRETE and use_ckpt and any(ctx.needs_input_grad))
         T = t.numel()
         fx0 = Wa is not None
         zc = z.detach().to(torch.float32).contiguous()

@@ -44,12 +44,15 @@ def test_fixed_grid_matches_oracle(shape, method, adjoint):
     _compare(shape, method, adjoint, B=200)
 
 
+@pytest.mark.parametrize("force", [True, False])
 @pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
 @pytest.mark.parametrize("shape", ["cvs", "proc", "h64"])
-def test_checkpointed_reverse_sweep_matches_oracle(shape, method, monkeypatch):
-    """EVAL_CHECKPOINTS: the forward stores every evaluation's (A, -D), the discrete sweep reads them back."""
+def test_forced_checkpoint_modes_match_oracle(shape, method, force, monkeypatch):
+    """EVAL_CHECKPOINTS True: the forward stores every evaluation's (A, -D) and the discrete sweep reads them back;
+    False: the sweep re-evaluates (piecewise-linearly for S <= 5, dense products for the proc shape).  The default
+    (None) picks by state width, so each shape runs one of the two in the other tests."""
     from structured_latent_odes_b200 import torchdiffeq_api as api
-    monkeypatch.setattr(api, "EVAL_CHECKPOINTS", True)
+    monkeypatch.setattr(api, "EVAL_CHECKPOINTS", force)
     _compare(shape, method, False, B=300)
 
 
