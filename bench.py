@@ -474,12 +474,20 @@ def main():
                    "unit": top["unit"], "frac": top["frac"], "traffic": traffic_map.get(traffic_key),
                    "peak_source": {"hbm": top.get("peak_source"), "fp32": fp32_src, "xu": xu_src}[bound],
                    "ms_per_launch": r["ms_per_launch"], "algorithmic_flop_per_launch": r["algorithmic_flop_per_launch"],
-                   "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"]}
+                   "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"], "note": r.get("note")}
             for k in ("hbm", "fp32", "xu"):
                 if k != bound:
                     out[k] = r[k]
             return out
 
+        # measured context for the fractions above (ncu --set full of the same kernels, profiles/r01/INDEX.md)
+        rl_b["note"] = ("re-evaluating sweep: bound by none of the three rooflines -- warp-instruction issue/latency "
+                        "(ncu: 2.10e9 warp instructions, 0.41 issued per cycle and scheduler at 2 warps per scheduler, "
+                        "254 registers; XU 24 %, FMA 22 %, DRAM 20 % of peak)" if not ckpt else
+                        "checkpointed sweep: HBM read stream of the stored evaluations (ncu: DRAM 59 % of peak, "
+                        "long_scoreboard 23 % of stall samples)")
+        rl_f["note"] = ("piecewise-linear heads: 15 MUFU lane-operations per trajectory and evaluation; ncu: XU pipe "
+                        "55 % of peak, FMA 21 %, mio_throttle + short_scoreboard 1.3 stall cycles per issue")
         tag = f"{args.method}_{int(args.adjoint)}" + ("_ckpt" if ckpt else "")
         dominant_is_bwd = bwd_ms >= fwd_ms
         line["roofline"] = flat(rl_b if dominant_is_bwd else rl_f, ("bwd_" if dominant_is_bwd else "fwd_") + tag)
