@@ -748,11 +748,15 @@ struct PlEval {
 //   tb   [Pack::N]        copy of one slot of the packed weights
 //   rinv [H, padded]      -1 / w1t_j (0 where w1t_j = 0)
 //   keys [2][H+1][kBlock] sorted crossing keys of the thread's two trajectories (SLODE_PL == 2)
-// The sorted walk serves hidden layers of up to 32 units (one gate word, 32-key sorting network in registers);
-// wider layers test all H gates per evaluation (two dozen registers of keys more would spill, and the (64,5)
-// midpoint sweep built with the walk failed parity on the device -- unresolved).
+// The sorted walk serves hidden layers of up to SLODE_WALK_MAXH = 32 units (one gate word, 32-key sorting network
+// in registers); wider layers test all H gates per evaluation.  Built with the walk (-DSLODE_WALK_MAXH=64) the
+// (64,5) midpoint reverse sweep fails parity at the default ptxas -O3 and passes at -Xptxas -O1, with the same
+// shared-memory layout passing without the walk: a code-generation problem under ~1.4 KB of spills, see DESIGN.md.
 template <int H>
-__host__ __device__ constexpr bool pl_walk() { return SLODE_PL == 2 && H <= 32; }
+#ifndef SLODE_WALK_MAXH
+#define SLODE_WALK_MAXH 32
+#endif
+__host__ __device__ constexpr bool pl_walk() { return SLODE_PL == 2 && H <= SLODE_WALK_MAXH; }
 template <int H, int S>
 __host__ __device__ constexpr int pl_smem_floats() {
   return Pack<H, S>::N + (H + 3) / 4 * 4 + (pl_walk<H>() ? 2 * (H + 1) * kBlock : 0);
