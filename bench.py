@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--adjoint", action="store_true", help="odeint_adjoint gradient semantics instead of discrete")
     ap.add_argument("--ref-batch", type=int, default=8192, help="trajectories per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--eval-ckpt", action="store_true",
                     help="reverse sweep reads the forward's evaluation checkpoints instead of re-evaluating the MLP")
     ap.add_argument("--layout", default="tbs", choices=["tbs", "bts"],
