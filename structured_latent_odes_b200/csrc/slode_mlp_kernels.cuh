@@ -173,6 +173,12 @@ template <int S> __device__ __forceinline__ Vec<S> vload2(const float* p0, const
   SLODE_FOR_S r.v[s] = pk(__ldg(p0 + s), __ldg(p1 + s));
   return r;
 }
+// a load the compiler may not sink to its use
+__device__ __forceinline__ float ld_early(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 // pull the S floats at p (20-32 bytes, may straddle two sectors) towards L1 for a later vload2
 template <int S> __device__ __forceinline__ void vprefetch(const float* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -929,9 +935,13 @@ __device__ __forceinline__ void lat_hidden(const LatSmem& ls, const LatentSrc& l
   }
   const float* z0 = lat.z + pi.b0 * lat.L;
   const float* z1 = lat.z + pi.b1 * lat.L;
+  // the latent row is read one element ahead of its use (each element feeds 2H dependent-free FFMA2, enough to
+  // cover an L1 hit but not a miss taken at the point of use)
+  f2 znext = lat.L > 0 ? pk(__ldg(z0), __ldg(z1)) : 0ull;
 #pragma unroll 1
   for (int l = 0; l < lat.L; ++l) {
-    const f2 zl = pk(__ldg(z0 + l), __ldg(z1 + l));
+    const f2 zl = znext;
+    if (l + 1 < lat.L) znext = pk(ld_early(z0 + l + 1), ld_early(z1 + l + 1));
     const float* wz = ls.Wz + l * H;
     const float* wa = ls.Wa + l * H;
 #pragma unroll
@@ -1081,9 +1091,11 @@ mlp_fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
       k1 = rhs<S>(A[0], D[0], x);
     }
 
+    float t_ahead = T > 1 ? __ldg(tgrid + 1) : t0;  // the grid is read one step ahead of its use
 #pragma unroll 1
     for (int i = 0; i + 1 < T; ++i) {
-      const float t1 = __ldg(tgrid + i + 1);
+      const float t1 = t_ahead;
+      if (i + 2 < T) t_ahead = ld_early(tgrid + i + 2);
       const float dt = t1 - t0;
       if (METHOD == SLODE_METHOD_EULER) {
         Vec<S> A[1], D[1];
@@ -1404,9 +1416,11 @@ __device__ __forceinline__ void lat_epilogue(BwdSmem<H, S>& sm, const LatSmem& l
   reduce_units<H>(lane, [&](int k) { return gcr[k]; }, [&](int k) { return gb1 + k; });
   const float* z0 = lat.z + pi.b0 * L;
   const float* z1 = lat.z + pi.b1 * L;
+  f2 znext = L > 0 ? pk(__ldg(z0), __ldg(z1)) : 0ull;
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
-    const f2 zl = pk(__ldg(z0 + l), __ldg(z1 + l));
+    const f2 zl = znext;
+    if (l + 1 < L) znext = pk(ld_early(z0 + l + 1), ld_early(z1 + l + 1));
     const float* wz = ls.Wz + l * H;
     const float* wa = ls.Wa + l * H;
     f2 dz = 0ull;
@@ -1558,6 +1572,11 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
     for (int i = T - 2; i >= 0; --i) {
       const float t0 = __ldg(tgrid + i);
       const Vec<S> x = vload2<S>(xs0 + (int64_t)i * st, xs1 + (int64_t)i * st);
+      // the cotangent row of grid point i is consumed at the END of this interval: issued here (volatile asm keeps
+      // it here) its latency hides behind the whole interval -- read at the point of use it cost 12 % of the sweep
+      Vec<S> gi;
+#pragma unroll
+      SLODE_FOR_S gi.v[s] = pk(ld_early(gs0 + (int64_t)i * gst + s), ld_early(gs1 + (int64_t)i * gst + s));
       if (i > 0) {  // next interval's state and cotangent rows: in L1 by the time they are read
         vprefetch<S>(xs0 + (int64_t)(i - 1) * st);
         vprefetch<S>(xs1 + (int64_t)(i - 1) * st);
@@ -1757,7 +1776,7 @@ mlp_fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const fl
           Dc = D[2];
         }
       }
-      lam = vadd<S>(lam, vscale2<S>(vload2<S>(gs0 + (int64_t)i * gst, gs1 + (int64_t)i * gst), live));
+      lam = vadd<S>(lam, vscale2<S>(gi, live));
       t1 = t0;
     }
 
