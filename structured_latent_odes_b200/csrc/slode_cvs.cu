@@ -320,23 +320,34 @@ cvs_bwd_kernel(int64_t B, int T, int nsub, const R* __restrict__ tgrid, const R*
     R gie = R(0), grm = R(0);
     V4<R> lam = load4<R>(gs + (int64_t)(T - 1) * gst);
     R t1 = tgrid[T - 1];
+    // the rows of grid point i are loaded one interval ahead of their use (loop-carried, so the compiler cannot
+    // sink the loads to the point of use, where their latency would be exposed once per interval)
+    V4<R> g_ahead = lam, x_ahead = lam;
+    if (T >= 2) {
+      g_ahead = load4<R>(gs + (int64_t)(T - 2) * gst);
+      x_ahead = load4<R>(xs + (int64_t)(MODE == SLODE_BWD_DISCRETE ? T - 2 : T - 1) * st);
+    }
     for (int i = T - 2; i >= 0; --i) {
       const R t0 = tgrid[i];
       const R h = (t1 - t0) / R(nsub);
+      const V4<R> g = g_ahead, xrow = x_ahead;
+      if (i > 0) {
+        g_ahead = load4<R>(gs + (int64_t)(i - 1) * gst);
+        x_ahead = load4<R>(xs + (int64_t)(MODE == SLODE_BWD_DISCRETE ? i - 1 : i) * st);
+      }
       if (MODE == SLODE_BWD_DISCRETE) {
         V4<R> ys[kMaxSub];
         V4<R> Y[4];
-        ys[0] = load4<R>(xs + (int64_t)i * st);
+        ys[0] = xrow;
         for (int k = 0; k + 1 < nsub; ++k) ys[k + 1] = step<R, METHOD>(ys[k], h, ie, rm, th, Y);
         for (int k = nsub - 1; k >= 0; --k) {
           step<R, METHOD>(ys[k], h, ie, rm, th, Y);
           lam = step_adjoint<R, METHOD>(Y, h, ie, rm, th, lam, gie, grm, gth);
         }
       } else {
-        V4<R> y = load4<R>(xs + (int64_t)(i + 1) * st);
+        V4<R> y = xrow;
         for (int k = 0; k < nsub; ++k) aug_step<R, METHOD>(y, lam, h, ie, rm, th, gie, grm, gth);
       }
-      const V4<R> g = load4<R>(gs + (int64_t)i * gst);
 #pragma unroll
       for (int c = 0; c < 4; ++c) lam.v[c] += g.v[c];
       t1 = t0;
