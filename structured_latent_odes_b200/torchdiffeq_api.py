@@ -35,6 +35,7 @@ FIXED_METHODS = ("euler", "midpoint", "rk4")
 # piecewise-linearly as fast as it could read them (and needs no memory), on for wider states, where it would
 # have to redo the dense products.  True / False force it.
 EVAL_CHECKPOINTS = None
+CKPT_MAX_FRACTION = 0.5   # of the free device memory; above it the reverse sweep re-evaluates instead
 
 
 class KernelTimer:
@@ -113,6 +114,37 @@ def _check_blackbox(func):
     return z, hid, gro, deg
 
 
+def _check_weights(dev, what, *tensors):
+    """Every weight the kernels read through a raw pointer must be float32 on the device of the batch: a model left
+    on the CPU / another GPU would be an illegal address (sticky, kills the context), a .double() model silent
+    garbage.  The reference raises torch's device / dtype errors here; so do we, before any launch."""
+    for name, x in tensors:
+        if x is None:
+            continue
+        if x.device != dev:
+            raise RuntimeError(f"{what}: {name} is on {x.device} but the batch is on {dev}; move the module with "
+                               ".to(device) (no implicit copies, no CPU fallback)")
+        if x.dtype != torch.float32:
+            raise TypeError(f"{what}: {name} has dtype {x.dtype}; the kernels compute in float32 like the reference")
+
+
+_T_CHECKED = [None, -1]   # (weak reference to the last grid tensor that passed, its version counter)
+
+
+def _check_monotone(t):
+    """t strictly increasing or decreasing.  For a device tensor the test is a device->host sync, so the verdict is
+    remembered for the SAME tensor object at the same version (``OdeModel.times`` is handed over unchanged on every
+    solve): repeated solves on one grid do not sync."""
+    import weakref
+    ref, ver = _T_CHECKED
+    if ref is not None and ref() is t and ver == t._version:
+        return
+    d = t.detach()[1:] - t.detach()[:-1]
+    if not (bool((d > 0).all()) or bool((d < 0).all())):
+        raise ValueError("t must be strictly increasing or decreasing")
+    _T_CHECKED[0], _T_CHECKED[1] = weakref.ref(t), t._version
+
+
 def _check_common(func, y0, t, method, options, event_fn):
     if event_fn is not None:
         raise NotImplementedError("event_fn is not used by the reference and is not supported")
@@ -135,11 +167,9 @@ def _check_common(func, y0, t, method, options, event_fn):
         raise ValueError("t must be a one-dimensional tensor")
     if not t.is_floating_point():
         raise TypeError("t must be floating point")
-    t = t.detach().to(device=y0.device, dtype=y0.dtype).contiguous()
     if t.numel() > 1:
-        d = t[1:] - t[:-1]
-        if not (bool((d > 0).all()) or bool((d < 0).all())):
-            raise ValueError("t must be strictly increasing or decreasing")
+        _check_monotone(t)
+    t = t.detach().to(device=y0.device, dtype=y0.dtype).contiguous()
     if method in FIXED_METHODS and options and not is_cvs:
         raise NotImplementedError(f"options={options!r} for fixed-grid solvers (the reference passes none: "
                                   "the solver grid is t itself)")
@@ -253,7 +283,14 @@ class _LatentFixedSolve(torch.autograd.Function):
         ckpt = None
         if want_ckpt and B > 0 and T > 1:
             n = _cabi.lib().slode_eval_ckpt_floats(method_id, B, T, S)
-            ckpt = torch.empty(n, device=z.device, dtype=torch.float32)
+            free, _total = torch.cuda.mem_get_info(z.device)
+            # 8S bytes per MLP evaluation and trajectory (20 GB at 2^20 x 100 rk4, S = 8): only when it fits next to
+            # the sweep's own tensors; otherwise the sweep re-evaluates (it does whenever ckpt is null)
+            if 4 * n <= int(CKPT_MAX_FRACTION * free):
+                try:
+                    ckpt = torch.empty(n, device=z.device, dtype=torch.float32)
+                except torch.OutOfMemoryError:
+                    ckpt = None
         with torch.cuda.device(z.device), _timed("fwd"):
             rc = _cabi.lib().slode_latent_fixed_fwd(
                 method_id, B, T, L, H, S, _ptr(t), _ptr(zc), *[_ptr(x) for x in w], *[_ptr(x) for x in x0w], _ptr(y0c),
@@ -326,6 +363,15 @@ def solve_latent(z, dynamics, x0_net, t, method, adjoint, layout="tbs"):
                                   f"{_cabi.supported_shapes()}. There is no generic fallback.")
     if la.out_features != H or lb.in_features != H or lb.out_features != S or la.in_features != z.shape[1]:
         raise ValueError("latent_to_ode_net layer sizes do not match the dynamics")
+    if z.ndim != 2 or hid.in_features != z.shape[1] + 1:
+        raise ValueError(f"z {tuple(z.shape)} does not match dynamics_hidden.in_features={hid.in_features}")
+    if not z.is_floating_point():
+        raise TypeError(f"z must be floating point, got {z.dtype}")
+    _check_weights(z.device, "solve_ODE", ("dynamics_hidden.weight", hid.weight), ("dynamics_hidden.bias", hid.bias),
+                   ("dyanamics_growth.weight", gro.weight), ("dyanamics_growth.bias", gro.bias),
+                   ("dyanmics_degradation.weight", deg.weight), ("dyanmics_degradation.bias", deg.bias),
+                   ("latent_to_ode_net.0.weight", la.weight), ("latent_to_ode_net.0.bias", la.bias),
+                   ("latent_to_ode_net.2.weight", lb.weight), ("latent_to_ode_net.2.bias", lb.bias))
     t = t.detach().to(device=z.device, dtype=torch.float32).contiguous()
     mode = _cabi.BWD_TDE_ADJOINT if adjoint else _cabi.BWD_DISCRETE
     return _LatentFixedSolve.apply(z, None, hid.weight, hid.bias, gro.weight, gro.bias, deg.weight, deg.bias,
@@ -395,6 +441,16 @@ def _dopri5_forward(y0, c, w, t, rtol, atol, options, layout, want_ckpt):
     return sol, (ckpt[:n_acc] if ckpt is not None else None), steps
 
 
+def _check_func_tensors(y0, z, hid, gro, deg):
+    if z.device != y0.device:
+        raise RuntimeError(f"func.constants is on {z.device} but y0 is on {y0.device}")
+    if not z.is_floating_point():
+        raise TypeError(f"func.constants must be floating point, got {z.dtype}")
+    _check_weights(y0.device, "odeint", ("dynamics_hidden.weight", hid.weight), ("dynamics_hidden.bias", hid.bias),
+                   ("dyanamics_growth.weight", gro.weight), ("dyanamics_growth.bias", gro.bias),
+                   ("dyanmics_degradation.weight", deg.weight), ("dyanmics_degradation.bias", deg.bias))
+
+
 def _solve_blackbox(func, y0, t, method, mode, layout):
     z, hid, gro, deg = _check_blackbox(func)
     B, S = y0.shape
@@ -407,8 +463,7 @@ def _solve_blackbox(func, y0, t, method, mode, layout):
         raise NotImplementedError(
             f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled kernel; available (H,S): "
             f"{_cabi.supported_shapes()}. There is no generic fallback.")
-    if z.device != y0.device or hid.weight.device != y0.device:
-        raise RuntimeError("func tensors and y0 must live on the same CUDA device")
+    _check_func_tensors(y0, z, hid, gro, deg)
     # the time-invariant part of the hidden pre-activation, c = z W1[:,1:]^T + b1, is computed inside the kernels
     return _LatentFixedSolve.apply(z, y0, hid.weight, hid.bias, gro.weight, gro.bias, deg.weight, deg.bias,
                                    None, None, None, None, t, _cabi.METHODS[method], mode, layout)
@@ -475,6 +530,7 @@ def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
     if gro.out_features != S or not _cabi.lib().slode_mlp_supported(H, S):
         raise NotImplementedError(f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled kernel; available: "
                                   f"{_cabi.supported_shapes()}")
+    _check_func_tensors(y0, z, hid, gro, deg)
     if t.numel() > 1 and bool(t[0] > t[-1]):
         raise NotImplementedError("dopri5 with decreasing output times (the reference always integrates forward)")
     needs_grad = torch.is_grad_enabled() and (y0.requires_grad or z.requires_grad

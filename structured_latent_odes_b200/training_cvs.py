@@ -98,6 +98,14 @@ class _Prior(nn.Module):
         return self.loc(u), torch.exp(self.log_scale(u))
 
 
+def _bernoulli_logp(probs, y):
+    """sum of Bernoulli(probs).log_prob(y) as pyro / torch.distributions compute it: probs are clamped to
+    [eps, 1 - eps] (``probs_to_logits``) so a saturated sigmoid gives a finite value instead of 0 * -inf = NaN."""
+    eps = torch.finfo(probs.dtype).eps
+    p = probs.clamp(eps, 1.0 - eps)
+    return -torch.nn.functional.binary_cross_entropy(p, y, reduction="sum")
+
+
 def _normal_logp(x, loc, scale):
     return (-0.5 * ((x - loc) / scale) ** 2 - torch.log(scale) - 0.5 * math.log(2 * math.pi)).sum()
 
@@ -158,8 +166,7 @@ class MechanisticModel(nn.Module):
         log_p = _normal_logp(z, loc, scale)
         a_i = self.q_iext_given_z_iext(z[:, :c.z_iext_dim])
         a_r = self.q_rtpr_given_z_rtpr(z[:, c.z_iext_dim:])
-        bern = lambda a, y: (y * torch.log(a) + (1 - y) * torch.log1p(-a)).sum()  # noqa: E731
-        log_p = log_p + float(c.aux_loss_multiplier) * (bern(a_i, iext) + bern(a_r, rtpr))
+        log_p = log_p + float(c.aux_loss_multiplier) * (_bernoulli_logp(a_i, iext) + _bernoulli_logp(a_r, rtpr))
         return -log_p
 
     # ---- evaluation helpers --------------------------------------------------------------------------------

@@ -196,6 +196,23 @@ def test_errors_on_device():
     m.init_with_params(t, 3, 15, 7, False, "rk4", "cuda")
     with pytest.raises(NotImplementedError, match="no compiled kernel"):
         m.cuda().solve_ODE(torch.randn(4, 15, device="cuda"))
+    # weights the kernels would read through raw pointers: wrong device / dtype must raise BEFORE any launch
+    # (an illegal address would be sticky and kill the context for every later test)
+    cpu_model = slode.OdeModel()
+    cpu_model.init_with_params(t, 5, 15, 25, False, "rk4", "cuda")   # parameters left on the CPU
+    with pytest.raises(RuntimeError, match="is on cpu"):
+        cpu_model.solve_ODE(torch.randn(4, 15, device="cuda"))
+    with pytest.raises(RuntimeError, match="is on cpu"):
+        slode.odeint(cpu_model.gen_dynamics(torch.randn(4, 15, device="cuda")), y0, t, method="rk4")
+    dbl = slode.OdeModel()
+    dbl.init_with_params(t, 5, 15, 25, False, "midpoint", "cuda")
+    dbl = dbl.cuda().double()
+    with pytest.raises(TypeError, match="float64"):
+        dbl.solve_ODE(torch.randn(4, 15, device="cuda"))
+    with pytest.raises(TypeError, match="float64"):
+        slode.odeint_adjoint(dbl.gen_dynamics(torch.randn(4, 15, device="cuda")), y0, t, method="midpoint")
+    torch.cuda.synchronize()  # the context is still healthy
+    assert p.solve_ODE(torch.randn(4, 15, device="cuda")).shape == (4, 86, 5)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -259,3 +276,38 @@ def test_full_size_batch_permutation_and_subset_consistency():
     whole = grads(slice(0, B))
     halves = grads(slice(0, B // 2)) + grads(slice(B // 2, B))
     assert U.rel_err(halves, whole) < 5e-5  # fp32 sums of 1e6 terms in a different order
+
+
+def test_full_size_exact_bench_step_oracle_spot_check():
+    """The EXACT step bench.py times (configs[1]: rk4, T=100, L15/H25/S5, seed-12 reference-init weights, 2^20
+    trajectories z ~ N(0,1) from Generator(seed 12), upstream gradient G from the same generator): 512 rows of the
+    full-size solve and of the full-size reverse sweep's grad_z against the CPU oracle, and the parameter gradients
+    of those rows solved alone (the sweep is row-independent; parameter gradients are sums over rows)."""
+    _cuda()
+    B, T = 1 << 20, 100
+    m = _full_model("rk4", adjoint=False, T=T)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    z = torch.randn(B, 15, device="cuda", generator=g).requires_grad_(True)
+    G = torch.randn(T, B, 5, device="cuda", generator=g).permute(1, 0, 2)   # bench.py's resident layout ("tbs")
+    sol = m.solve_ODE(z)
+    sol.backward(G)
+    rows = torch.cat([torch.arange(0, 256, device="cuda"),                      # first tile
+                      torch.randint(0, B, (192,), device="cuda", generator=g),  # anywhere
+                      torch.arange(B - 64, B, device="cuda")])                  # last tile
+    o = U.make_oracle("cvs", "rk4", False)
+    o.times = torch.arange(0.0, T, 1.0)
+    o.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    zo = z.detach()[rows].cpu().requires_grad_(True)
+    so = o.solve_ODE(zo)
+    (so * G[rows].cpu()).sum().backward()
+    assert U.rel_err(sol.detach()[rows], so) < TOL
+    assert U.rel_err(z.grad[rows], zo.grad) < TOL
+    # parameter gradients: the same rows through the product alone
+    m.zero_grad()
+    zs = z.detach()[rows].clone().requires_grad_(True)
+    (m.solve_ODE(zs) * G[rows]).sum().backward()
+    gro = {k: p.grad for k, p in o.named_parameters() if p.grad is not None and ".prod." not in k and ".degr." not in k}
+    grp = {k: p.grad for k, p in m.named_parameters() if p.grad is not None and ".prod." not in k and ".degr." not in k}
+    assert set(gro) == set(grp)
+    for k in gro:
+        assert U.rel_err(grp[k], gro[k]) < TOL, (k, U.rel_err(grp[k], gro[k]))

@@ -97,3 +97,15 @@ def test_a_few_steps_reduce_both_objectives():
     assert last[0] < first[0] and last[1] < first[1]
     stats = tc.input_pred_stats(m, batch, is_post=True)
     assert set(stats) == {"iext", "rtpr", "l1", "elbo"} and stats["elbo"].shape == (2,)
+
+
+def test_bernoulli_term_is_finite_when_the_classifier_saturates():
+    """y*log(a) + (1-y)*log1p(-a) is NaN for a == 1.0 / 0.0 in fp32; pyro's Bernoulli(probs) clamps."""
+    from structured_latent_odes_b200.training_cvs import _bernoulli_logp
+    a = torch.tensor([[1.0], [0.0], [1.0], [0.0], [0.3]], requires_grad=True)
+    y = torch.tensor([[1.0], [0.0], [0.0], [1.0], [1.0]])
+    got = _bernoulli_logp(a, y)
+    want = D.Bernoulli(probs=a.detach()).log_prob(y).sum()
+    assert torch.isfinite(got) and torch.allclose(got, want, rtol=1e-6)
+    got.backward()
+    assert torch.isfinite(a.grad).all()
