@@ -20,15 +20,18 @@
  *     asynchronously on it and the call returns immediately;
  *   - return value 0 = ok, otherwise an SLODE_E* code; slode_last_error() gives the message of
  *     the last failure on the calling thread;
- *   - thread-safe; calls on different streams of one device are serialised on the device
- *     (they share one packed-weight buffer in constant memory, ordered by an event).
+ *   - the fixed-grid entry points keep no state between calls: weights are staged per block from the
+ *     caller's tensors, scratch memory is the caller's (`workspace`, sized by slode_fixed_workspace_bytes),
+ *     so they are re-entrant, may run concurrently on any streams and can be captured into CUDA graphs.
+ *     (The dopri5 entry points still share one library-owned scratch area per device and are serialised.)
  *
  * The blackbox right-hand side (Dynamics.forward, models/blackbox_ode.py:97-109):
  *     x = [t, z];  h = relu(W1 x + b1);  f = sigmoid(Wg h + bg) - sigmoid(Wd h + bd) * state
  * enters as   h_j(t) = relu(w1t[j] * t + c[b][j])   with
  *     w1t = W1[:, 0]            (the column that multiplies t, :72,:101)
- *     c   = z @ W1[:, 1:]^T + b1   (B,H)  -- time-invariant per trajectory, a plain GEMM done by
- *                                            the host with cuBLAS (torch.addmm)
+ *     c   = z @ W1[:, 1:]^T + b1   (B,H)  -- time-invariant per trajectory; computed inside the kernels
+ *                                            by the slode_latent_* entry points (from z), or handed in
+ *                                            precomputed to the slode_mlp_* entry points
  * Wg/Wd are dyanamics_growth.weight / dyanmics_degradation.weight, torch Linear layout (S,H).
  */
 #ifndef SLODE_B200_H
@@ -73,8 +76,24 @@ extern "C" {
 int slode_query(int what);
 const char* slode_last_error(void);
 
-/* 1 if kernels for this (H,S) pair exist, else 0 */
+/* 1 if fixed-grid kernels (slode_*_fixed_*) for this (H,S) pair exist, else 0 */
 int slode_mlp_supported(int H, int S);
+/* 1 if the dopri5 kernels (slode_mlp_dopri5_*) exist for this (H,S) pair, else 0 */
+int slode_dopri5_supported(int H, int S);
+
+/*
+ * Scratch memory of the fixed-grid entry points below, in bytes, for a call with these arguments (0 is
+ * possible).  The caller allocates it on the device (any alignment cudaMalloc / the torch allocator gives),
+ * passes it as `workspace` and may free or reuse it once the call's work on `stream` has finished.  Contents
+ * need not be initialised and are not preserved.
+ *   backward     0: slode_*_fixed_fwd, 1: slode_*_fixed_bwd (flip records of the reverse sweep: NQ*16 bytes
+ *                per hidden unit and RESIDENT thread -- it does not grow with B beyond one wave of blocks)
+ *   fused        0: slode_mlp_fixed_* (c, y0 given), 1: slode_latent_* with y0 given, 2: with the x0 net fused
+ *   rows_in_time 1 if sol is (B,T,S)-contiguous (sol_stride_t == S)
+ * Returns -1 for arguments the entry point itself would reject.
+ */
+int64_t slode_fixed_workspace_bytes(int backward, int method, int mode, int64_t B, int T, int L, int H, int S,
+                                    int fused, int rows_in_time);
 
 /*
  * Forward fixed-grid solve; replaces torchdiffeq.odeint(func=OdeFunc, y0, t, method) for
@@ -93,7 +112,7 @@ int slode_mlp_fixed_fwd(int method, int64_t B, int T, int H, int S,
                         const float* w1t, const float* Wg, const float* bg,
                         const float* Wd, const float* bd,
                         float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
-                        void* stream);
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Reverse-mode gradient of slode_mlp_fixed_fwd (one reverse sweep over the stored grid states;
@@ -113,14 +132,15 @@ int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
                         const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
                         const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
                         float* grad_y0, float* grad_c, float* grad_w,
-                        void* stream);
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Fused variants of slode_mlp_fixed_fwd / _bwd: the solve together with the two small nets in front of it, i.e.
  * the whole of OdeModel.solve_ODE (models/blackbox_ode.py:36-47):
  *     c  = z W1[:,1:]^T + b1                               (first layer of Dynamics on the constants, :99-106)
  *     x0 = sigmoid(Wb relu(Wa z + ba) + bb)                (latent_to_ode_net, :19-22, :32-34)
- * computed per trajectory inside the solver kernels (no (B,H) intermediates in HBM, no cuBLAS calls).
+ * computed per trajectory inside the solver kernels (no (B,H) intermediates in HBM, no cuBLAS calls).  The reverse
+ * sweep re-evaluates the heads from sol[i] (piecewise-linear evaluator); nothing but sol is checkpointed.
  *   z (B,L);  W1 = dynamics_hidden.weight (H, L+1), b1 its bias;  Wa (H,L), ba (H), Wb (S,H), bb (S) =
  *   latent_to_ode_net[0] / [2] -- pass all four as NULL and give y0 (B,S) instead when the caller computes the
  *   initial state itself (the torchdiffeq.odeint entry, where y0 is an argument).
@@ -129,15 +149,7 @@ int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S,
  * zero-fills), flat
  *     [ dw1t (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) | dW1[:,1:] (H*L) | db1 (H) |
  *       dWa (H*L) | dba (H) | dWb (S*H) | dbb (S) ]           (the last four only when the x0 net is fused).
- *
- * eval_ckpt (optional, may be NULL): slode_eval_ckpt_floats(method, B, T, S) floats.  When given, the forward stores
- * the growth / degradation sigmoids of every MLP evaluation of the solve there (120 B per trajectory and rk4 step at
- * S = 5, stored per tile of 256 trajectories) and the DISCRETE reverse sweep reads them back instead of re-evaluating the MLP (it then only recomputes the
- * hidden-layer gates): trades 12.5 GB of HBM per 2^20 x 100 solve for ~60 % of the reverse sweep's arithmetic.  The
- * odeint_adjoint mode evaluates at its own stage times and ignores it.
  */
-int64_t slode_eval_ckpt_floats(int method, int64_t B, int T, int S);
-
 int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S,
                            const float* t, const float* z,
                            const float* W1, const float* b1, const float* Wg, const float* bg,
@@ -145,7 +157,7 @@ int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S,
                            const float* Wa, const float* ba, const float* Wb, const float* bb,
                            const float* y0,
                            float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
-                           float* eval_ckpt, void* stream);
+                           void* workspace, int64_t workspace_bytes, void* stream);
 
 int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H, int S,
                            const float* t, const float* z,
@@ -155,7 +167,7 @@ int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H,
                            const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
                            const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
                            float* grad_z, float* grad_y0, float* grad_params,
-                           const float* eval_ckpt, void* stream);
+                           void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Adaptive Dormand-Prince 5(4) forward solve; replaces torchdiffeq.odeint(func=OdeFunc, y0, t, method="dopri5",

@@ -11,8 +11,10 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(CSRC, "libslode_b200.so")
-SOURCES = ["slode_host.cu", "slode_mlp.cu", "slode_cvs.cu", "slode_heads.cu",
-           "slode_mlp_25_5.cu", "slode_mlp_25_8.cu", "slode_mlp_16_4.cu", "slode_mlp_32_5.cu", "slode_mlp_64_5.cu"]
+SOURCES = ["slode_host.cu", "slode_mlp.cu", "slode_fixed_api.cu", "slode_cvs.cu", "slode_heads.cu",
+           "slode_mlp_25_5.cu", "slode_mlp_25_8.cu", "slode_mlp_16_4.cu", "slode_mlp_32_5.cu", "slode_mlp_64_5.cu",
+           "slode_fixed_25_5.cu", "slode_fixed_25_8.cu", "slode_fixed_16_4.cu", "slode_fixed_32_5.cu",
+           "slode_fixed_64_5.cu", "slode_fixed_128_5.cu", "slode_fixed_256_5.cu", "slode_fixed_512_5.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

@@ -28,13 +28,14 @@ SIGNATURES = {
     "slode_query": (_i, [_i]),
     "slode_last_error": (ctypes.c_char_p, []),
     "slode_mlp_supported": (_i, [_i, _i]),
-    "slode_mlp_fixed_fwd": (_i, [_i, _i64, _i, _i, _i] + [_p] * 8 + [_p, _i64, _i64, _p]),
+    "slode_dopri5_supported": (_i, [_i, _i]),
+    "slode_fixed_workspace_bytes": (_i64, [_i, _i, _i, _i64, _i, _i, _i, _i, _i, _i]),
+    "slode_mlp_fixed_fwd": (_i, [_i, _i64, _i, _i, _i] + [_p] * 8 + [_p, _i64, _i64, _p, _i64, _p]),
     "slode_mlp_fixed_bwd": (_i, [_i, _i, _i64, _i, _i, _i] + [_p] * 7 + [_p, _i64, _i64, _p, _i64, _i64]
-                            + [_p, _p, _p, _p]),
-    "slode_latent_fixed_fwd": (_i, [_i, _i64, _i, _i, _i, _i] + [_p] * 13 + [_p, _i64, _i64, _p, _p]),
+                            + [_p, _p, _p, _p, _i64, _p]),
+    "slode_latent_fixed_fwd": (_i, [_i, _i64, _i, _i, _i, _i] + [_p] * 13 + [_p, _i64, _i64, _p, _i64, _p]),
     "slode_latent_fixed_bwd": (_i, [_i, _i, _i64, _i, _i, _i, _i] + [_p] * 12 + [_p, _i64, _i64, _p, _i64, _i64]
-                               + [_p, _p, _p, _p, _p]),
-    "slode_eval_ckpt_floats": (_i64, [_i, _i64, _i, _i]),
+                               + [_p, _p, _p, _p, _i64, _p]),
     "slode_mlp_dopri5_fwd": (_i, [_i64, _i, _i, _i] + [_p] * 8 + [ctypes.c_double] * 3 + [_i64, _p, _i64]
                              + [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p]),
     "slode_mlp_dopri5_bwd": (_i, [_i64, _i, _i, _i] + [_p] * 7 + [_i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),

@@ -1,0 +1,1412 @@
+// Fixed-grid solve of the SLODE blackbox latent ODE and its reverse sweep, hand-written for sm_100a (round 2).
+//
+// Right-hand side (reference: Dynamics.forward, models/blackbox_ode.py:97-109):
+//     h_j(t)  = relu(w1t_j * t + c_j)                       c = z W1[:,1:]^T + b1  (per trajectory)
+//     A_s(t)  = sigmoid(bg_s + sum_j Wg_sj h_j(t))          "growth"
+//     D_s(t)  = sigmoid(bd_s + sum_j Wd_sj h_j(t))          "degradation"
+//     f(t,x)  = A(t) - D(t) * x                              (affine in the state, elementwise)
+// integrated by torchdiffeq's fixed-grid euler / midpoint / rk4 (= 3/8 rule) with grid == output times
+// (models/blackbox_ode.py:40-45), reverse sweep = exact discrete adjoint (odeint + autograd) or the
+// odeint_adjoint re-discretisation.
+//
+// Formulation (unchanged from round 1): along one trajectory the head pre-activations are
+// piecewise linear in t,  o_k(t) = alpha_k t + beta_k,  with coefficients that change only where a relu gate
+// flips; the crossings are sorted once per trajectory and walked in sweep order.  The weight / hidden-layer
+// gradients come from prefix sums P = sum delta, Q = sum delta*t of the head cotangents, snapshotted when a gate
+// flips ("flip records") and combined per unit at the end of the sweep.
+//
+// Mapping (new in round 2).  ONE thread = ONE trajectory.  Round 1 packed two trajectories per thread in fp32x2
+// halves, which doubled the live registers (254, 2 warps per scheduler) and left the reverse sweep bound by
+// instruction issue latency at 0.44 IPC.  Here the fp32x2 halves hold two STATES of the same trajectory
+// (s = 2p, 2p+1): every S-vector operation is ceil(S/2) packed instructions, the evaluator's merged reciprocal
+// pairs the two sigmoids of a register pair, and the register footprint roughly halves, so that 4-5 blocks of 128
+// threads are resident per SM (16-20 warps) and the schedulers always have an eligible warp.
+// Weights are staged per block into shared memory straight from the torch tensors (no constant-memory symbol,
+// no pack kernel, no cross-call state: the entry points are re-entrant and CUDA-graph capturable).
+#pragma once
+
+#include <algorithm>
+#include <type_traits>
+
+#include "slode_common.cuh"
+#include "slode_mlp_api.h"
+
+#ifndef SLODE_FX_FWD_MINB
+#define SLODE_FX_FWD_MINB 5
+#endif
+#ifndef SLODE_FX_BWD_MINB
+#define SLODE_FX_BWD_MINB 4
+#endif
+
+namespace slode {
+namespace fx {
+
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (lo = state 2p, hi = state 2p+1 of one trajectory)
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f2;
+
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 bc(float v) { return pk(v, v); }
+__device__ __forceinline__ void unpk(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float lo_of(f2 v) {
+  float a, b;
+  unpk(v, a, b);
+  return a;
+}
+__device__ __forceinline__ float hi_of(f2 v) {
+  float a, b;
+  unpk(v, a, b);
+  return b;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// min that propagates NaN (torch's relu / sigmoid would; fminf launders it)
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float relu_nan(float a) {
+  float d;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(d) : "f"(a));
+  return d;
+}
+__device__ __forceinline__ float ld_early(const float* p) {  // a load the compiler may not sink to its use
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr float kNegLn2 = -0.6931471805599453f;  // unscaled weight = packed weight * kNegLn2
+
+template <int N>
+struct V {  // N register pairs = 2N states (the last half is padding when S is odd: it stays exactly zero)
+  f2 v[N];
+};
+#define FX_FOR(N) _Pragma("unroll") for (int p = 0; p < N; ++p)
+
+template <int N> __device__ __forceinline__ V<N> vzero() {
+  V<N> r;
+  FX_FOR(N) r.v[p] = 0ull;
+  return r;
+}
+template <int N> __device__ __forceinline__ V<N> vadd(const V<N>& a, const V<N>& b) {
+  V<N> r;
+  FX_FOR(N) r.v[p] = add2(a.v[p], b.v[p]);
+  return r;
+}
+template <int N> __device__ __forceinline__ V<N> vsub(const V<N>& a, const V<N>& b) {
+  V<N> r;
+  FX_FOR(N) r.v[p] = sub2(a.v[p], b.v[p]);
+  return r;
+}
+template <int N> __device__ __forceinline__ V<N> vmul(const V<N>& a, const V<N>& b) {
+  V<N> r;
+  FX_FOR(N) r.v[p] = mul2(a.v[p], b.v[p]);
+  return r;
+}
+template <int N> __device__ __forceinline__ V<N> vscale(const V<N>& a, float c) {
+  V<N> r;
+  const f2 cc = bc(c);
+  FX_FOR(N) r.v[p] = mul2(a.v[p], cc);
+  return r;
+}
+template <int N> __device__ __forceinline__ V<N> vaxpy(float c, const V<N>& a, const V<N>& b) {  // c*a + b
+  V<N> r;
+  const f2 cc = bc(c);
+  FX_FOR(N) r.v[p] = fma2(cc, a.v[p], b.v[p]);
+  return r;
+}
+template <int N> __device__ __forceinline__ V<N> vfma(const V<N>& a, const V<N>& b, const V<N>& c) {  // a*b + c
+  V<N> r;
+  FX_FOR(N) r.v[p] = fma2(a.v[p], b.v[p], c.v[p]);
+  return r;
+}
+// f = A - D*x = G + ND*x  (ND holds MINUS the degradation sigmoid)
+template <int N> __device__ __forceinline__ V<N> rhs(const V<N>& G, const V<N>& ND, const V<N>& x) {
+  return vfma<N>(ND, x, G);
+}
+
+// S floats at p (row of sol / grad_sol / y0) -> pairs; the padding half of an odd S is zero
+template <int S> __device__ __forceinline__ V<(S + 1) / 2> vload(const float* p) {
+  V<(S + 1) / 2> r;
+#pragma unroll
+  for (int q = 0; q < (S + 1) / 2; ++q) r.v[q] = pk(__ldg(p + 2 * q), (2 * q + 1 < S) ? __ldg(p + 2 * q + 1) : 0.0f);
+  return r;
+}
+template <int S> __device__ __forceinline__ V<(S + 1) / 2> vload_early(const float* p) {
+  V<(S + 1) / 2> r;
+#pragma unroll
+  for (int q = 0; q < (S + 1) / 2; ++q) r.v[q] = pk(ld_early(p + 2 * q), (2 * q + 1 < S) ? ld_early(p + 2 * q + 1) : 0.0f);
+  return r;
+}
+template <int S> __device__ __forceinline__ void vstore(float* p, bool ok, const V<(S + 1) / 2>& a) {
+  if (!ok) return;
+#pragma unroll
+  for (int q = 0; q < (S + 1) / 2; ++q) {
+    float lo, hi;
+    unpk(a.v[q], lo, hi);
+    p[2 * q] = lo;
+    if (2 * q + 1 < S) p[2 * q + 1] = hi;
+  }
+}
+template <int S> __device__ __forceinline__ void vprefetch(const float* p) {
+  prefetch_l1(p);
+  prefetch_l1(p + S - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compile-time shape parameters
+// ---------------------------------------------------------------------------------------------
+template <int H, int S>
+struct Shape {
+  static constexpr int NP = (S + 1) / 2;               // state pairs
+  static constexpr int NQ = 2 * NP;                    // head pairs: growth pairs [0,NP), degradation pairs [NP,NQ)
+  static constexpr int UNIT = (2 * NQ + 2 + 3) / 4 * 4;  // floats per unit record: NQ pairs, w1t, -1/w1t, padding
+  static constexpr int BIAS = (2 * NQ + 3) / 4 * 4;
+  static constexpr int WT = BIAS + H * UNIT;           // floats of the staged weight table
+  static constexpr int IB = H <= 32 ? 5 : (H <= 64 ? 6 : (H <= 128 ? 7 : (H <= 256 ? 8 : 9)));  // unit-index bits of a key
+  static constexpr uint32_t IMASK = (1u << IB) - 1u;
+  static constexpr bool BIG = H > 64;                  // per-trajectory tables in global memory, rolled unit loops
+  static constexpr int N2 = H <= 32 ? 32 : 64;         // register sorting network size (!BIG)
+  static constexpr int NWR = BIG ? 1 : (H + 31) / 32;  // gate words kept in registers (!BIG)
+  static constexpr int JC = H <= 32 ? H : 32;          // unit chunk of the small-net prologue / epilogue
+  static constexpr int JS = (JC % 2) ? JC : JC + 1;    // odd row stride of the warp's transposition buffer
+  static constexpr int HP = (H + 1 > JS) ? H + 1 : JS; // rows of the key table (>= H + 1 keys, >= the buffer it doubles as)
+  static constexpr int HQ = (H + 3) / 4 * 4;           // padded row length of the staged small-net weights
+  static_assert(H <= 512, "key layout holds 9 index bits");
+  static_assert(H <= 32 || H % 32 == 0, "hidden widths above 32 must be multiples of 32");
+};
+
+constexpr uint32_t kNever = 0x7f800000u;  // +inf: a key that is never due
+
+// Stage the dynamics weights from the torch tensors into the block's table (see Shape):
+//   [ bias pairs (NQ) | H unit records ],  record j = [ NQ head-weight pairs | w1t_j | -1/w1t_j | pad ]
+// biases and head weights pre-scaled by -log2(e) so that sigmoid(u) = rcp(1 + ex2(v)).
+template <int H, int S>
+__device__ __forceinline__ void stage_weights(float* __restrict__ wt, const float* __restrict__ w1t, int w1t_stride,
+                                              const float* __restrict__ Wg, const float* __restrict__ bg,
+                                              const float* __restrict__ Wd, const float* __restrict__ bd) {
+  using SH = Shape<H, S>;
+  for (int i = threadIdx.x; i < SH::WT; i += kThreads) {
+    float v = 0.0f;
+    const bool bias = i < SH::BIAS;
+    const int j = bias ? 0 : (i - SH::BIAS) / SH::UNIT;
+    const int r = bias ? i : (i - SH::BIAS) % SH::UNIT;
+    if (r < 2 * SH::NQ) {
+      const int q = r >> 1, h = r & 1;
+      const bool growth = q < SH::NP;
+      const int s = 2 * (growth ? q : q - SH::NP) + h;
+      if (s < S) {
+        if (bias) v = kNegLog2e * (growth ? bg[s] : bd[s]);
+        else v = kNegLog2e * (growth ? Wg[s * H + j] : Wd[s * H + j]);
+      }
+    } else if (!bias && r == 2 * SH::NQ) {
+      v = w1t[(size_t)j * w1t_stride];
+    } else if (!bias && r == 2 * SH::NQ + 1) {
+      const float w = w1t[(size_t)j * w1t_stride];
+      v = (w == 0.0f) ? 0.0f : -1.0f / w;
+    }
+    wt[i] = v;
+  }
+}
+
+// per-trajectory tables of the thread: c_j and the sorted crossing keys.  Shared memory, warp-major
+// ([warp][row][32 lanes]: conflict-free for any row index) -- or, for wide hidden layers, global scratch
+// ([row][all resident threads]: coalesced).
+struct Tab {
+  float* c;       // element j at c[j * stride]
+  uint32_t* k;    // key p at k[p * stride]
+  uint8_t* fs;    // BIG only: per-unit status bytes (bit0: gate at the first evaluation, bit1: flipped)
+  int stride;
+};
+
+// ---------------------------------------------------------------------------------------------
+// piecewise-linear evaluator of one trajectory
+// ---------------------------------------------------------------------------------------------
+template <int H, int S>
+struct Pl {
+  using SH = Shape<H, S>;
+  static constexpr int NP = SH::NP, NQ = SH::NQ;
+  f2 al[NQ], be[NQ];
+  float nk;       // next pending key (as float: keys are non-negative floats with the unit index in the low bits)
+  int pos;        // its position in the sorted table
+  float t_start, dirsign;
+
+  __device__ __forceinline__ static f2 wpair(const float* rec, int q) { return reinterpret_cast<const f2*>(rec)[q]; }
+
+  // one unit at the first evaluation time: dense contribution to (alpha, beta), its key, its gate
+  __device__ __forceinline__ uint32_t init_unit(const float* __restrict__ rec, int j, float c, float ts, bool& on) {
+    const float w1 = rec[2 * NQ], rinv = rec[2 * NQ + 1];
+    on = (__float_as_uint(fmaf(w1, ts, c)) >> 31) == 0u;  // the gate test of the dense evaluation
+    const float u = on ? w1 : 0.0f, v = on ? c : 0.0f;
+    const f2 uu = bc(u), vv = bc(v);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const f2 w = wpair(rec, q);
+      al[q] = fma2(w, uu, al[q]);
+      be[q] = fma2(w, vv, be[q]);
+    }
+    // p_j(t) = w1t_j t + c_j is monotone in t (also in fp32: fma is correctly rounded), so a unit changes state at
+    // most once along the sweep, and only if it is not already in the state it has beyond its crossing.
+    const bool post = dirsign * w1 > 0.0f;
+    const float tx = c * rinv;                               // crossing time -c_j / w1t_j
+    const float slack = 4e-7f * (fabsf(tx) + fabsf(ts));
+    const float uq = dirsign * (tx - ts);                    // sweep coordinate of the crossing
+    const float ub = fmaxf(fmaf(uq, 0.99998474f, -slack), 0.0f);  // biased early: a key is never late
+    const bool pending = (rinv != 0.0f) && (on != post) && (ub < 3.0e38f);
+    return pending ? ((__float_as_uint(ub) & ~SH::IMASK) | (uint32_t)j) : kNever;
+  }
+
+  // first evaluation of the trajectory at time ts; first[] receives the gate pattern (bit j of word j/32)
+  __device__ __forceinline__ void init(const float* __restrict__ wt, const Tab& tab, float ts, float dir,
+                                       uint32_t (&first)[SH::NWR]) {
+    t_start = ts;
+    dirsign = dir;
+    const f2* bp = reinterpret_cast<const f2*>(wt);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      al[q] = 0ull;
+      be[q] = bp[q];
+    }
+    const float* recs = wt + SH::BIAS;
+    if constexpr (!SH::BIG) {
+      uint32_t k[SH::N2];
+#pragma unroll
+      for (int w = 0; w < SH::NWR; ++w) first[w] = 0u;
+#pragma unroll
+      for (int j = 0; j < SH::N2; ++j) {
+        k[j] = kNever;
+        if (j < H) {
+          bool on;
+          k[j] = init_unit(recs + j * SH::UNIT, j, tab.c[j * tab.stride], ts, on);
+          first[j >> 5] |= on ? (1u << (j & 31)) : 0u;
+        }
+      }
+      // bitonic sorting network in registers
+#pragma unroll
+      for (int size = 2; size <= SH::N2; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+          for (int i = 0; i < SH::N2; ++i) {
+            const int l = i ^ stride;
+            if (l > i) {
+              const uint32_t a = k[i], b = k[l];
+              const bool up = (i & size) == 0;
+              k[i] = up ? min(a, b) : max(a, b);
+              k[l] = up ? max(a, b) : min(a, b);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < H; ++j) tab.k[j * tab.stride] = k[j];
+      tab.k[H * tab.stride] = kNever;
+      nk = __uint_as_float(k[0]);
+    } else {
+      first[0] = 0u;
+      constexpr int NS = H <= 128 ? 128 : (H <= 256 ? 256 : 512);  // power of two >= H
+#pragma unroll 2
+      for (int j = 0; j < H; ++j) {
+        bool on;
+        const uint32_t key = init_unit(recs + j * SH::UNIT, j, tab.c[(size_t)j * tab.stride], ts, on);
+        tab.k[(size_t)j * tab.stride] = key;
+        tab.fs[(size_t)j * tab.stride] = on ? 1 : 0;
+      }
+      for (int j = H; j <= NS; ++j) tab.k[(size_t)j * tab.stride] = kNever;  // padding + the end sentinel
+      // bitonic sort of the thread's own column of the global key table (the table holds NS + 1 rows)
+      for (int size = 2; size <= NS; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll 4
+          for (int m = 0; m < NS / 2; ++m) {
+            const int i = ((m & ~(stride - 1)) << 1) | (m & (stride - 1));  // index with bit `stride` clear
+            const int l = i | stride;
+            uint32_t* pa = tab.k + (size_t)i * tab.stride;
+            uint32_t* pb = tab.k + (size_t)l * tab.stride;
+            const uint32_t a = *pa, b = *pb;
+            const bool up = (i & size) == 0;
+            *pa = up ? min(a, b) : max(a, b);
+            *pb = up ? max(a, b) : min(a, b);
+          }
+        }
+      }
+      nk = __uint_as_float(tab.k[0]);
+    }
+    pos = 0;
+  }
+
+  // move (alpha, beta) to evaluation time te: every pending crossing whose key is due is confirmed with the exact
+  // gate test of the dense evaluation and applied as one rank-one update.  Divergent but short: a unit flips at
+  // most once per trajectory and sweep.
+  __device__ __forceinline__ void seek(const float* __restrict__ wt, const Tab& tab, float te) {
+    const float uq = dirsign * (te - t_start);
+    while (uq >= nk) {
+      const int j = (int)(__float_as_uint(nk) & SH::IMASK);
+      const float* rec = wt + SH::BIAS + j * SH::UNIT;
+      const float w1 = rec[2 * NQ];
+      const float c = tab.c[(size_t)j * tab.stride];
+      const bool post = dirsign * w1 > 0.0f;
+      const bool now = (__float_as_uint(fmaf(w1, te, c)) >> 31) == 0u;
+      if (now != post) break;  // not across yet at te (the key is early by construction): stays pending
+      const float sgn = post ? 1.0f : -1.0f;
+      const f2 uu = bc(sgn * w1), vv = bc(sgn * c);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const f2 w = wpair(rec, q);
+        al[q] = fma2(w, uu, al[q]);
+        be[q] = fma2(w, vv, be[q]);
+      }
+      ++pos;
+      nk = __uint_as_float(tab.k[(size_t)pos * tab.stride]);
+    }
+  }
+
+  // G = sigmoid(growth heads), ND = -sigmoid(degradation heads) at time te.  The XU pipe (16 MUFU lanes per SM)
+  // bounds the forward kernel, so the two reciprocals of a register pair share one MUFU.RCP:
+  //   1/a = b * rcp(ab), 1/b = a * rcp(ab);  the exponentials are written into swapped halves so that the final
+  //   packed multiply lands each quotient in its own half.  Exponents are clamped at 2^60 so ab stays finite
+  //   (sigmoid floor 1e-18); the clamp propagates NaN.
+  __device__ __forceinline__ void eval(float te, V<NP>& G, V<NP>& ND) const {
+    const f2 tt = bc(te);
+    const f2 one = bc(1.0f), minus_one = bc(-1.0f);
+    float tail_g = 0.0f, tail_d = 0.0f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const bool growth = q < NP;
+      const int p = growth ? q : q - NP;
+      float v0, v1;
+      unpk(fma2(al[q], tt, be[q]), v0, v1);
+      const float e0 = ex2_approx(min_nan(v0, 60.0f));
+      if (2 * p + 1 < S) {
+        const float e1 = ex2_approx(min_nan(v1, 60.0f));
+        const f2 esw = pk(e1, e0);
+        const f2 dsw = growth ? add2(esw, one) : sub2(minus_one, esw);
+        float d0, d1;
+        unpk(dsw, d0, d1);
+        const f2 r = bc(rcp_approx(d0 * d1));
+        if (growth) G.v[p] = mul2(dsw, r); else ND.v[p] = mul2(dsw, r);
+      } else {
+        if (growth) tail_g = 1.0f + e0; else tail_d = -1.0f - e0;
+      }
+    }
+    if constexpr ((S & 1) != 0) {
+      const float r = rcp_approx(tail_g * tail_d);
+      G.v[NP - 1] = pk(tail_d * r, 0.0f);
+      ND.v[NP - 1] = pk(tail_g * r, 0.0f);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions (as in round 1): sum K values over the 32 lanes with ~K shuffles
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ float warp_sum_scatter(float (&v)[K], int lane, int& slot) {
+  int base = 0;
+  int n = K;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    if (n > 1) {
+      const int hn = n / 2;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int k = 0; k < K / 2; ++k) {
+        if (k < hn) {
+          const float mine = upper ? v[k + hn] : v[k];
+          const float give = upper ? v[k] : v[k + hn];
+          v[k] = mine + __shfl_xor_sync(0xffffffffu, give, off);
+        }
+      }
+      if (upper) base += hn;
+      n = hn;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+  slot = base;
+  return v[0];
+}
+template <int K, class Dst>
+__device__ __forceinline__ void warp_reduce_to(float (&v)[K], int lane, Dst dst) {
+  int slot;
+  const float tot = warp_sum_scatter<K>(v, lane, slot);
+  if ((lane & (32 / K - 1)) == 0) {
+    float* p = dst(slot);
+    if (p) atomicAdd(p, tot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the two small nets in front of the solve, weights staged in shared memory:
+//   Wz [L][HQ] = W1[:,1:]^T,  Wa [L][HQ] = latent_to_ode_net[0].weight^T,  b1 [HQ], ba [HQ],  Wb [S][HQ], bb [S]
+// ---------------------------------------------------------------------------------------------
+template <int H, int S>
+struct LatSmem {
+  float *Wz, *Wa, *b1, *ba, *Wb, *bb;
+  static constexpr int HQ = Shape<H, S>::HQ;
+  __host__ __device__ static int floats(int L) { return 2 * L * HQ + 2 * HQ + S * HQ + (S + 3) / 4 * 4; }
+  __device__ __forceinline__ void stage(float* base, const LatentSrc& lat) {  // caller syncs afterwards
+    const int L = lat.L;
+    Wz = base;
+    Wa = Wz + L * HQ;
+    b1 = Wa + L * HQ;
+    ba = b1 + HQ;
+    Wb = ba + HQ;
+    bb = Wb + S * HQ;
+    const bool fx0 = lat.Wa != nullptr;
+    for (int i = threadIdx.x; i < L * HQ; i += kThreads) {
+      const int l = i / HQ, j = i % HQ;
+      Wz[i] = j < H ? lat.W1[j * (L + 1) + 1 + l] : 0.0f;
+      Wa[i] = (fx0 && j < H) ? lat.Wa[j * L + l] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < HQ; i += kThreads) {
+      b1[i] = i < H ? lat.b1[i] : 0.0f;
+      ba[i] = (fx0 && i < H) ? lat.ba[i] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < S * HQ; i += kThreads) {
+      const int s = i / HQ, j = i % HQ;
+      Wb[i] = (fx0 && j < H) ? lat.Wb[s * H + j] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < S; i += kThreads) bb[i] = fx0 ? lat.bb[i] : 0.0f;
+  }
+};
+
+// acc[j0 .. j0+JC) = bias + sum_l W[l][j] z_l  for one chunk of units (z row read through L1: 60-200 bytes, hit
+// after the first chunk)
+template <int JC>
+__device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const float* __restrict__ bias, int HQ, int j0,
+                                          const float* __restrict__ zrow, int L, float (&acc)[JC]) {
+#pragma unroll
+  for (int j = 0; j < JC; ++j) acc[j] = bias[j0 + j];
+  float znext = L > 0 ? __ldg(zrow) : 0.0f;
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const float zl = znext;
+    if (l + 1 < L) znext = ld_early(zrow + l + 1);
+    const float* w = W + l * HQ + j0;
+#pragma unroll
+    for (int j = 0; j < JC; ++j) acc[j] = fmaf(w[j], zl, acc[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+constexpr int kStageT = 4;  // output times staged per trajectory for (B,T,S)-contiguous storage
+
+template <int H, int S>
+__host__ __device__ constexpr size_t fwd_smem_bytes(int L, bool lat, bool rows_in_time) {
+  using SH = Shape<H, S>;
+  size_t n = SH::WT;
+  if (!SH::BIG) n += (size_t)kThreads * H + (size_t)kThreads * SH::HP;
+  if (lat) n += LatSmem<H, S>::floats(L);
+  if (rows_in_time) n += (size_t)kThreads * kStageT * S;
+  return n * sizeof(float);
+}
+
+// bytes of global scratch per resident thread (wide hidden layers only)
+template <int H, int S>
+__host__ __device__ constexpr size_t big_tab_bytes() {
+  constexpr int NS = H <= 128 ? 128 : (H <= 256 ? 256 : 512);
+  return Shape<H, S>::BIG ? (size_t)H * 4 + (size_t)(NS + 1) * 4 + (size_t)H : 0;
+}
+
+template <int H, int S>
+__device__ __forceinline__ Tab make_tab(float* smem_tables, unsigned char* ws, int warp, int lane) {
+  using SH = Shape<H, S>;
+  Tab tab;
+  if constexpr (!SH::BIG) {
+    tab.c = smem_tables + (size_t)warp * H * 32 + lane;
+    tab.k = reinterpret_cast<uint32_t*>(smem_tables + (size_t)kThreads * H) + (size_t)warp * SH::HP * 32 + lane;
+    tab.fs = nullptr;
+    tab.stride = 32;
+  } else {
+    constexpr int NS = H <= 128 ? 128 : (H <= 256 ? 256 : 512);
+    const size_t nt = (size_t)gridDim.x * kThreads, gt = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    tab.c = reinterpret_cast<float*>(ws) + gt;
+    tab.k = reinterpret_cast<uint32_t*>(ws + nt * H * 4) + gt;
+    tab.fs = ws + nt * H * 4 + nt * (NS + 1) * 4 + gt;
+    tab.stride = (int)nt;
+  }
+  return tab;
+}
+
+// c_j into the thread's table (from z through the staged W1[:,1:], or from the given (B,H) array); returns x0
+template <int H, int S, bool WANT_X0>
+__device__ __forceinline__ void prologue(const LatSmem<H, S>& ls, const LatentSrc& lat, const float* __restrict__ cin,
+                                         int64_t b, const Tab& tab, V<(S + 1) / 2>& x0) {
+  using SH = Shape<H, S>;
+  constexpr int JC = SH::JC;
+  if (lat.z) {
+    const float* zrow = lat.z + b * lat.L;
+    float xa[S];
+    if (WANT_X0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) xa[s] = ls.bb[s];
+    }
+#pragma unroll 1
+    for (int j0 = 0; j0 < H; j0 += JC) {
+      float acc[JC];
+      lat_chunk<JC>(ls.Wz, ls.b1, SH::HQ, j0, zrow, lat.L, acc);
+#pragma unroll
+      for (int j = 0; j < JC; ++j) tab.c[(size_t)(j0 + j) * tab.stride] = acc[j];
+      if (WANT_X0) {
+        lat_chunk<JC>(ls.Wa, ls.ba, SH::HQ, j0, zrow, lat.L, acc);
+#pragma unroll
+        for (int j = 0; j < JC; ++j) {
+          const float h = relu_nan(acc[j]);
+#pragma unroll
+          for (int s = 0; s < S; ++s) xa[s] = fmaf(ls.Wb[s * SH::HQ + j0 + j], h, xa[s]);
+        }
+      }
+    }
+    if (WANT_X0) {
+#pragma unroll
+      for (int p = 0; p < SH::NP; ++p) {
+        const float a = sigmoid_from_scaled(kNegLog2e * xa[2 * p]);
+        const float bq = (2 * p + 1 < S) ? sigmoid_from_scaled(kNegLog2e * xa[(2 * p + 1 < S) ? 2 * p + 1 : 0]) : 0.0f;
+        x0.v[p] = pk(a, bq);
+      }
+    }
+  } else {
+    const float* crow = cin + b * H;
+#pragma unroll 4
+    for (int j = 0; j < H; ++j) tab.c[(size_t)j * tab.stride] = ld_stream(crow + j);
+  }
+}
+
+template <int H, int S, int METHOD>
+__global__ void __launch_bounds__(kThreads, (Shape<H, S>::BIG || S > 5) ? 3 : SLODE_FX_FWD_MINB)
+fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
+                 const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, PackSrc w,
+                 int w1t_stride, LatentSrc lat, unsigned char* __restrict__ ws) {
+  using SH = Shape<H, S>;
+  constexpr int NP = SH::NP;
+  extern __shared__ __align__(16) float fx_smem[];
+  float* const wt = fx_smem;
+  float* const tables = wt + SH::WT;
+  float* lat_base = tables + (SH::BIG ? 0 : kThreads * H + kThreads * SH::HP);
+  const bool rows_in_time = (st == S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  LatSmem<H, S> ls{};
+  stage_weights<H, S>(wt, w.w1t, w1t_stride, w.Wg, w.bg, w.Wd, w.bd);
+  if (lat.z) ls.stage(lat_base, lat);
+  float* const ostage = lat_base + (lat.z ? LatSmem<H, S>::floats(lat.L) : 0) + (size_t)tid * kStageT * S;
+  __syncthreads();
+  const Tab tab = make_tab<H, S>(tables, ws, warp, lane);
+  const float dir = (T < 2 || __ldg(tgrid + T - 1) >= __ldg(tgrid)) ? 1.0f : -1.0f;
+  const int64_t ntiles = (B + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t br = tile * kThreads + tid;
+    const bool ok = br < B;
+    const int64_t b = ok ? br : B - 1;  // tail threads redo trajectory B-1 with their stores masked off
+    V<NP> x;
+    if (lat.z && lat.Wa) {
+      prologue<H, S, true>(ls, lat, cin, b, tab, x);
+    } else {
+      prologue<H, S, false>(ls, lat, cin, b, tab, x);
+      x = vload<S>(y0 + b * S);
+    }
+    float* out = sol + b * sb;
+    float* const row = out;
+
+    auto put = [&](int k, const V<NP>& xv) {
+      if (!rows_in_time) {
+        vstore<S>(out, ok, xv);
+        return;
+      }
+      // (B,T,S)-contiguous storage: a trajectory's rows are contiguous in time -> stage kStageT of them and write
+      // one run of kStageT*S floats with 16-byte stores
+      const int slot = k & (kStageT - 1);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        float lo, hi;
+        unpk(xv.v[p], lo, hi);
+        ostage[slot * S + 2 * p] = lo;
+        if (2 * p + 1 < S) ostage[slot * S + 2 * p + 1] = hi;
+      }
+      if ((slot == kStageT - 1 || k == T - 1) && ok) {
+        const int n = (slot + 1) * S;
+        float* dst = row + (int64_t)(k - slot) * S;
+        if (n == kStageT * S && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (kStageT * S) % 4 == 0) {
+#pragma unroll
+          for (int q = 0; q < kStageT * S / 4; ++q)
+            reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(ostage)[q];
+        } else {
+          for (int q = 0; q < n; ++q) dst[q] = ostage[q];
+        }
+      }
+    };
+
+    put(0, x);
+    float t0 = __ldg(tgrid);
+    Pl<H, S> pl;
+    uint32_t first[SH::NWR];
+    if (T > 1) pl.init(wt, tab, t0, dir, first);
+    V<NP> k1;
+    if (METHOD == SLODE_METHOD_RK4 && T > 1) {  // k1 of the first step; afterwards carried over from the step before
+      V<NP> G, D;
+      pl.eval(t0, G, D);
+      k1 = rhs<NP>(G, D, x);
+    }
+    float t_ahead = T > 1 ? __ldg(tgrid + 1) : t0;  // the grid is read one step ahead of its use
+#pragma unroll 1
+    for (int i = 0; i + 1 < T; ++i) {
+      const float t1 = t_ahead;
+      if (i + 2 < T) t_ahead = ld_early(tgrid + i + 2);
+      const float dt = t1 - t0;
+      if (METHOD == SLODE_METHOD_EULER) {
+        V<NP> G, D;
+        pl.seek(wt, tab, t0);
+        pl.eval(t0, G, D);
+        x = vaxpy<NP>(dt, rhs<NP>(G, D, x), x);
+      } else if (METHOD == SLODE_METHOD_MIDPOINT) {
+        const float half_dt = 0.5f * dt;
+        V<NP> G, D;
+        pl.seek(wt, tab, t0);
+        pl.eval(t0, G, D);
+        const V<NP> ym = vaxpy<NP>(half_dt, rhs<NP>(G, D, x), x);
+        const float tm = t0 + half_dt;
+        pl.seek(wt, tab, tm);
+        pl.eval(tm, G, D);
+        x = vaxpy<NP>(dt, rhs<NP>(G, D, ym), x);
+      } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func); the evaluation at t1 is the next step's k1
+        V<NP> G, D;
+        const float ta = t0 + dt * kOneThird, tb = t0 + dt * kTwoThirds;
+        V<NP> y = vaxpy<NP>(dt * kOneThird, k1, x);
+        pl.seek(wt, tab, ta);
+        pl.eval(ta, G, D);
+        const V<NP> k2 = rhs<NP>(G, D, y);
+        y = vaxpy<NP>(dt, vaxpy<NP>(-kOneThird, k1, k2), x);
+        pl.seek(wt, tab, tb);
+        pl.eval(tb, G, D);
+        const V<NP> k3 = rhs<NP>(G, D, y);
+        y = vaxpy<NP>(dt, vadd<NP>(vsub<NP>(k1, k2), k3), x);
+        pl.seek(wt, tab, t1);
+        pl.eval(t1, G, D);
+        const V<NP> k4 = rhs<NP>(G, D, y);
+        x = vaxpy<NP>(dt * 0.125f, vadd<NP>(vaxpy<NP>(3.0f, vadd<NP>(k2, k3), k1), k4), x);
+        k1 = rhs<NP>(G, D, x);
+      }
+      out += st;
+      put(i + 1, x);
+      t0 = t1;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// Flat layout of the block's gradient accumulators == layout of grad_params (slode_b200.h):
+//   [ dw1t (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) | dW1z (H*L) | db1 (H) | dWa (H*L) | dba (H) | dWb (S*H) | dbb (S) ]
+template <int H, int S>
+struct GradLayout {
+  static constexpr int w1t = 0, Wg = H, bg = H + S * H, Wd = H + S * H + S, bd = H + 2 * S * H + S;
+  static constexpr int base = H + 2 * (S * H + S);
+  __host__ __device__ static int W1z(int) { return base; }
+  __host__ __device__ static int b1(int L) { return base + H * L; }
+  __host__ __device__ static int Wa(int L) { return base + H * L + H; }
+  __host__ __device__ static int ba(int L) { return base + 2 * H * L + H; }
+  __host__ __device__ static int Wb(int L) { return base + 2 * H * L + 2 * H; }
+  __host__ __device__ static int bb(int L) { return base + 2 * H * L + 2 * H + S * H; }
+  __host__ __device__ static int total(int L, bool lat, bool fx0) {
+    return base + (lat ? H * L + H : 0) + (fx0 ? H * L + H + S * H + S : 0);
+  }
+};
+
+// flip records: per resident thread and hidden unit one snapshot of (P, Q) = 2 * NQ register pairs, stored
+// [thread][unit][P pairs | Q pairs]: a record is one contiguous run written with immediate offsets from a single
+// address (the write sits in a divergent trip that usually serves one lane); the end-of-sweep pass reads a unit's
+// records of all lanes through L1
+template <int H, int S>
+__host__ __device__ constexpr size_t rec_bytes_per_thread() {
+  return (size_t)H * Shape<H, S>::NQ * 16;
+}
+
+template <int H, int S>
+struct Sweep {
+  using SH = Shape<H, S>;
+  static constexpr int NP = SH::NP, NQ = SH::NQ;
+  f2 P[NQ], Q[NQ];
+  uint32_t flipped[SH::NWR];
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) P[q] = Q[q] = 0ull;
+#pragma unroll
+    for (int w = 0; w < SH::NWR; ++w) flipped[w] = 0u;
+  }
+
+  // the units whose keys sit at positions [p0, p1) of the sorted table flipped between the previous contributing
+  // evaluation and the next one: snapshot the prefix sums as they stand into each unit's record
+  __device__ __forceinline__ void events(f2* __restrict__ rec, const Tab& tab, int p0, int p1) {
+    for (int p = p0; p < p1; ++p) {
+      const int j = (int)(tab.k[(size_t)p * tab.stride] & SH::IMASK);
+      f2* dst = rec + j * (2 * NQ);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        dst[q] = P[q];
+        dst[NQ + q] = Q[q];
+      }
+      if constexpr (SH::BIG) {
+        tab.fs[(size_t)j * tab.stride] |= 2;
+      } else {
+#pragma unroll
+        for (int w = 0; w < SH::NWR; ++w) {
+          if (w == (j >> 5)) flipped[w] |= 1u << (j & 31);
+        }
+      }
+    }
+  }
+
+  // add the cotangents of the head pre-activations of one evaluation at time te:
+  //   f = G + ND*y with upstream gf:  d(pre_G) = gf*G(1-G),  d(pre_D) = gf*y*(ND^2 + ND)   (ND = -D)
+  __device__ __forceinline__ void add(float te, const V<NP>& gf, const V<NP>& y, const V<NP>& G, const V<NP>& ND) {
+    const f2 tt = bc(te);
+    const f2 one = bc(1.0f), minus_one = bc(-1.0f);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const f2 dg = mul2(gf.v[p], mul2(G.v[p], fma2(G.v[p], minus_one, one)));
+      const f2 dd = mul2(mul2(gf.v[p], y.v[p]), fma2(ND.v[p], ND.v[p], ND.v[p]));
+      P[p] = add2(P[p], dg);
+      Q[p] = fma2(dg, tt, Q[p]);
+      P[NP + p] = add2(P[NP + p], dd);
+      Q[NP + p] = fma2(dd, tt, Q[NP + p]);
+    }
+  }
+};
+
+template <int H, int S>
+__host__ __device__ constexpr size_t bwd_smem_bytes(int L, bool lat) {
+  using SH = Shape<H, S>;
+  size_t n = SH::WT;
+  if (!SH::BIG) n += (size_t)kThreads * H + (size_t)kThreads * SH::HP;
+  else n += (size_t)kThreads * SH::JS;               // the warps' transposition buffers
+  n += (size_t)(GradLayout<H, S>::total(L, lat, lat) + 3) / 4 * 4;  // block accumulators
+  if (lat) n += LatSmem<H, S>::floats(L) + (size_t)kThreads * ((L + 3) / 4 * 4);  // staged nets + the warps' z rows
+  return n * sizeof(float);
+}
+
+template <int H, int S, int METHOD, int MODE>
+__global__ void __launch_bounds__(kThreads, (Shape<H, S>::BIG || S > 5) ? 2 : SLODE_FX_BWD_MINB)
+fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
+                 const float* __restrict__ sol, int64_t st, int64_t sb, const float* __restrict__ gsol, int64_t gst,
+                 int64_t gsb, float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,
+                 PackSrc w, int w1t_stride, LatentSrc lat, float* __restrict__ grad_z,
+                 unsigned char* __restrict__ ws) {
+  using SH = Shape<H, S>;
+  using GL = GradLayout<H, S>;
+  constexpr int NP = SH::NP, NQ = SH::NQ;
+  extern __shared__ __align__(16) float fx_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = lat.L;
+  const bool fused = lat.z != nullptr, fx0 = fused && lat.Wa != nullptr;
+  float* const wt = fx_smem;
+  float* const tables = wt + SH::WT;
+  float* p_ = tables + (SH::BIG ? kThreads * SH::JS : kThreads * H + kThreads * SH::HP);
+  float* const acc = p_;
+  const int n_acc = GL::total(L, fused, fx0);
+  p_ += (GL::total(L, fused, fused) + 3) / 4 * 4;  // keeps the float4 rows behind it 16-byte aligned
+  LatSmem<H, S> ls{};
+  float* zT = nullptr;  // this warp's z rows, [32][LQ]
+  const int LQ = (L + 3) / 4 * 4;
+  if (fused) {
+    ls.stage(p_, lat);
+    zT = p_ + LatSmem<H, S>::floats(L) + (size_t)warp * 32 * LQ;
+  }
+  stage_weights<H, S>(wt, w.w1t, w1t_stride, w.Wg, w.bg, w.Wd, w.bd);
+  for (int i = tid; i < n_acc; i += kThreads) acc[i] = 0.0f;
+  __syncthreads();
+  const size_t nthreads = (size_t)gridDim.x * kThreads, gthread = (size_t)blockIdx.x * kThreads + tid;
+  const Tab tab = make_tab<H, S>(tables, ws, warp, lane);
+  f2* const rec = reinterpret_cast<f2*>(ws + big_tab_bytes<H, S>() * nthreads) + gthread * (size_t)(H * 2 * NQ);
+  // the warp's transposition buffer [32][JS]: the key table's rows once the walk is over (narrow layers), else
+  // its own region
+  float* const dcT = SH::BIG ? tables + (size_t)warp * 32 * SH::JS
+                             : tables + (size_t)kThreads * H + (size_t)warp * SH::HP * 32;
+  // the reverse sweep visits the grid from its last time to its first
+  const float dir = (T < 2 || __ldg(tgrid + T - 1) >= __ldg(tgrid)) ? -1.0f : 1.0f;
+  const int64_t ntiles = (B + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t br = tile * kThreads + tid;
+    const bool ok = br < B;
+    const int64_t b = ok ? br : B - 1;
+    {
+      V<NP> dummy;
+      prologue<H, S, false>(ls, lat, cin, b, tab, dummy);
+    }
+    const float* xs = sol + b * sb;
+    const float* gs = gsol + b * gsb;
+    const float live = ok ? 1.0f : 0.0f;   // a masked-off thread carries zero cotangents: it only adds zeros
+    V<NP> lam = vscale<NP>(vload<S>(gs + (int64_t)(T - 1) * gst), live);
+
+    Sweep<H, S> sw;
+    sw.init();
+    Pl<H, S> pl;
+    uint32_t first[SH::NWR];
+#pragma unroll
+    for (int ww = 0; ww < SH::NWR; ++ww) first[ww] = 0u;
+    float t1 = __ldg(tgrid + T - 1);
+    V<NP> Gc, Dc;  // rk4: the evaluation at t1, carried over from the interval processed before
+    int pdone = 0;  // keys [0, pdone) have had their records written
+    if (T > 1) {
+      // first evaluation time of the sweep
+      float tfirst = t1;
+      if (MODE == SLODE_BWD_DISCRETE) {
+        const float tp = __ldg(tgrid + T - 2);
+        if (METHOD == SLODE_METHOD_EULER) tfirst = tp;
+        if (METHOD == SLODE_METHOD_MIDPOINT) tfirst = tp + 0.5f * (t1 - tp);
+      }
+      pl.init(wt, tab, tfirst, dir, first);
+      if (METHOD == SLODE_METHOD_RK4) pl.eval(t1, Gc, Dc);
+    }
+
+    float t_ahead = T > 1 ? __ldg(tgrid + T - 2) : t1;  // the grid is read one interval ahead of its use
+#pragma unroll 1
+    for (int i = T - 2; i >= 0; --i) {
+      const float t0 = t_ahead;
+      if (i > 0) t_ahead = ld_early(tgrid + i - 1);
+      // state and cotangent rows of grid point i were pulled into L1 one interval ago; they are loaded where they
+      // are used (forcing the loads up here made the evaluator's first shared-memory wait also wait for them:
+      // loads issued together share a scoreboard)
+      const V<NP> x = vload<S>(xs + (int64_t)i * st);
+      if (i > 0) {  // next interval's state and cotangent rows: in L1 by the time they are read
+        vprefetch<S>(xs + (int64_t)(i - 1) * st);
+        vprefetch<S>(gs + (int64_t)(i - 1) * gst);
+      }
+      if (MODE == SLODE_BWD_DISCRETE) {
+        const float dt = t1 - t0;
+        if (METHOD == SLODE_METHOD_EULER) {
+          V<NP> G, D;
+          pl.seek(wt, tab, t0);
+          pl.eval(t0, G, D);
+          const V<NP> gk = vscale<NP>(lam, dt);
+          sw.events(rec, tab, pdone, pl.pos);
+          pdone = pl.pos;
+          sw.add(t0, gk, x, G, D);
+          lam = vfma<NP>(gk, D, lam);
+        } else if (METHOD == SLODE_METHOD_MIDPOINT) {
+          const float half_dt = 0.5f * dt;
+          const float tm = t0 + half_dt;
+          V<NP> G1, D1, G0, D0;
+          pl.seek(wt, tab, tm);
+          const int pm = pl.pos;
+          pl.eval(tm, G1, D1);
+          pl.seek(wt, tab, t0);
+          pl.eval(t0, G0, D0);
+          const V<NP> ym = vaxpy<NP>(half_dt, rhs<NP>(G0, D0, x), x);
+          V<NP> gk = vscale<NP>(lam, dt);  // dL/dk2
+          sw.events(rec, tab, pdone, pm);
+          sw.add(tm, gk, ym, G1, D1);
+          const V<NP> gy = vmul<NP>(gk, D1);  // dL/dy_mid (D holds -sigmoid)
+          lam = vadd<NP>(lam, gy);
+          gk = vscale<NP>(gy, half_dt);  // dL/dk1
+          sw.events(rec, tab, pm, pl.pos);
+          pdone = pl.pos;
+          sw.add(t0, gk, x, G0, D0);
+          lam = vfma<NP>(gk, D0, lam);
+        } else {  // rk4 3/8
+          const float dt3 = dt * kOneThird;
+          const float ta = t0 + dt * kOneThird, tb = t0 + dt * kTwoThirds;
+          V<NP> G2, D2, G1, D1, G0, D0;
+          pl.seek(wt, tab, tb);
+          const int pb = pl.pos;
+          pl.eval(tb, G2, D2);
+          pl.seek(wt, tab, ta);
+          const int pa = pl.pos;
+          pl.eval(ta, G1, D1);
+          pl.seek(wt, tab, t0);
+          pl.eval(t0, G0, D0);
+          V<NP> Y2, Y3, Y4;
+          {
+            const V<NP> k1 = rhs<NP>(G0, D0, x);
+            Y2 = vaxpy<NP>(dt3, k1, x);
+            const V<NP> k2 = rhs<NP>(G1, D1, Y2);
+            Y3 = vaxpy<NP>(dt, vaxpy<NP>(-kOneThird, k1, k2), x);
+            const V<NP> k3 = rhs<NP>(G2, D2, Y3);
+            Y4 = vaxpy<NP>(dt, vadd<NP>(vsub<NP>(k1, k2), k3), x);
+          }
+          const V<NP> wv = vscale<NP>(lam, 0.125f * dt);
+          // stage 4 (time t1, carried evaluation): gk4 = w
+          sw.add(t1, wv, Y4, Gc, Dc);
+          V<NP> gy = vmul<NP>(wv, Dc);
+          lam = vadd<NP>(lam, gy);
+          V<NP> gk1 = vaxpy<NP>(dt, gy, wv);
+          V<NP> gk2 = vaxpy<NP>(-dt, gy, vscale<NP>(wv, 3.0f));
+          const V<NP> gk3 = vaxpy<NP>(dt, gy, vscale<NP>(wv, 3.0f));
+          // stage 3
+          sw.events(rec, tab, pdone, pb);
+          sw.add(tb, gk3, Y3, G2, D2);
+          gy = vmul<NP>(gk3, D2);
+          lam = vadd<NP>(lam, gy);
+          gk2 = vaxpy<NP>(dt, gy, gk2);
+          gk1 = vaxpy<NP>(-dt3, gy, gk1);
+          // stage 2
+          sw.events(rec, tab, pb, pa);
+          sw.add(ta, gk2, Y2, G1, D1);
+          gy = vmul<NP>(gk2, D1);
+          lam = vadd<NP>(lam, gy);
+          gk1 = vaxpy<NP>(dt3, gy, gk1);
+          // stage 1 (time t0; its evaluation is the carried one of the next interval)
+          sw.events(rec, tab, pa, pl.pos);
+          pdone = pl.pos;
+          sw.add(t0, gk1, x, G0, D0);
+          lam = vfma<NP>(gk1, D0, lam);
+          Gc = G0;
+          Dc = D0;
+        }
+      } else {
+        // torchdiffeq.odeint_adjoint emulation: one step of the same method on the augmented system
+        // [y, a, a_theta] from t1 down to t0, y restarted from the stored sol[i+1].  In reversed time s=-t the
+        // step is ds = t1 - t0 > 0 with  Ky = D*y - A,  Ka = -a*D,  a_theta += w_m * a_m^T df/dtheta(t_m, y_m).
+        const float ds = t1 - t0;
+        const V<NP> y = vload<S>(xs + (int64_t)(i + 1) * st);
+        if (METHOD == SLODE_METHOD_EULER) {
+          V<NP> G, D;
+          pl.seek(wt, tab, t1);
+          pl.eval(t1, G, D);
+          const V<NP> v = vscale<NP>(lam, ds);
+          sw.events(rec, tab, pdone, pl.pos);
+          pdone = pl.pos;
+          sw.add(t1, v, y, G, D);
+          lam = vfma<NP>(v, D, lam);
+        } else if (METHOD == SLODE_METHOD_MIDPOINT) {
+          const float half = 0.5f * ds;
+          const float tm = t1 - half;
+          V<NP> G1, D1, Gm, Dm;
+          pl.seek(wt, tab, t1);   // the stage at t1 has weight 0 in a_theta: its flips are recorded with the next
+          pl.eval(t1, G1, D1);
+          pl.seek(wt, tab, tm);
+          pl.eval(tm, Gm, Dm);
+          const V<NP> ym = vaxpy<NP>(-half, rhs<NP>(G1, D1, y), y);  // y + half*(D1*y - A1)
+          const V<NP> am = vaxpy<NP>(half, vmul<NP>(lam, D1), lam);  // a + half*(-a*D1), D holds -sigmoid
+          const V<NP> v = vscale<NP>(am, ds);
+          sw.events(rec, tab, pdone, pl.pos);
+          pdone = pl.pos;
+          sw.add(tm, v, ym, Gm, Dm);
+          lam = vfma<NP>(v, Dm, lam);
+        } else {  // rk4 3/8 on the augmented system; Ky = -f, Ka = -a*D; new evaluations at ta, tb, t0
+          const float w8 = 0.125f * ds;
+          const float ta = t1 - ds * kOneThird, tb = t1 - ds * kTwoThirds;
+          V<NP> G0, D0, G1, D1, G2, D2;
+          pl.seek(wt, tab, ta);
+          const int pa = pl.pos;
+          pl.eval(ta, G0, D0);
+          pl.seek(wt, tab, tb);
+          const int pb = pl.pos;
+          pl.eval(tb, G1, D1);
+          pl.seek(wt, tab, t0);
+          pl.eval(t0, G2, D2);
+          // stage 1 at t1 (carried evaluation)
+          const V<NP> f1 = rhs<NP>(Gc, Dc, y);
+          const V<NP> ka1 = vmul<NP>(lam, Dc);
+          sw.add(t1, vscale<NP>(lam, w8), y, Gc, Dc);
+          // stage 2
+          V<NP> ym = vaxpy<NP>(-ds * kOneThird, f1, y);
+          V<NP> am = vaxpy<NP>(ds * kOneThird, ka1, lam);
+          const V<NP> f2_ = rhs<NP>(G0, D0, ym);
+          const V<NP> ka2 = vmul<NP>(am, D0);
+          sw.events(rec, tab, pdone, pa);
+          sw.add(ta, vscale<NP>(am, 3.0f * w8), ym, G0, D0);
+          // stage 3
+          ym = vaxpy<NP>(-ds, vaxpy<NP>(-kOneThird, f1, f2_), y);
+          am = vaxpy<NP>(ds, vaxpy<NP>(-kOneThird, ka1, ka2), lam);
+          const V<NP> f3 = rhs<NP>(G1, D1, ym);
+          const V<NP> ka3 = vmul<NP>(am, D1);
+          sw.events(rec, tab, pa, pb);
+          sw.add(tb, vscale<NP>(am, 3.0f * w8), ym, G1, D1);
+          // stage 4 at t0 (becomes the carried evaluation)
+          ym = vaxpy<NP>(-ds, vadd<NP>(vsub<NP>(f1, f2_), f3), y);
+          am = vaxpy<NP>(ds, vadd<NP>(vsub<NP>(ka1, ka2), ka3), lam);
+          const V<NP> ka4 = vmul<NP>(am, D2);
+          sw.events(rec, tab, pb, pl.pos);
+          pdone = pl.pos;
+          sw.add(t0, vscale<NP>(am, w8), ym, G2, D2);
+          const V<NP> asum = vadd<NP>(vaxpy<NP>(3.0f, vadd<NP>(ka2, ka3), ka1), ka4);
+          lam = vaxpy<NP>(w8, asum, lam);
+          Gc = G2;
+          Dc = D2;
+        }
+      }
+      lam = vadd<NP>(lam, vscale<NP>(vload<S>(gs + (int64_t)i * gst), live));
+      t1 = t0;
+    }
+
+    // ---- end of the sweep: per hidden unit (uniform loop, all lanes busy) combine the recorded and the final
+    // prefix sums into the sums over the evaluations where the unit was active,
+    //     active throughout: final      turned off: record      turned on: final - record      never: 0
+    // and turn them into dc_j (per trajectory), dw1t_j and dW_oj (warp reduction, one shared atomic per warp and
+    // value).  Units are taken in chunks of JC; each chunk's dc_j goes through the warp's transposition buffer
+    // into the fused small-net gradients.
+    constexpr int JC = SH::JC, JS = SH::JS;
+    constexpr int KR = (2 * NQ + 1 <= 16) ? 16 : 32;
+    static_assert(2 * NQ + 1 <= 32, "state dimension");
+    if (fused) {
+      // this warp's z rows -> zT[lane][l]
+      const float* zrow = lat.z + b * L;
+      for (int l = 0; l < LQ; ++l) zT[lane * LQ + l] = l < L ? __ldg(zrow + l) : 0.0f;
+    }
+    __syncwarp();  // (also: every lane is done with the key table before it is overwritten below)
+
+    const float* recs = wt + SH::BIAS;
+#pragma unroll 1
+    for (int j0 = 0; j0 < H; j0 += JC) {
+      // ---- pass 1 of the chunk: dc_j per lane, weight-gradient sums over the warp
+#pragma unroll 1
+      for (int jj = 0; jj < JC; ++jj) {
+        const int j = j0 + jj;
+        bool f, fl;
+        if constexpr (SH::BIG) {
+          const uint8_t sbits = T > 1 ? tab.fs[(size_t)j * tab.stride] : 0;
+          f = sbits & 1;
+          fl = sbits & 2;
+        } else {
+          uint32_t fw = first[0], lw = sw.flipped[0];
+#pragma unroll
+          for (int ww = 1; ww < SH::NWR; ++ww) {
+            if ((j >> 5) == ww) { fw = first[ww]; lw = sw.flipped[ww]; }
+          }
+          f = (fw >> (j & 31)) & 1u;
+          fl = (lw >> (j & 31)) & 1u;
+        }
+        const bool last = f != fl;
+        const f2 ar = bc(fl ? (f ? 1.0f : -1.0f) : 0.0f), af = bc(last ? 1.0f : 0.0f);
+        const float* wrec = recs + j * SH::UNIT;
+        const f2 wj = bc(wrec[2 * NQ]);
+        const f2 cj = bc(tab.c[(size_t)j * tab.stride]);
+        f2 s1 = 0ull, s2 = 0ull;
+        float red[KR];
+#pragma unroll
+        for (int k = 0; k < KR; ++k) red[k] = 0.0f;
+        const f2* src = rec + j * (2 * NQ);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          f2 rp = 0ull, rq = 0ull;
+          if (fl) {
+            rp = src[q];
+            rq = src[NQ + q];
+          }
+          const f2 pe = fma2(ar, rp, mul2(af, sw.P[q]));
+          const f2 qe = fma2(ar, rq, mul2(af, sw.Q[q]));
+          const f2 wq = reinterpret_cast<const f2*>(wrec)[q];
+          s1 = fma2(wq, pe, s1);
+          s2 = fma2(wq, qe, s2);
+          unpk(fma2(wj, qe, mul2(cj, pe)), red[2 * q], red[2 * q + 1]);
+        }
+        const float dc = kNegLn2 * (lo_of(s1) + hi_of(s1));   // packed head weights are scaled by -log2(e)
+        red[2 * NQ] = kNegLn2 * (lo_of(s2) + hi_of(s2));
+        if (fused) {
+          dcT[lane * JS + jj] = dc;
+        } else if (ok) {
+          grad_c[b * H + j] = dc;
+        }
+        warp_reduce_to<KR>(red, lane, [&](int slot) -> float* {
+          if (slot == 2 * NQ) return acc + GL::w1t + j;
+          if (slot > 2 * NQ) return nullptr;
+          const int q = slot >> 1, h = slot & 1;
+          const bool growth = q < NP;
+          const int s = 2 * (growth ? q : q - NP) + h;
+          if (s >= S) return nullptr;
+          return acc + (growth ? GL::Wg : GL::Wd) + s * H + j;
+        });
+      }
+      if (!fused) continue;
+      __syncwarp();
+      // ---- pass 2: lane <-> unit j0 + lane.  dW1z[j][l] += sum_b dc[b][j] z[b][l],  db1[j] += sum_b dc[b][j];
+      //      per trajectory (discrete mode) dz_l += sum_j W1z[l][j] dc_j
+      auto outer = [&](float* gW, float* gb) {
+        // gW[j][l] (row stride L) += sum_b buf[b][lane] * z[b][l]
+        for (int l0 = 0; l0 < L; l0 += 16) {
+          float a[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) a[k] = 0.0f;
+          float sb_ = 0.0f;
+#pragma unroll 2
+          for (int bb_ = 0; bb_ < 32; ++bb_) {
+            const float d = lane < JC ? dcT[bb_ * JS + lane] : 0.0f;
+            sb_ += d;
+            const float4* zr = reinterpret_cast<const float4*>(zT + bb_ * LQ + l0);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (l0 + 4 * k4 < L) {
+                const float4 zz = zr[k4];
+                a[4 * k4] = fmaf(d, zz.x, a[4 * k4]);
+                a[4 * k4 + 1] = fmaf(d, zz.y, a[4 * k4 + 1]);
+                a[4 * k4 + 2] = fmaf(d, zz.z, a[4 * k4 + 2]);
+                a[4 * k4 + 3] = fmaf(d, zz.w, a[4 * k4 + 3]);
+              }
+            }
+          }
+          if (lane < JC) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              if (l0 + k < L) atomicAdd(gW + (j0 + lane) * L + l0 + k, a[k]);
+            }
+            if (l0 == 0) atomicAdd(gb + j0 + lane, sb_);
+          }
+        }
+      };
+      auto dz_from = [&](const float* Wl, bool accumulate) {
+        // grad_z[b][l] (+)= sum_jj Wl[l][j0 + jj] * buf[lane][jj]:  the trajectory's row of the buffer in registers,
+        // the weight rows read as float4 over the units (broadcast); partial sums of later chunks / the second net
+        // go through grad_z itself (the row stays in L1)
+        constexpr int JC4 = (JC + 3) / 4 * 4;
+        float d[JC4];
+#pragma unroll
+        for (int jj = 0; jj < JC4; ++jj) d[jj] = jj < JC ? dcT[lane * JS + jj] : 0.0f;
+        float* gzrow = grad_z + b * L;
+#pragma unroll 1
+        for (int l = 0; l < L; ++l) {
+          const float4* wr = reinterpret_cast<const float4*>(Wl + l * SH::HQ + j0);
+          float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+          for (int q4 = 0; q4 < JC4 / 4; ++q4) {
+            const float4 ww = wr[q4];
+            a0 = fmaf(ww.x, d[4 * q4], a0);
+            a1 = fmaf(ww.y, d[4 * q4 + 1], a1);
+            a0 = fmaf(ww.z, d[4 * q4 + 2], a0);
+            a1 = fmaf(ww.w, d[4 * q4 + 3], a1);
+          }
+          if (ok) gzrow[l] = (accumulate ? gzrow[l] : 0.0f) + (a0 + a1);
+        }
+      };
+      outer(acc + GL::W1z(L), acc + GL::b1(L));
+      // dz through c (discrete mode only: odeint_adjoint gives z no gradient through the dynamics)
+      if (MODE == SLODE_BWD_DISCRETE) {
+        dz_from(ls.Wz, j0 != 0);
+      } else if (j0 == 0 && ok) {
+        for (int l = 0; l < L; ++l) grad_z[b * L + l] = 0.0f;
+      }
+      __syncwarp();
+      if (fx0) {
+        // ---- x0 net: da_j = [ha_j > 0] sum_s Wb[s][j] db_s,  db = dL/dx0 * x0 (1 - x0);  hr_j = relu(ha_j)
+        const V<NP> x0 = vload<S>(xs);
+        float db[S];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          float l0_, l1_, a0, a1;
+          unpk(lam.v[p], l0_, l1_);
+          unpk(x0.v[p], a0, a1);
+          db[2 * p] = l0_ * (a0 - a0 * a0);
+          if (2 * p + 1 < S) db[2 * p + 1] = l1_ * (a1 - a1 * a1);
+        }
+        float ha[JC];
+        lat_chunk<JC>(ls.Wa, ls.ba, SH::HQ, j0, lat.z + b * L, L, ha);
+        // da -> buffer
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) {
+          float a = 0.0f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) a = fmaf(ls.Wb[s * SH::HQ + j0 + jj], db[s], a);
+          dcT[lane * JS + jj] = ha[jj] > 0.0f ? a * live : 0.0f;
+        }
+        __syncwarp();
+        outer(acc + GL::Wa(L), acc + GL::ba(L));
+        dz_from(ls.Wa, true);
+        __syncwarp();
+        // hr -> buffer;  dWb[s][j] += sum_b db[b][s] hr[b][j]
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) dcT[lane * JS + jj] = fmaxf(ha[jj], 0.0f) * live;
+        __syncwarp();
+        {
+          float a[S];
+#pragma unroll
+          for (int s = 0; s < S; ++s) a[s] = 0.0f;
+#pragma unroll 2
+          for (int bb_ = 0; bb_ < 32; ++bb_) {
+            const float h = lane < JC ? dcT[bb_ * JS + lane] : 0.0f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) a[s] = fmaf(__shfl_sync(0xffffffffu, db[s], bb_), h, a[s]);
+          }
+          if (lane < JC) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) atomicAdd(acc + GL::Wb(L) + s * H + j0 + lane, a[s]);
+          }
+        }
+        if (j0 == 0) {
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = k < S ? db[k < S ? k : 0] * live : 0.0f;
+          warp_reduce_to<16>(v, lane, [&](int slot) -> float* { return slot < S ? acc + GL::bb(L) + slot : nullptr; });
+        }
+        __syncwarp();
+      }
+    }
+    // head biases: total of the cotangents over all evaluations
+    {
+      float red[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) red[k] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) unpk(sw.P[q], red[2 * q], red[2 * q + 1]);
+      warp_reduce_to<KR>(red, lane, [&](int slot) -> float* {
+        if (slot >= 2 * NQ) return nullptr;
+        const int q = slot >> 1, h = slot & 1;
+        const bool growth = q < NP;
+        const int s = 2 * (growth ? q : q - NP) + h;
+        if (s >= S) return nullptr;
+        return acc + (growth ? GL::bg : GL::bd) + s;
+      });
+    }
+    if (fused && T <= 1 && ok && MODE == SLODE_BWD_DISCRETE && !fx0) {
+      // no evaluation at all: the loops above wrote zeros already
+    }
+    if (!fx0) vstore<S>(grad_y0 + b * S, ok, lam);
+    __syncwarp();  // the transposition buffer doubles as the next tile's key table
+  }
+
+  __syncthreads();
+  for (int i = tid; i < n_acc; i += kThreads) atomicAdd(grad_w + i, acc[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch plans and launchers (one instantiation set per compiled shape, see slode_fixed_<H>_<S>.cu)
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  int grid;
+  size_t smem;
+  size_t ws_bytes;   // global scratch the caller provides: wide-layer tables (+ flip records, backward)
+};
+
+template <class K>
+int plan_grid(K kern, size_t smem, int64_t B, int sms, int* grid) {
+  SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks_per_sm = 0;
+  SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem));
+  if (blocks_per_sm < 1) {
+    set_error("fixed-grid kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+    return SLODE_EUNSUPPORTED;
+  }
+  const int64_t tiles = (B + kThreads - 1) / kThreads;
+  // whole waves of resident blocks; tiles are handed out grid-stride
+  *grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sms * blocks_per_sm));
+  return SLODE_OK;
+}
+
+template <int H, int S, int METHOD>
+int plan_fwd(const FwdArgs& a, Plan* p) {
+  p->smem = fwd_smem_bytes<H, S>(a.lat.L, a.lat.z != nullptr, a.st == S);
+  const int rc = plan_grid(fixed_fwd_kernel<H, S, METHOD>, p->smem, a.B, a.sms, &p->grid);
+  if (rc) return rc;
+  p->ws_bytes = big_tab_bytes<H, S>() * (size_t)p->grid * kThreads;
+  return SLODE_OK;
+}
+
+template <int H, int S, int METHOD, int MODE>
+int plan_bwd(const BwdArgs& a, Plan* p) {
+  p->smem = bwd_smem_bytes<H, S>(a.lat.L, a.lat.z != nullptr);
+  const int rc = plan_grid(fixed_bwd_kernel<H, S, METHOD, MODE>, p->smem, a.B, a.sms, &p->grid);
+  if (rc) return rc;
+  p->ws_bytes = (big_tab_bytes<H, S>() + rec_bytes_per_thread<H, S>()) * (size_t)p->grid * kThreads;
+  return SLODE_OK;
+}
+
+template <int H, int S, int METHOD>
+int launch_fwd(const FwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {
+  Plan p;
+  const int rc = plan_fwd<H, S, METHOD>(a, &p);
+  if (rc) return rc;
+  *ws_need = p.ws_bytes;
+  if (plan_only) return SLODE_OK;
+  if (p.ws_bytes > a.ws_bytes || (p.ws_bytes && !a.ws)) {
+    set_error("fixed-grid forward: workspace of %zu bytes given, %zu needed (slode_fixed_workspace_bytes)", a.ws_bytes,
+              p.ws_bytes);
+    return SLODE_EINVAL;
+  }
+  fixed_fwd_kernel<H, S, METHOD><<<p.grid, kThreads, p.smem, a.stream>>>(
+      a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb, w, w1t_stride, a.lat, static_cast<unsigned char*>(a.ws));
+  SLODE_CUDA_TRY(cudaGetLastError());
+  return SLODE_OK;
+}
+
+template <int H, int S, int METHOD, int MODE>
+int launch_bwd(const BwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {
+  Plan p;
+  const int rc = plan_bwd<H, S, METHOD, MODE>(a, &p);
+  if (rc) return rc;
+  *ws_need = p.ws_bytes;
+  if (plan_only) return SLODE_OK;
+  if (p.ws_bytes > a.ws_bytes || !a.ws) {
+    set_error("fixed-grid backward: workspace of %zu bytes given, %zu needed (slode_fixed_workspace_bytes)", a.ws_bytes,
+              p.ws_bytes);
+    return SLODE_EINVAL;
+  }
+  fixed_bwd_kernel<H, S, METHOD, MODE><<<p.grid, kThreads, p.smem, a.stream>>>(
+      a.B, a.T, a.t, a.c, a.sol, a.st, a.sb, a.gsol, a.gst, a.gsb, a.gy0, a.gc, a.gw, w, w1t_stride, a.lat, a.gz,
+      static_cast<unsigned char*>(a.ws));
+  SLODE_CUDA_TRY(cudaGetLastError());
+  return SLODE_OK;
+}
+
+template <int H, int S>
+int fwd_shape(const FwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {
+  switch (a.method) {
+    case SLODE_METHOD_EULER: return launch_fwd<H, S, SLODE_METHOD_EULER>(a, w, w1t_stride, plan_only, ws_need);
+    case SLODE_METHOD_MIDPOINT: return launch_fwd<H, S, SLODE_METHOD_MIDPOINT>(a, w, w1t_stride, plan_only, ws_need);
+    case SLODE_METHOD_RK4: return launch_fwd<H, S, SLODE_METHOD_RK4>(a, w, w1t_stride, plan_only, ws_need);
+  }
+  set_error("fixed-grid forward: unknown method %d", a.method);
+  return SLODE_EINVAL;
+}
+
+template <int H, int S>
+int bwd_shape(const BwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {
+#define SLODE_FX_BWD_CASE(M)                                                                              \
+  case M:                                                                                                 \
+    if (a.mode == SLODE_BWD_DISCRETE)                                                                     \
+      return launch_bwd<H, S, M, SLODE_BWD_DISCRETE>(a, w, w1t_stride, plan_only, ws_need);               \
+    return launch_bwd<H, S, M, SLODE_BWD_TDE_ADJOINT>(a, w, w1t_stride, plan_only, ws_need);
+  switch (a.method) {
+    SLODE_FX_BWD_CASE(SLODE_METHOD_EULER)
+    SLODE_FX_BWD_CASE(SLODE_METHOD_MIDPOINT)
+    SLODE_FX_BWD_CASE(SLODE_METHOD_RK4)
+  }
+#undef SLODE_FX_BWD_CASE
+  set_error("fixed-grid backward: unknown method %d", a.method);
+  return SLODE_EINVAL;
+}
+
+}  // namespace fx
+}  // namespace slode
+
+// Defines the two entry functions of one compiled shape (looked up by slode_mlp.cu through slode_mlp_api.h).
+#define SLODE_DEFINE_FIXED_SHAPE(H, S)                                                                             \
+  namespace slode {                                                                                                \
+  int fixed_fwd_##H##_##S(const FwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {   \
+    return fx::fwd_shape<H, S>(a, w, w1t_stride, plan_only, ws_need);                                              \
+  }                                                                                                                \
+  int fixed_bwd_##H##_##S(const BwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {   \
+    return fx::bwd_shape<H, S>(a, w, w1t_stride, plan_only, ws_need);                                              \
+  }                                                                                                                \
+  }

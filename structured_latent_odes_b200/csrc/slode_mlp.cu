@@ -1,5 +1,6 @@
-// C-ABI entry points of the blackbox latent-ODE solve: argument checks and dispatch to the compiled (H,S) shapes.
-// The kernels live in slode_mlp_kernels.cuh, one translation unit per shape (slode_mlp_<H>_<S>.cu).
+// C-ABI entry points: library queries and the dopri5 solve (argument checks and dispatch to the compiled (H,S)
+// shapes; kernels in slode_dopri5_kernels.cuh, one translation unit per shape slode_mlp_<H>_<S>.cu).  The
+// fixed-grid entry points live in slode_fixed_api.cu.
 #include <algorithm>
 
 #include "slode_common.cuh"
@@ -7,13 +8,6 @@
 
 namespace slode {
 
-struct ShapeEntry {
-  int H, S;
-  mlp_fwd_fn fwd;
-  mlp_bwd_fn bwd;
-  dopri5_fwd_fn dopri5_fwd;
-  dopri5_bwd_fn dopri5_bwd;
-};
 static const ShapeEntry kShapes[] = {
 #define X(h, s) {h, s, mlp_fwd_##h##_##s, mlp_bwd_##h##_##s, dopri5_fwd_##h##_##s, dopri5_bwd_##h##_##s},
     SLODE_SHAPES(X)
@@ -21,9 +15,22 @@ static const ShapeEntry kShapes[] = {
 };
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
-static const ShapeEntry* find_shape(int H, int S) {
+const ShapeEntry* find_shape(int H, int S) {
   for (int i = 0; i < kNumShapes; ++i)
     if (kShapes[i].H == H && kShapes[i].S == S) return &kShapes[i];
+  return nullptr;
+}
+
+static const FixedShapeEntry kFixedShapes[] = {
+#define X(h, s) {h, s, fixed_fwd_##h##_##s, fixed_bwd_##h##_##s},
+    SLODE_FIXED_SHAPES(X)
+#undef X
+};
+constexpr int kNumFixedShapes = sizeof(kFixedShapes) / sizeof(kFixedShapes[0]);
+
+const FixedShapeEntry* find_fixed_shape(int H, int S) {
+  for (int i = 0; i < kNumFixedShapes; ++i)
+    if (kFixedShapes[i].H == H && kFixedShapes[i].S == S) return &kFixedShapes[i];
   return nullptr;
 }
 
@@ -43,91 +50,33 @@ static int check_common(const char* who, int64_t B, int T, int H, int S) {
 
 using namespace slode;
 
-extern "C" int slode_mlp_supported(int H, int S) { return find_shape(H, S) ? 1 : 0; }
+extern "C" int slode_mlp_supported(int H, int S) { return find_fixed_shape(H, S) ? 1 : 0; }
+extern "C" int slode_dopri5_supported(int H, int S) { return find_shape(H, S) ? 1 : 0; }
 
 extern "C" int slode_query(int what) {
   switch (what) {
-    case SLODE_Q_VERSION: return 3;
+    case SLODE_Q_VERSION: return 4;
     case SLODE_Q_SM_ARCH: return 100;
     case SLODE_Q_MAX_HIDDEN: {
       int m = 0;
-      for (int i = 0; i < kNumShapes; ++i) m = std::max(m, kShapes[i].H);
+      for (int i = 0; i < kNumFixedShapes; ++i) m = std::max(m, kFixedShapes[i].H);
       return m;
     }
     case SLODE_Q_MAX_STATE: {
       int m = 0;
-      for (int i = 0; i < kNumShapes; ++i) m = std::max(m, kShapes[i].S);
+      for (int i = 0; i < kNumFixedShapes; ++i) m = std::max(m, kFixedShapes[i].S);
       return m;
     }
-    case SLODE_Q_N_SHAPES: return kNumShapes;
+    case SLODE_Q_N_SHAPES: return kNumFixedShapes;
     case SLODE_Q_FWD_LAUNCHES: return g_fwd_launches;
     case SLODE_Q_BWD_LAUNCHES: return g_bwd_launches;
     case SLODE_Q_TOTAL_LAUNCHES: return (int)(g_total_launches.load() & 0x7fffffff);
   }
-  if (what >= SLODE_Q_SHAPE_BASE && what < SLODE_Q_SHAPE_BASE + 2 * kNumShapes) {
+  if (what >= SLODE_Q_SHAPE_BASE && what < SLODE_Q_SHAPE_BASE + 2 * kNumFixedShapes) {
     const int i = (what - SLODE_Q_SHAPE_BASE) / 2;
-    return ((what - SLODE_Q_SHAPE_BASE) & 1) ? kShapes[i].S : kShapes[i].H;
+    return ((what - SLODE_Q_SHAPE_BASE) & 1) ? kFixedShapes[i].S : kFixedShapes[i].H;
   }
   return -1;
-}
-
-extern "C" int slode_mlp_fixed_fwd(int method, int64_t B, int T, int H, int S, const float* t, const float* c,
-                                   const float* y0, const float* w1t, const float* Wg, const float* bg,
-                                   const float* Wd, const float* bd, float* sol, int64_t sol_stride_t,
-                                   int64_t sol_stride_b, void* stream_) {
-  int rc = check_common("slode_mlp_fixed_fwd", B, T, H, S);
-  if (rc) return rc;
-  if (method != SLODE_METHOD_EULER && method != SLODE_METHOD_MIDPOINT && method != SLODE_METHOD_RK4) {
-    set_error("slode_mlp_fixed_fwd: unknown method %d", method);
-    return SLODE_EINVAL;
-  }
-  if (!t || !w1t || !Wg || !bg || !Wd || !bd || (B > 0 && (!c || !y0 || !sol))) {
-    set_error("slode_mlp_fixed_fwd: null pointer");
-    return SLODE_EINVAL;
-  }
-  g_fwd_launches = 0;
-  if (B == 0) return SLODE_OK;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  PackGuard guard(stream);
-  if (guard.status) return guard.status;
-  const FwdArgs a{method, B, T, t, c, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, LatentSrc{}, nullptr};
-  const PackSrc w{w1t, Wg, bg, Wd, bd};
-  rc = find_shape(H, S)->fwd(a, w, guard.staging);
-  if (rc == SLODE_OK) g_fwd_launches = 2;  // pack kernel + solver kernel
-  return rc;
-}
-
-extern "C" int slode_mlp_fixed_bwd(int method, int mode, int64_t B, int T, int H, int S, const float* t,
-                                   const float* c, const float* w1t, const float* Wg, const float* bg,
-                                   const float* Wd, const float* bd, const float* sol, int64_t sol_stride_t,
-                                   int64_t sol_stride_b, const float* grad_sol, int64_t gsol_stride_t,
-                                   int64_t gsol_stride_b, float* grad_y0, float* grad_c, float* grad_w,
-                                   void* stream_) {
-  int rc = check_common("slode_mlp_fixed_bwd", B, T, H, S);
-  if (rc) return rc;
-  if (method != SLODE_METHOD_EULER && method != SLODE_METHOD_MIDPOINT && method != SLODE_METHOD_RK4) {
-    set_error("slode_mlp_fixed_bwd: unknown method %d", method);
-    return SLODE_EINVAL;
-  }
-  if (mode != SLODE_BWD_DISCRETE && mode != SLODE_BWD_TDE_ADJOINT) {
-    set_error("slode_mlp_fixed_bwd: unknown mode %d", mode);
-    return SLODE_EINVAL;
-  }
-  if (!t || !w1t || !Wg || !bg || !Wd || !bd || !grad_w || (B > 0 && (!c || !sol || !grad_sol || !grad_y0 || !grad_c))) {
-    set_error("slode_mlp_fixed_bwd: null pointer");
-    return SLODE_EINVAL;
-  }
-  g_bwd_launches = 0;
-  if (B == 0) return SLODE_OK;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  PackGuard guard(stream);
-  if (guard.status) return guard.status;
-  const BwdArgs a{method, mode,          B,  T,      t,        c,       w1t, Wg, Wd, sol, sol_stride_t, sol_stride_b,
-                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, grad_c, grad_w, stream, guard.sms, LatentSrc{}, nullptr, nullptr};
-  const PackSrc w{w1t, Wg, bg, Wd, bd};
-  rc = find_shape(H, S)->bwd(a, w, guard.staging);
-  if (rc == SLODE_OK) g_bwd_launches = 2;
-  return rc;
 }
 
 extern "C" int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S, const float* t, const float* c, const float* y0,
@@ -199,117 +148,3 @@ extern "C" int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S, const float*
   return rc;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// fused entry points: the solve together with the two small nets in front of it
-// ---------------------------------------------------------------------------------------------------------
-static int check_latent(const char* who, int method, int L, const float* z, const float* W1, const float* b1,
-                        const float* Wa, const float* ba, const float* Wb, const float* bb, const float* y0or) {
-  if (method != SLODE_METHOD_EULER && method != SLODE_METHOD_MIDPOINT && method != SLODE_METHOD_RK4) {
-    set_error("%s: unknown method %d", who, method);
-    return SLODE_EINVAL;
-  }
-  if (L < 1 || !z || !W1 || !b1) {
-    set_error("%s: latent inputs missing (L=%d)", who, L);
-    return SLODE_EINVAL;
-  }
-  const int n = (Wa != nullptr) + (ba != nullptr) + (Wb != nullptr) + (bb != nullptr);
-  if (n != 0 && n != 4) {
-    set_error("%s: latent_to_ode_net weights must be given all together or not at all", who);
-    return SLODE_EINVAL;
-  }
-  if (n == 0 && !y0or) {
-    set_error("%s: neither latent_to_ode_net weights nor y0 / grad_y0 given", who);
-    return SLODE_EINVAL;
-  }
-  return SLODE_OK;
-}
-
-// W1[:,0] (stride L+1) -> contiguous copy in the device staging area (behind the packed weights)
-static int gather_w1t(const float* W1, int L, int H, float* dst, cudaStream_t stream) {
-  SLODE_CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(float), W1, sizeof(float) * (L + 1), sizeof(float), H,
-                                   cudaMemcpyDeviceToDevice, stream));
-  return SLODE_OK;
-}
-
-extern "C" int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S, const float* t, const float* z,
-                                      const float* W1, const float* b1, const float* Wg, const float* bg,
-                                      const float* Wd, const float* bd, const float* Wa, const float* ba,
-                                      const float* Wb, const float* bb, const float* y0, float* sol,
-                                      int64_t sol_stride_t, int64_t sol_stride_b, float* eval_ckpt, void* stream_) {
-  int rc = check_common("slode_latent_fixed_fwd", B, T, H, S);
-  if (rc) return rc;
-  if (B > 0) {
-    rc = check_latent("slode_latent_fixed_fwd", method, L, z, W1, b1, Wa, ba, Wb, bb, y0);
-    if (rc) return rc;
-  }
-  if (!t || !Wg || !bg || !Wd || !bd || (B > 0 && !sol)) {
-    set_error("slode_latent_fixed_fwd: null pointer");
-    return SLODE_EINVAL;
-  }
-  g_fwd_launches = 0;
-  if (B == 0) return SLODE_OK;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  PackGuard guard(stream);
-  if (guard.status) return guard.status;
-  float* w1t = guard.staging + 12288;
-  rc = gather_w1t(W1, L, H, w1t, stream);
-  if (rc) return rc;
-  const LatentSrc lat{z, L, W1, b1, Wa, ba, Wb, bb};
-  const FwdArgs a{method, B, T, t, nullptr, y0, sol, sol_stride_t, sol_stride_b, stream, guard.sms, lat, eval_ckpt};
-  const PackSrc w{w1t, Wg, bg, Wd, bd};
-  rc = find_shape(H, S)->fwd(a, w, guard.staging);
-  if (rc == SLODE_OK) g_fwd_launches = 2;
-  return rc;
-}
-
-extern "C" int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H, int S, const float* t,
-                                      const float* z, const float* W1, const float* b1, const float* Wg,
-                                      const float* bg, const float* Wd, const float* bd, const float* Wa,
-                                      const float* ba, const float* Wb, const float* bb, const float* sol,
-                                      int64_t sol_stride_t, int64_t sol_stride_b, const float* grad_sol,
-                                      int64_t gsol_stride_t, int64_t gsol_stride_b, float* grad_z, float* grad_y0,
-                                      float* grad_params, const float* eval_ckpt, void* stream_) {
-  int rc = check_common("slode_latent_fixed_bwd", B, T, H, S);
-  if (rc) return rc;
-  if (mode != SLODE_BWD_DISCRETE && mode != SLODE_BWD_TDE_ADJOINT) {
-    set_error("slode_latent_fixed_bwd: unknown mode %d", mode);
-    return SLODE_EINVAL;
-  }
-  if (B > 0) {
-    rc = check_latent("slode_latent_fixed_bwd", method, L, z, W1, b1, Wa, ba, Wb, bb, grad_y0);
-    if (rc) return rc;
-  }
-  if (!t || !Wg || !bg || !Wd || !bd || !grad_params || (B > 0 && (!sol || !grad_sol || !grad_z))) {
-    set_error("slode_latent_fixed_bwd: null pointer");
-    return SLODE_EINVAL;
-  }
-  g_bwd_launches = 0;
-  if (B == 0) return SLODE_OK;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  PackGuard guard(stream);
-  if (guard.status) return guard.status;
-  float* w1t = guard.staging + 12288;
-  rc = gather_w1t(W1, L, H, w1t, stream);
-  if (rc) return rc;
-  const LatentSrc lat{z, L, W1, b1, Wa, ba, Wb, bb};
-  const BwdArgs a{method, mode, B, T, t, nullptr, w1t, Wg, Wd, sol, sol_stride_t, sol_stride_b,
-                  grad_sol, gsol_stride_t, gsol_stride_b, grad_y0, nullptr, grad_params, stream, guard.sms, lat, grad_z,
-                  mode == SLODE_BWD_DISCRETE ? eval_ckpt : nullptr};
-  const PackSrc w{w1t, Wg, bg, Wd, bd};
-  rc = find_shape(H, S)->bwd(a, w, guard.staging);
-  if (rc == SLODE_OK) g_bwd_launches = 2;
-  return rc;
-}
-
-extern "C" int64_t slode_eval_ckpt_floats(int method, int64_t B, int T, int S) {
-  if (B < 0 || T < 1 || S < 1) return -1;
-  int64_t nev;
-  switch (method) {
-    case SLODE_METHOD_EULER: nev = T - 1; break;
-    case SLODE_METHOD_MIDPOINT: nev = 2 * (int64_t)(T - 1); break;
-    case SLODE_METHOD_RK4: nev = 3 * (int64_t)(T - 1) + 1; break;
-    default: return -1;
-  }
-  const int64_t tiles = ((B + 1) / 2 + 127) / 128;  // tile-major: every tile of 128 trajectory pairs owns nev * 2S KB
-  return tiles * nev * (2 * (int64_t)S) * 128 * 2;
-}

@@ -31,7 +31,9 @@ struct FwdArgs {
   cudaStream_t stream;
   int sms;
   LatentSrc lat;
-  float* eval_ckpt;  // optional: every MLP evaluation (A, -D) of the solve, see slode_b200.h
+  float* eval_ckpt;  // round-1 kernels only: every MLP evaluation (A, -D) of the solve
+  void* ws;          // caller-provided scratch (slode_fixed_workspace_bytes), may be null when 0 bytes are needed
+  size_t ws_bytes;
 };
 
 struct BwdArgs {
@@ -47,7 +49,9 @@ struct BwdArgs {
   int sms;
   LatentSrc lat;
   float* gz;  // (B,L), fused mode only
-  const float* eval_ckpt;  // optional (discrete mode): the forward's evaluation checkpoints instead of recomputing
+  const float* eval_ckpt;  // round-1 kernels only
+  void* ws;                // caller-provided scratch: flip records (+ wide-layer tables)
+  size_t ws_bytes;
 };
 
 // dopri5 forward (slode_dopri5_kernels.cuh); scratch pointers are filled in by the launcher
@@ -89,13 +93,22 @@ struct Dopri5BwdArgs {
   float* flip_ws;
 };
 
+// round-2 fixed-grid kernels (slode_fixed.cuh): w1t may be strided (W1[:,0] of dynamics_hidden.weight); with
+// plan_only nothing is launched and *ws_need receives the scratch bytes a launch with these arguments needs
+typedef int (*fixed_fwd_fn)(const FwdArgs&, const PackSrc&, int w1t_stride, bool plan_only, size_t* ws_need);
+typedef int (*fixed_bwd_fn)(const BwdArgs&, const PackSrc&, int w1t_stride, bool plan_only, size_t* ws_need);
 typedef int (*mlp_fwd_fn)(const FwdArgs&, const PackSrc&, float* staging);
 typedef int (*mlp_bwd_fn)(const BwdArgs&, const PackSrc&, float* staging);
 typedef int (*dopri5_fwd_fn)(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 typedef int (*dopri5_bwd_fn)(const Dopri5BwdArgs&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 
 // (25,5): CVS / challenge configs; (25,8): proc config; the rest serve tests and the width sweep.
+// SLODE_SHAPES: shapes of the round-1 translation units (dopri5; the round-1 fixed-grid kernels kept for A/B runs)
 #define SLODE_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5) X(64, 5)
+// SLODE_FIXED_SHAPES: shapes of the fixed-grid kernels (slode_fixed.cuh, one unit slode_fixed_<H>_<S>.cu each)
+#ifndef SLODE_FIXED_SHAPES
+#define SLODE_FIXED_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5) X(64, 5) X(128, 5) X(256, 5) X(512, 5)
+#endif
 
 #define SLODE_DECLARE_SHAPE(H, S)                                         \
   int mlp_fwd_##H##_##S(const FwdArgs&, const PackSrc&, float* staging);  \
@@ -104,5 +117,26 @@ typedef int (*dopri5_bwd_fn)(const Dopri5BwdArgs&, const PackSrc&, float* stagin
   int dopri5_bwd_##H##_##S(const Dopri5BwdArgs&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 SLODE_SHAPES(SLODE_DECLARE_SHAPE)
 #undef SLODE_DECLARE_SHAPE
+#define SLODE_DECLARE_FIXED_SHAPE(H, S)                                                                       \
+  int fixed_fwd_##H##_##S(const FwdArgs&, const PackSrc&, int w1t_stride, bool plan_only, size_t* ws_need);   \
+  int fixed_bwd_##H##_##S(const BwdArgs&, const PackSrc&, int w1t_stride, bool plan_only, size_t* ws_need);
+SLODE_FIXED_SHAPES(SLODE_DECLARE_FIXED_SHAPE)
+#undef SLODE_DECLARE_FIXED_SHAPE
+
+struct ShapeEntry {
+  int H, S;
+  mlp_fwd_fn fwd;
+  mlp_bwd_fn bwd;
+  dopri5_fwd_fn dopri5_fwd;
+  dopri5_bwd_fn dopri5_bwd;
+};
+struct FixedShapeEntry {
+  int H, S;
+  fixed_fwd_fn fwd;
+  fixed_bwd_fn bwd;
+};
+const ShapeEntry* find_shape(int H, int S);             // round-1 units (dopri5)
+const FixedShapeEntry* find_fixed_shape(int H, int S);  // fixed-grid kernels
+int device_sms(int* sms);                               // SM count of the current device (cached)
 
 }  // namespace slode

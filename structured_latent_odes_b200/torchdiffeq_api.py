@@ -29,14 +29,6 @@ __all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_fu
            "solve_fixed_from_c"]
 
 FIXED_METHODS = ("euler", "midpoint", "rk4")
-# Evaluation checkpoints: a forward solve that may be differentiated also stores the head outputs (A, -D) of every
-# MLP evaluation (2S floats each: 12.5 GB per 2^20 x 100 rk4 solve at S = 5) and the discrete reverse sweep reads
-# them back instead of re-evaluating.  None = automatic: off for S <= 5, where the sweep re-evaluates the heads
-# piecewise-linearly as fast as it could read them (and needs no memory), on for wider states, where it would
-# have to redo the dense products.  True / False force it.
-EVAL_CHECKPOINTS = None
-CKPT_MAX_FRACTION = 0.5   # of the free device memory; above it the reverse sweep re-evaluates instead
-
 
 class KernelTimer:
     """Optional CUDA-event timing of the C-ABI calls (bench.py uses it for the roofline numbers).
@@ -183,6 +175,15 @@ def _ptr(x):
     return x.data_ptr() if x is not None else None
 
 
+def _workspace(dev, backward, method_id, mode, B, T, L, H, S, fused, rows_in_time):
+    """Scratch tensor for one fixed-grid call (flip records of the reverse sweep; wide-layer tables): sized by the
+    library, owned by the torch caching allocator -- stream-ordered reuse, and safe inside CUDA-graph capture."""
+    n = _cabi.lib().slode_fixed_workspace_bytes(int(backward), method_id, mode, B, T, L, H, S, fused, int(rows_in_time))
+    if n < 0:
+        raise _cabi.SlodeError("slode_fixed_workspace_bytes: " + _cabi.lib().slode_last_error().decode("utf-8", "replace"))
+    return torch.empty(n, device=dev, dtype=torch.uint8) if n > 0 else None
+
+
 def _dense_tbs_strides(x):
     """(stride_t, stride_b) of a (T,B,S) tensor usable by the kernels, or None if it must be copied."""
     st, sb, ss = x.stride()
@@ -211,9 +212,11 @@ class _MlpFixedSolve(torch.autograd.Function):
             sol = torch.empty((T, B, S), device=y0.device, dtype=torch.float32)
         st, sb = sol.stride(0), sol.stride(1)
         with torch.cuda.device(y0.device), _timed("fwd"):
+            ws = _workspace(y0.device, False, method_id, mode, B, T, 0, H, S, 0, st == S)
             stream = torch.cuda.current_stream().cuda_stream
             rc = _cabi.lib().slode_mlp_fixed_fwd(method_id, B, T, H, S, _ptr(t), _ptr(cc), _ptr(y0c),
-                                                 *[_ptr(x) for x in w], _ptr(sol), st, sb, stream)
+                                                 *[_ptr(x) for x in w], _ptr(sol), st, sb, _ptr(ws),
+                                                 ws.numel() if ws is not None else 0, stream)
         _cabi.check(rc, "slode_mlp_fixed_fwd")
         ctx.save_for_backward(cc, *w, t, sol)
         ctx.method_id, ctx.mode = method_id, mode
@@ -232,11 +235,12 @@ class _MlpFixedSolve(torch.autograd.Function):
         grad_c = torch.empty((B, H), device=sol.device, dtype=torch.float32)
         grad_w = torch.zeros(H + 2 * (S * H + S), device=sol.device, dtype=torch.float32)
         with torch.cuda.device(sol.device), _timed("bwd"):
+            ws = _workspace(sol.device, True, ctx.method_id, ctx.mode, B, T, 0, H, S, 0, False)
             stream = torch.cuda.current_stream().cuda_stream
             rc = _cabi.lib().slode_mlp_fixed_bwd(
                 ctx.method_id, ctx.mode, B, T, H, S, _ptr(t), _ptr(cc), _ptr(w1t), _ptr(Wg), _ptr(bg), _ptr(Wd),
                 _ptr(bd), _ptr(sol), sol.stride(0), sol.stride(1), _ptr(grad_sol), strides[0], strides[1],
-                _ptr(grad_y0), _ptr(grad_c), _ptr(grad_w), stream)
+                _ptr(grad_y0), _ptr(grad_c), _ptr(grad_w), _ptr(ws), ws.numel() if ws is not None else 0, stream)
         _cabi.check(rc, "slode_mlp_fixed_bwd")
         o = 0
         gw1t = grad_w[o:o + H]; o += H
@@ -265,11 +269,8 @@ class _LatentFixedSolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, y0, W1, b1, Wg, bg, Wd, bd, Wa, ba, Wb, bb, t, method_id, mode, layout):
         B, L = z.shape
-        # evaluation checkpoints for the discrete reverse sweep (see slode_b200.h): only when a backward can follow
         H = W1.shape[0]
         S = Wg.shape[0]
-        use_ckpt = (S > 5) if EVAL_CHECKPOINTS is None else bool(EVAL_CHECKPOINTS)
-        want_ckpt = (mode == _cabi.BWD_DISCRETE and use_ckpt and any(ctx.needs_input_grad))
         T = t.numel()
         fx0 = Wa is not None
         zc = z.detach().to(torch.float32).contiguous()
@@ -280,24 +281,14 @@ class _LatentFixedSolve(torch.autograd.Function):
             sol = torch.empty((B, T, S), device=z.device, dtype=torch.float32).permute(1, 0, 2)
         else:
             sol = torch.empty((T, B, S), device=z.device, dtype=torch.float32)
-        ckpt = None
-        if want_ckpt and B > 0 and T > 1:
-            n = _cabi.lib().slode_eval_ckpt_floats(method_id, B, T, S)
-            free, _total = torch.cuda.mem_get_info(z.device)
-            # 8S bytes per MLP evaluation and trajectory (20 GB at 2^20 x 100 rk4, S = 8): only when it fits next to
-            # the sweep's own tensors; otherwise the sweep re-evaluates (it does whenever ckpt is null)
-            if 4 * n <= int(CKPT_MAX_FRACTION * free):
-                try:
-                    ckpt = torch.empty(n, device=z.device, dtype=torch.float32)
-                except torch.OutOfMemoryError:
-                    ckpt = None
         with torch.cuda.device(z.device), _timed("fwd"):
+            ws = _workspace(z.device, False, method_id, mode, B, T, L, H, S, 2 if fx0 else 1, sol.stride(0) == S)
             rc = _cabi.lib().slode_latent_fixed_fwd(
                 method_id, B, T, L, H, S, _ptr(t), _ptr(zc), *[_ptr(x) for x in w], *[_ptr(x) for x in x0w], _ptr(y0c),
-                _ptr(sol), sol.stride(0), sol.stride(1), _ptr(ckpt), torch.cuda.current_stream().cuda_stream)
+                _ptr(sol), sol.stride(0), sol.stride(1), _ptr(ws), ws.numel() if ws is not None else 0,
+                torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "slode_latent_fixed_fwd")
         ctx.save_for_backward(zc, *w, t, sol, *(x0w if fx0 else []))
-        ctx.ckpt = ckpt
         ctx.cfg = (method_id, mode, fx0)
         return sol
 
@@ -320,13 +311,13 @@ class _LatentFixedSolve(torch.autograd.Function):
         n = nbase + H * L + H + ((H * L + H + S * H + S) if fx0 else 0)
         gp = torch.zeros(n, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev), _timed("bwd"):
+            ws = _workspace(dev, True, method_id, mode, B, T, L, H, S, 2 if fx0 else 1, False)
             rc = _cabi.lib().slode_latent_fixed_bwd(
                 method_id, mode, B, T, L, H, S, _ptr(t), _ptr(zc), _ptr(W1), _ptr(b1), _ptr(Wg), _ptr(bg), _ptr(Wd),
                 _ptr(bd), *[_ptr(x) for x in x0w], _ptr(sol), sol.stride(0), sol.stride(1), _ptr(grad_sol), strides[0],
-                strides[1], _ptr(grad_z), _ptr(grad_y0), _ptr(gp), _ptr(ctx.ckpt),
+                strides[1], _ptr(grad_z), _ptr(grad_y0), _ptr(gp), _ptr(ws), ws.numel() if ws is not None else 0,
                 torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "slode_latent_fixed_bwd")
-        ctx.ckpt = None  # 120 B per trajectory-step: release it as soon as the sweep has been enqueued
         o = 0
 
         def take(*shape):
@@ -527,9 +518,8 @@ def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
     if z.shape[0] != B:
         raise ValueError(f"constants batch {z.shape[0]} != y0 batch {B}")
     H = hid.out_features
-    if gro.out_features != S or not _cabi.lib().slode_mlp_supported(H, S):
-        raise NotImplementedError(f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled kernel; available: "
-                                  f"{_cabi.supported_shapes()}")
+    if gro.out_features != S or not _cabi.lib().slode_dopri5_supported(H, S):
+        raise NotImplementedError(f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled dopri5 kernel")
     _check_func_tensors(y0, z, hid, gro, deg)
     if t.numel() > 1 and bool(t[0] > t[-1]):
         raise NotImplementedError("dopri5 with decreasing output times (the reference always integrates forward)")

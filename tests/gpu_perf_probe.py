@@ -3,8 +3,6 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import structured_latent_odes_b200 as slode
-from structured_latent_odes_b200 import torchdiffeq_api as _api
-_api.EVAL_CHECKPOINTS = True if os.environ.get("SLODE_CKPT") else None
 
 def run(B, T, L, H, S, method, adjoint, layout="tbs", reps=5):
     dev = "cuda"

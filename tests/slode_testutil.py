@@ -22,6 +22,10 @@ SHAPES = {
     "small": (6, 16, 4, torch.linspace(0.0, 3.0, 17)),
     "h32": (15, 32, 5, torch.arange(0.0, 40.0, 1.0)),
     "h64": (15, 64, 5, torch.arange(0.0, 30.0, 1.0)),
+    # BASELINE configs[4] width sweep: per-trajectory tables in global scratch, rolled unit loops
+    "h128": (15, 128, 5, torch.arange(0.0, 20.0, 1.0)),
+    "h256": (15, 256, 5, torch.arange(0.0, 12.0, 1.0)),
+    "h512": (15, 512, 5, torch.arange(0.0, 9.0, 1.0)),
 }
 
 

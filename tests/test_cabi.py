@@ -52,18 +52,24 @@ def test_query_without_a_gpu(handle):
 def test_argument_validation_happens_before_any_cuda_call(handle):
     L = _cabi.lib()
     # unsupported (H,S): no generic fallback
-    rc = L.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, 4, 3, 7, 3, *([None] * 8), None, 0, 0, None)
+    rc = L.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, 4, 3, 7, 3, *([None] * 8), None, 0, 0, None, 0, None)
     assert rc == 2 and b"not compiled in" in L.slode_last_error()
     with pytest.raises(NotImplementedError):
         _cabi.check(rc, "fwd")
-    rc = L.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, -1, 3, 25, 5, *([None] * 8), None, 0, 0, None)
+    rc = L.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, -1, 3, 25, 5, *([None] * 8), None, 0, 0, None, 0, None)
     assert rc == 1
-    rc = L.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, 4, 3, 25, 5, *([None] * 8), None, 0, 0, None)
+    rc = L.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, 4, 3, 25, 5, *([None] * 8), None, 0, 0, None, 0, None)
     assert rc == 1 and b"null pointer" in L.slode_last_error()
     with pytest.raises(_cabi.SlodeError):
         _cabi.check(rc, "fwd")
-    rc = L.slode_mlp_fixed_bwd(_cabi.METHOD_RK4, 7, 4, 3, 25, 5, *([None] * 7), None, 0, 0, None, 0, 0, None, None, None, None)
+    rc = L.slode_mlp_fixed_bwd(_cabi.METHOD_RK4, 7, 4, 3, 25, 5, *([None] * 7), None, 0, 0, None, 0, 0, None, None, None, None, 0, None)
     assert rc == 1 and b"unknown mode" in L.slode_last_error()
+    # the workspace query validates like the entry points (no CUDA call for rejected arguments)
+    assert L.slode_fixed_workspace_bytes(1, _cabi.METHOD_RK4, 0, 4, 3, 15, 7, 3, 2, 0) == -1
+    assert L.slode_fixed_workspace_bytes(1, 9, 0, 4, 3, 15, 25, 5, 2, 0) == -1
+    assert L.slode_fixed_workspace_bytes(1, _cabi.METHOD_RK4, 0, 0, 3, 15, 25, 5, 2, 0) == 0
+    assert L.slode_dopri5_supported(25, 5) == 1 and L.slode_dopri5_supported(512, 5) == 0
+    assert L.slode_mlp_supported(512, 5) == 1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -31,12 +31,16 @@ def test_raw_pointer_call_matches_the_python_api():
     s.wait_stream(torch.cuda.current_stream())
     rc = L_.slode_mlp_fixed_fwd(_cabi.METHOD_RK4, B, T, H, S, p.times.data_ptr(), c.data_ptr(), y0.data_ptr(),
                                 w1t.data_ptr(), Wg.data_ptr(), bg.data_ptr(), Wd.data_ptr(), bd.data_ptr(),
-                                sol.data_ptr(), B * S, S, ctypes.c_void_p(s.cuda_stream))
+                                sol.data_ptr(), B * S, S, None, 0, ctypes.c_void_p(s.cuda_stream))
     assert rc == 0, L_.slode_last_error()
     s.synchronize()
     # the Python API runs the FUSED entry point (c and x0 computed inside the kernel): same numbers to rounding
     assert U.rel_err(sol, want) < 1e-6
     assert L_.slode_query(_cabi.Q_FWD_LAUNCHES) >= 1
+    # narrow layers keep their tables in shared memory: the forward needs no workspace, the reverse sweep its records
+    assert L_.slode_fixed_workspace_bytes(0, _cabi.METHOD_RK4, 0, B, T, L, H, S, 2, 0) == 0
+    assert L_.slode_fixed_workspace_bytes(1, _cabi.METHOD_RK4, 0, B, T, L, H, S, 2, 0) > 0
+    assert L_.slode_fixed_workspace_bytes(1, _cabi.METHOD_RK4, 0, B, T, L, 7, 3, 2, 0) == -1
     # the fused entry point with raw pointers: bit-identical to the Python API
     n0, n2 = p.latent_to_ode_net[0], p.latent_to_ode_net[2]
     sol2 = torch.empty(T, B, S, device="cuda")
@@ -45,7 +49,7 @@ def test_raw_pointer_call_matches_the_python_api():
                                    Wg.data_ptr(), bg.data_ptr(), Wd.data_ptr(), bd.data_ptr(),
                                    n0.weight.detach().data_ptr(), n0.bias.detach().data_ptr(),
                                    n2.weight.detach().data_ptr(), n2.bias.detach().data_ptr(), None,
-                                   sol2.data_ptr(), B * S, S, None,
+                                   sol2.data_ptr(), B * S, S, None, 0,
                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, L_.slode_last_error()
     torch.cuda.synchronize()

@@ -75,10 +75,14 @@ def test_gaussian_decoder_and_raw_heads():
         assert U.rel_err(a, b) < 1e-5
 
 
-@pytest.mark.skipif(not shims.reference_available(), reason="/root/reference only exists in the build container")
 def test_state_dict_keys_equal_reference_decoder():
+    """Against the reference's REAL decoder classes (unmodified copies shipped in baseline/_ref)."""
     import structured_latent_odes_b200 as slode
-    _, dec_ref = shims.import_reference_blackbox()
+    from baseline import make_ref, ref_shims
+    from oracle import torchdiffeq_oracle
+    if not make_ref.available():
+        pytest.fail("baseline/_ref is missing: run __graft_entry__.build() in the build container")
+    _, dec_ref = ref_shims.import_real(torchdiffeq_oracle)
     L, H, S, times = U.SHAPES["cvs"]
     cfg = _cfg("cvs", "midpoint", True, 3)
     with contextlib.redirect_stdout(io.StringIO()):

@@ -44,18 +44,6 @@ def test_fixed_grid_matches_oracle(shape, method, adjoint):
     _compare(shape, method, adjoint, B=200)
 
 
-@pytest.mark.parametrize("force", [True, False])
-@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
-@pytest.mark.parametrize("shape", ["cvs", "proc", "h64"])
-def test_forced_checkpoint_modes_match_oracle(shape, method, force, monkeypatch):
-    """EVAL_CHECKPOINTS True: the forward stores every evaluation's (A, -D) and the discrete sweep reads them back;
-    False: the sweep re-evaluates (piecewise-linearly for S <= 5, dense products for the proc shape).  The default
-    (None) picks by state width, so each shape runs one of the two in the other tests."""
-    from structured_latent_odes_b200 import torchdiffeq_api as api
-    monkeypatch.setattr(api, "EVAL_CHECKPOINTS", force)
-    _compare(shape, method, False, B=300)
-
-
 def test_long_horizon_many_relu_crossings():
     """Every hidden unit crosses zero somewhere on a long, non-uniform grid that starts at a negative time: the
     piecewise-linear evaluator must follow all of them (increasing and decreasing grids)."""
@@ -97,6 +85,15 @@ def test_many_crossings_per_evaluation(shape):
             assert U.rel_err(gzp, gzo) < 2 * TOL
         for k in gro:
             assert U.rel_err(grp[k], gro[k]) < 2 * TOL, (method, adjoint, k, U.rel_err(grp[k], gro[k]))
+
+
+@pytest.mark.parametrize("adjoint", [False, True])
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+@pytest.mark.parametrize("shape", ["h128", "h256", "h512"])
+def test_wide_hidden_layers_match_oracle(shape, method, adjoint):
+    """BASELINE configs[4] (hidden 32-512): above 64 units the per-trajectory tables (c, sorted crossing keys, unit
+    status) live in caller-provided global scratch and the unit loops are rolled."""
+    _compare(shape, method, adjoint, B=150)
 
 
 @pytest.mark.parametrize("B", [1, 2, 127, 128, 129, 1000])
