@@ -35,7 +35,10 @@
 #define SLODE_FX_FWD_MINB 5
 #endif
 #ifndef SLODE_FX_BWD_MINB
-#define SLODE_FX_BWD_MINB 4
+#define SLODE_FX_BWD_MINB 4      // resident blocks per SM the reverse sweep is compiled for (euler, midpoint: 128 registers)
+#endif
+#ifndef SLODE_FX_BWD_MINB_RK4
+#define SLODE_FX_BWD_MINB_RK4 3  // rk4 holds three evaluations at once: 168 registers (at 128 it spills in the time loop)
 #endif
 
 namespace slode {
@@ -102,7 +105,15 @@ __device__ __forceinline__ float ld_early(const float* p) {  // a load the compi
   return v;
 }
 __device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
+__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// asynchronous 4-byte copies global -> shared (LDGSTS): no destination register, completion tracked per group and
+// not through the scoreboards the evaluator's own loads wait on
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr float kNegLn2 = -0.6931471805599453f;  // unscaled weight = packed weight * kNegLn2
@@ -182,6 +193,18 @@ template <int S> __device__ __forceinline__ void vprefetch(const float* p) {
   prefetch_l1(p);
   prefetch_l1(p + S - 1);
 }
+// a row of S floats of this thread: k-th float at col[k * kThreads] (conflict-free column of a [S][kThreads] block)
+template <int S> __device__ __forceinline__ void row_fetch(float* col, const float* grow) {
+#pragma unroll
+  for (int k = 0; k < S; ++k) cp_async4(col + k * 128, grow + k);
+}
+template <int S> __device__ __forceinline__ V<(S + 1) / 2> row_read(const float* col) {
+  V<(S + 1) / 2> r;
+#pragma unroll
+  for (int q = 0; q < (S + 1) / 2; ++q) r.v[q] = pk(col[2 * q * 128], (2 * q + 1 < S) ? col[(2 * q + 1) * 128] : 0.0f);
+  return r;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // compile-time shape parameters
@@ -200,7 +223,15 @@ struct Shape {
   static constexpr int NWR = BIG ? 1 : (H + 31) / 32;  // gate words kept in registers (!BIG)
   static constexpr int JC = H <= 32 ? H : 32;          // unit chunk of the small-net prologue / epilogue
   static constexpr int JS = (JC % 2) ? JC : JC + 1;    // odd row stride of the warp's transposition buffer
-  static constexpr int HP = (H + 1 > JS) ? H + 1 : JS; // rows of the key table (>= H + 1 keys, >= the buffer it doubles as)
+  // the warp's key-table region doubles, once the walk is over, as the exchange buffer [32][PQS] of the final
+  // prefix sums (4 NQ floats per trajectory) and as the x0 net's transposition buffer [32][JS]; PQS/4 odd keeps
+  // the 16-byte row accesses conflict-free
+  static constexpr int PQ0 = (4 * NQ > JC ? 4 * NQ : JC);
+  static constexpr int PQ1 = (PQ0 + 3) / 4;
+  static constexpr int PQS = 4 * ((PQ1 % 2) ? PQ1 : PQ1 + 1);
+  static constexpr int HP = (H + 1 > PQS) ? H + 1 : PQS;  // rows of the region (>= H + 1 keys)
+  static constexpr int CS = 33;                        // lane stride of the c table rows (odd: element (j, b) is
+                                                       // reached conflict-free with lanes over b AND over j)
   static constexpr int HQ = (H + 3) / 4 * 4;           // padded row length of the staged small-net weights
   static_assert(H <= 512, "key layout holds 9 index bits");
   static_assert(H <= 32 || H % 32 == 0, "hidden widths above 32 must be multiples of 32");
@@ -243,10 +274,10 @@ __device__ __forceinline__ void stage_weights(float* __restrict__ wt, const floa
 // ([warp][row][32 lanes]: conflict-free for any row index) -- or, for wide hidden layers, global scratch
 // ([row][all resident threads]: coalesced).
 struct Tab {
-  float* c;       // element j at c[j * stride]
-  uint32_t* k;    // key p at k[p * stride]
-  uint8_t* fs;    // BIG only: per-unit status bytes (bit0: gate at the first evaluation, bit1: flipped)
-  int stride;
+  float* c;       // element j at c[j * cs]
+  uint32_t* k;    // key p at k[p * ks]
+  uint8_t* fs;    // BIG only: per-unit status bytes (bit0: gate at the first evaluation, bit1: flipped), stride ks
+  int cs, ks;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -307,7 +338,7 @@ struct Pl {
         k[j] = kNever;
         if (j < H) {
           bool on;
-          k[j] = init_unit(recs + j * SH::UNIT, j, tab.c[j * tab.stride], ts, on);
+          k[j] = init_unit(recs + j * SH::UNIT, j, tab.c[j * tab.cs], ts, on);
           first[j >> 5] |= on ? (1u << (j & 31)) : 0u;
         }
       }
@@ -329,8 +360,8 @@ struct Pl {
         }
       }
 #pragma unroll
-      for (int j = 0; j < H; ++j) tab.k[j * tab.stride] = k[j];
-      tab.k[H * tab.stride] = kNever;
+      for (int j = 0; j < H; ++j) tab.k[j * tab.ks] = k[j];
+      tab.k[H * tab.ks] = kNever;
       nk = __uint_as_float(k[0]);
     } else {
       first[0] = 0u;
@@ -338,11 +369,11 @@ struct Pl {
 #pragma unroll 2
       for (int j = 0; j < H; ++j) {
         bool on;
-        const uint32_t key = init_unit(recs + j * SH::UNIT, j, tab.c[(size_t)j * tab.stride], ts, on);
-        tab.k[(size_t)j * tab.stride] = key;
-        tab.fs[(size_t)j * tab.stride] = on ? 1 : 0;
+        const uint32_t key = init_unit(recs + j * SH::UNIT, j, tab.c[(size_t)j * tab.cs], ts, on);
+        tab.k[(size_t)j * tab.ks] = key;
+        tab.fs[(size_t)j * tab.ks] = on ? 1 : 0;
       }
-      for (int j = H; j <= NS; ++j) tab.k[(size_t)j * tab.stride] = kNever;  // padding + the end sentinel
+      for (int j = H; j <= NS; ++j) tab.k[(size_t)j * tab.ks] = kNever;  // padding + the end sentinel
       // bitonic sort of the thread's own column of the global key table (the table holds NS + 1 rows)
       for (int size = 2; size <= NS; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -350,8 +381,8 @@ struct Pl {
           for (int m = 0; m < NS / 2; ++m) {
             const int i = ((m & ~(stride - 1)) << 1) | (m & (stride - 1));  // index with bit `stride` clear
             const int l = i | stride;
-            uint32_t* pa = tab.k + (size_t)i * tab.stride;
-            uint32_t* pb = tab.k + (size_t)l * tab.stride;
+            uint32_t* pa = tab.k + (size_t)i * tab.ks;
+            uint32_t* pb = tab.k + (size_t)l * tab.ks;
             const uint32_t a = *pa, b = *pb;
             const bool up = (i & size) == 0;
             *pa = up ? min(a, b) : max(a, b);
@@ -373,7 +404,7 @@ struct Pl {
       const int j = (int)(__float_as_uint(nk) & SH::IMASK);
       const float* rec = wt + SH::BIAS + j * SH::UNIT;
       const float w1 = rec[2 * NQ];
-      const float c = tab.c[(size_t)j * tab.stride];
+      const float c = tab.c[(size_t)j * tab.cs];
       const bool post = dirsign * w1 > 0.0f;
       const bool now = (__float_as_uint(fmaf(w1, te, c)) >> 31) == 0u;
       if (now != post) break;  // not across yet at te (the key is early by construction): stays pending
@@ -386,15 +417,18 @@ struct Pl {
         be[q] = fma2(w, vv, be[q]);
       }
       ++pos;
-      nk = __uint_as_float(tab.k[(size_t)pos * tab.stride]);
+      nk = __uint_as_float(tab.k[(size_t)pos * tab.ks]);
     }
   }
 
-  // G = sigmoid(growth heads), ND = -sigmoid(degradation heads) at time te.  The XU pipe (16 MUFU lanes per SM)
-  // bounds the forward kernel, so the two reciprocals of a register pair share one MUFU.RCP:
-  //   1/a = b * rcp(ab), 1/b = a * rcp(ab);  the exponentials are written into swapped halves so that the final
-  //   packed multiply lands each quotient in its own half.  Exponents are clamped at 2^60 so ab stays finite
-  //   (sigmoid floor 1e-18); the clamp propagates NaN.
+  // G = sigmoid(growth heads), ND = -sigmoid(degradation heads) at time te.
+  // MERGE (forward kernel): the XU pipe (16 MUFU lanes per SM) is what the forward comes closest to, so the two
+  //   reciprocals of a register pair share one MUFU.RCP:  1/a = b * rcp(ab), 1/b = a * rcp(ab);  the exponentials are
+  //   written into swapped halves so that the final packed multiply lands each quotient in its own half.  Exponents
+  //   are clamped at 2^60 so ab stays finite (sigmoid floor 1e-18); the clamp propagates NaN.
+  // !MERGE (reverse sweep): one MUFU.RCP per sigmoid (rcp(inf) = 0: no clamp needed).  The sweep is bound by
+  //   instruction issue with the XU pipe a quarter busy: 6 instructions per pair instead of 10 for 1.33x the MUFU work.
+  template <bool MERGE>
   __device__ __forceinline__ void eval(float te, V<NP>& G, V<NP>& ND) const {
     const f2 tt = bc(te);
     const f2 one = bc(1.0f), minus_one = bc(-1.0f);
@@ -405,20 +439,29 @@ struct Pl {
       const int p = growth ? q : q - NP;
       float v0, v1;
       unpk(fma2(al[q], tt, be[q]), v0, v1);
-      const float e0 = ex2_approx(min_nan(v0, 60.0f));
-      if (2 * p + 1 < S) {
-        const float e1 = ex2_approx(min_nan(v1, 60.0f));
-        const f2 esw = pk(e1, e0);
-        const f2 dsw = growth ? add2(esw, one) : sub2(minus_one, esw);
-        float d0, d1;
-        unpk(dsw, d0, d1);
-        const f2 r = bc(rcp_approx(d0 * d1));
-        if (growth) G.v[p] = mul2(dsw, r); else ND.v[p] = mul2(dsw, r);
+      if (MERGE) {
+        const float e0 = ex2_approx(min_nan(v0, 60.0f));
+        if (2 * p + 1 < S) {
+          const float e1 = ex2_approx(min_nan(v1, 60.0f));
+          const f2 esw = pk(e1, e0);
+          const f2 dsw = growth ? add2(esw, one) : sub2(minus_one, esw);
+          float d0, d1;
+          unpk(dsw, d0, d1);
+          const f2 r = bc(rcp_approx(d0 * d1));
+          if (growth) G.v[p] = mul2(dsw, r); else ND.v[p] = mul2(dsw, r);
+        } else {
+          if (growth) tail_g = 1.0f + e0; else tail_d = -1.0f - e0;
+        }
       } else {
-        if (growth) tail_g = 1.0f + e0; else tail_d = -1.0f - e0;
+        const bool full = 2 * p + 1 < S;
+        const f2 e = pk(ex2_approx(v0), full ? ex2_approx(v1) : 0.0f);
+        float d0, d1;
+        unpk(growth ? add2(e, one) : sub2(minus_one, e), d0, d1);
+        const f2 r = pk(rcp_approx(d0), full ? rcp_approx(d1) : 0.0f);
+        if (growth) G.v[p] = r; else ND.v[p] = r;
       }
     }
-    if constexpr ((S & 1) != 0) {
+    if constexpr (MERGE && (S & 1) != 0) {
       const float r = rcp_approx(tail_g * tail_d);
       G.v[NP - 1] = pk(tail_d * r, 0.0f);
       ND.v[NP - 1] = pk(tail_g * r, 0.0f);
@@ -501,21 +544,35 @@ struct LatSmem {
 };
 
 // acc[j0 .. j0+JC) = bias + sum_l W[l][j] z_l  for one chunk of units (z row read through L1: 60-200 bytes, hit
-// after the first chunk)
+// after the first chunk).  Two units per instruction: the staged rows are zero-padded to a multiple of four floats
+// and 16-byte aligned, so a row is read as 16-byte vectors of two weight pairs each.
 template <int JC>
 __device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const float* __restrict__ bias, int HQ, int j0,
                                           const float* __restrict__ zrow, int L, float (&acc)[JC]) {
+  constexpr int J4 = (JC + 3) / 4;  // 16-byte vectors per row
+  f2 a2[2 * J4];
+  const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(bias + j0);
 #pragma unroll
-  for (int j = 0; j < JC; ++j) acc[j] = bias[j0 + j];
+  for (int q = 0; q < J4; ++q) {
+    const ulonglong2 v = b4[q];
+    a2[2 * q] = v.x;
+    a2[2 * q + 1] = v.y;
+  }
   float znext = L > 0 ? __ldg(zrow) : 0.0f;
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
-    const float zl = znext;
+    const f2 zl = bc(znext);
     if (l + 1 < L) znext = ld_early(zrow + l + 1);
-    const float* w = W + l * HQ + j0;
+    const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(W + l * HQ + j0);
 #pragma unroll
-    for (int j = 0; j < JC; ++j) acc[j] = fmaf(w[j], zl, acc[j]);
+    for (int q = 0; q < J4; ++q) {
+      const ulonglong2 v = w4[q];
+      a2[2 * q] = fma2(v.x, zl, a2[2 * q]);
+      a2[2 * q + 1] = fma2(v.y, zl, a2[2 * q + 1]);
+    }
   }
+#pragma unroll
+  for (int j = 0; j < JC; ++j) acc[j] = (j & 1) ? hi_of(a2[j >> 1]) : lo_of(a2[j >> 1]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -523,11 +580,17 @@ __device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const flo
 // ---------------------------------------------------------------------------------------------
 constexpr int kStageT = 4;  // output times staged per trajectory for (B,T,S)-contiguous storage
 
+// shared-memory floats of the per-trajectory tables of a block (narrow layers): c [warp][H][CS], keys [warp][HP][32]
+template <int H, int S>
+__host__ __device__ constexpr size_t table_floats() {
+  return (size_t)kWarps * H * Shape<H, S>::CS + (size_t)kThreads * Shape<H, S>::HP;
+}
+
 template <int H, int S>
 __host__ __device__ constexpr size_t fwd_smem_bytes(int L, bool lat, bool rows_in_time) {
   using SH = Shape<H, S>;
   size_t n = SH::WT;
-  if (!SH::BIG) n += (size_t)kThreads * H + (size_t)kThreads * SH::HP;
+  if (!SH::BIG) n += table_floats<H, S>();
   if (lat) n += LatSmem<H, S>::floats(L);
   if (rows_in_time) n += (size_t)kThreads * kStageT * S;
   return n * sizeof(float);
@@ -545,17 +608,18 @@ __device__ __forceinline__ Tab make_tab(float* smem_tables, unsigned char* ws, i
   using SH = Shape<H, S>;
   Tab tab;
   if constexpr (!SH::BIG) {
-    tab.c = smem_tables + (size_t)warp * H * 32 + lane;
-    tab.k = reinterpret_cast<uint32_t*>(smem_tables + (size_t)kThreads * H) + (size_t)warp * SH::HP * 32 + lane;
+    tab.c = smem_tables + (size_t)warp * H * SH::CS + lane;
+    tab.k = reinterpret_cast<uint32_t*>(smem_tables + (size_t)kWarps * H * SH::CS) + (size_t)warp * SH::HP * 32 + lane;
     tab.fs = nullptr;
-    tab.stride = 32;
+    tab.cs = SH::CS;
+    tab.ks = 32;
   } else {
     constexpr int NS = H <= 128 ? 128 : (H <= 256 ? 256 : 512);
     const size_t nt = (size_t)gridDim.x * kThreads, gt = (size_t)blockIdx.x * kThreads + threadIdx.x;
     tab.c = reinterpret_cast<float*>(ws) + gt;
     tab.k = reinterpret_cast<uint32_t*>(ws + nt * H * 4) + gt;
     tab.fs = ws + nt * H * 4 + nt * (NS + 1) * 4 + gt;
-    tab.stride = (int)nt;
+    tab.cs = tab.ks = (int)nt;
   }
   return tab;
 }
@@ -578,7 +642,7 @@ __device__ __forceinline__ void prologue(const LatSmem<H, S>& ls, const LatentSr
       float acc[JC];
       lat_chunk<JC>(ls.Wz, ls.b1, SH::HQ, j0, zrow, lat.L, acc);
 #pragma unroll
-      for (int j = 0; j < JC; ++j) tab.c[(size_t)(j0 + j) * tab.stride] = acc[j];
+      for (int j = 0; j < JC; ++j) tab.c[(size_t)(j0 + j) * tab.cs] = acc[j];
       if (WANT_X0) {
         lat_chunk<JC>(ls.Wa, ls.ba, SH::HQ, j0, zrow, lat.L, acc);
 #pragma unroll
@@ -600,7 +664,7 @@ __device__ __forceinline__ void prologue(const LatSmem<H, S>& ls, const LatentSr
   } else {
     const float* crow = cin + b * H;
 #pragma unroll 4
-    for (int j = 0; j < H; ++j) tab.c[(size_t)j * tab.stride] = ld_stream(crow + j);
+    for (int j = 0; j < H; ++j) tab.c[(size_t)j * tab.cs] = ld_stream(crow + j);
   }
 }
 
@@ -614,7 +678,7 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
   extern __shared__ __align__(16) float fx_smem[];
   float* const wt = fx_smem;
   float* const tables = wt + SH::WT;
-  float* lat_base = tables + (SH::BIG ? 0 : kThreads * H + kThreads * SH::HP);
+  float* lat_base = tables + (SH::BIG ? 0 : table_floats<H, S>());
   const bool rows_in_time = (st == S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   LatSmem<H, S> ls{};
@@ -675,7 +739,7 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     V<NP> k1;
     if (METHOD == SLODE_METHOD_RK4 && T > 1) {  // k1 of the first step; afterwards carried over from the step before
       V<NP> G, D;
-      pl.eval(t0, G, D);
+      pl.template eval<true>(t0, G, D);
       k1 = rhs<NP>(G, D, x);
     }
     float t_ahead = T > 1 ? __ldg(tgrid + 1) : t0;  // the grid is read one step ahead of its use
@@ -687,32 +751,32 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
       if (METHOD == SLODE_METHOD_EULER) {
         V<NP> G, D;
         pl.seek(wt, tab, t0);
-        pl.eval(t0, G, D);
+        pl.template eval<true>(t0, G, D);
         x = vaxpy<NP>(dt, rhs<NP>(G, D, x), x);
       } else if (METHOD == SLODE_METHOD_MIDPOINT) {
         const float half_dt = 0.5f * dt;
         V<NP> G, D;
         pl.seek(wt, tab, t0);
-        pl.eval(t0, G, D);
+        pl.template eval<true>(t0, G, D);
         const V<NP> ym = vaxpy<NP>(half_dt, rhs<NP>(G, D, x), x);
         const float tm = t0 + half_dt;
         pl.seek(wt, tab, tm);
-        pl.eval(tm, G, D);
+        pl.template eval<true>(tm, G, D);
         x = vaxpy<NP>(dt, rhs<NP>(G, D, ym), x);
       } else {  // rk4, 3/8 rule (torchdiffeq rk4_alt_step_func); the evaluation at t1 is the next step's k1
         V<NP> G, D;
         const float ta = t0 + dt * kOneThird, tb = t0 + dt * kTwoThirds;
         V<NP> y = vaxpy<NP>(dt * kOneThird, k1, x);
         pl.seek(wt, tab, ta);
-        pl.eval(ta, G, D);
+        pl.template eval<true>(ta, G, D);
         const V<NP> k2 = rhs<NP>(G, D, y);
         y = vaxpy<NP>(dt, vaxpy<NP>(-kOneThird, k1, k2), x);
         pl.seek(wt, tab, tb);
-        pl.eval(tb, G, D);
+        pl.template eval<true>(tb, G, D);
         const V<NP> k3 = rhs<NP>(G, D, y);
         y = vaxpy<NP>(dt, vadd<NP>(vsub<NP>(k1, k2), k3), x);
         pl.seek(wt, tab, t1);
-        pl.eval(t1, G, D);
+        pl.template eval<true>(t1, G, D);
         const V<NP> k4 = rhs<NP>(G, D, y);
         x = vaxpy<NP>(dt * 0.125f, vadd<NP>(vaxpy<NP>(3.0f, vadd<NP>(k2, k3), k1), k4), x);
         k1 = rhs<NP>(G, D, x);
@@ -746,7 +810,7 @@ struct GradLayout {
 };
 
 // flip records: per resident thread and hidden unit one snapshot of (P, Q) = 2 * NQ register pairs, stored
-// [thread][unit][P pairs | Q pairs]: a record is one contiguous run written with immediate offsets from a single
+// [thread][unit][q] -> (P[q], Q[q]): a record is one contiguous run written with immediate offsets from a single
 // address (the write sits in a divergent trip that usually serves one lane); the end-of-sweep pass reads a unit's
 // records of all lanes through L1
 template <int H, int S>
@@ -772,15 +836,12 @@ struct Sweep {
   // evaluation and the next one: snapshot the prefix sums as they stand into each unit's record
   __device__ __forceinline__ void events(f2* __restrict__ rec, const Tab& tab, int p0, int p1) {
     for (int p = p0; p < p1; ++p) {
-      const int j = (int)(tab.k[(size_t)p * tab.stride] & SH::IMASK);
-      f2* dst = rec + j * (2 * NQ);
+      const int j = (int)(tab.k[(size_t)p * tab.ks] & SH::IMASK);
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(rec + j * (2 * NQ));
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        dst[q] = P[q];
-        dst[NQ + q] = Q[q];
-      }
+      for (int q = 0; q < NQ; ++q) dst[q] = make_ulonglong2(P[q], Q[q]);  // record: [q] -> (P[q], Q[q])
       if constexpr (SH::BIG) {
-        tab.fs[(size_t)j * tab.stride] |= 2;
+        tab.fs[(size_t)j * tab.ks] |= 2;
       } else {
 #pragma unroll
         for (int w = 0; w < SH::NWR; ++w) {
@@ -811,15 +872,16 @@ template <int H, int S>
 __host__ __device__ constexpr size_t bwd_smem_bytes(int L, bool lat) {
   using SH = Shape<H, S>;
   size_t n = SH::WT;
-  if (!SH::BIG) n += (size_t)kThreads * H + (size_t)kThreads * SH::HP;
-  else n += (size_t)kThreads * SH::JS;               // the warps' transposition buffers
-  n += (size_t)(GradLayout<H, S>::total(L, lat, lat) + 3) / 4 * 4;  // block accumulators
+  if (!SH::BIG) n += table_floats<H, S>();
+  else n += (size_t)kThreads * SH::PQS;              // the warps' exchange buffers
+  if (!SH::BIG) n += (size_t)(GradLayout<H, S>::total(L, lat, lat) + 3) / 4 * 4;  // block accumulators
   if (lat) n += LatSmem<H, S>::floats(L) + (size_t)kThreads * ((L + 3) / 4 * 4);  // staged nets + the warps' z rows
+  n += (size_t)2 * S * kThreads;  // the threads' state / cotangent rows of the interval in flight (cp.async targets)
   return n * sizeof(float);
 }
 
 template <int H, int S, int METHOD, int MODE>
-__global__ void __launch_bounds__(kThreads, (Shape<H, S>::BIG || S > 5) ? 2 : SLODE_FX_BWD_MINB)
+__global__ void __launch_bounds__(kThreads, (Shape<H, S>::BIG || S > 5) ? 2 : (METHOD == SLODE_METHOD_RK4 ? SLODE_FX_BWD_MINB_RK4 : SLODE_FX_BWD_MINB))
 fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                  const float* __restrict__ sol, int64_t st, int64_t sb, const float* __restrict__ gsol, int64_t gst,
                  int64_t gsb, float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,
@@ -834,27 +896,31 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
   const bool fused = lat.z != nullptr, fx0 = fused && lat.Wa != nullptr;
   float* const wt = fx_smem;
   float* const tables = wt + SH::WT;
-  float* p_ = tables + (SH::BIG ? kThreads * SH::JS : kThreads * H + kThreads * SH::HP);
-  float* const acc = p_;
-  const int n_acc = GL::total(L, fused, fx0);
-  p_ += (GL::total(L, fused, fused) + 3) / 4 * 4;  // keeps the float4 rows behind it 16-byte aligned
+  float* p_ = tables + (SH::BIG ? (size_t)kThreads * SH::PQS : table_floats<H, S>());
+  // parameter-gradient sums: block accumulators in shared memory, flushed once at the end -- except for wide layers,
+  // whose 25k-100k sums do not fit next to the staged weights and are added to grad_params directly
+  float* const acc = SH::BIG ? grad_w : p_;
+  const int n_acc = SH::BIG ? 0 : GL::total(L, fused, fx0);
+  if (!SH::BIG) p_ += (GL::total(L, fused, fused) + 3) / 4 * 4;  // keeps the float4 rows behind it 16-byte aligned
   LatSmem<H, S> ls{};
   float* zT = nullptr;  // this warp's z rows, [32][LQ]
   const int LQ = (L + 3) / 4 * 4;
   if (fused) {
     ls.stage(p_, lat);
     zT = p_ + LatSmem<H, S>::floats(L) + (size_t)warp * 32 * LQ;
+    p_ += LatSmem<H, S>::floats(L) + (size_t)kThreads * LQ;
   }
+  float* const rowx = p_ + tid;                 // this thread's state row of the interval in flight
+  float* const rowg = p_ + S * kThreads + tid;  // ... and its upstream-gradient row
   stage_weights<H, S>(wt, w.w1t, w1t_stride, w.Wg, w.bg, w.Wd, w.bd);
   for (int i = tid; i < n_acc; i += kThreads) acc[i] = 0.0f;
   __syncthreads();
   const size_t nthreads = (size_t)gridDim.x * kThreads, gthread = (size_t)blockIdx.x * kThreads + tid;
   const Tab tab = make_tab<H, S>(tables, ws, warp, lane);
   f2* const rec = reinterpret_cast<f2*>(ws + big_tab_bytes<H, S>() * nthreads) + gthread * (size_t)(H * 2 * NQ);
-  // the warp's transposition buffer [32][JS]: the key table's rows once the walk is over (narrow layers), else
-  // its own region
-  float* const dcT = SH::BIG ? tables + (size_t)warp * 32 * SH::JS
-                             : tables + (size_t)kThreads * H + (size_t)warp * SH::HP * 32;
+  // the warp's exchange buffer [32][PQS]: the key table's rows once the walk is over (narrow layers), else its own
+  float* const pqw = SH::BIG ? tables + (size_t)warp * 32 * SH::PQS
+                             : tables + (size_t)kWarps * H * SH::CS + (size_t)warp * SH::HP * 32;
   // the reverse sweep visits the grid from its last time to its first
   const float dir = (T < 2 || __ldg(tgrid + T - 1) >= __ldg(tgrid)) ? -1.0f : 1.0f;
   const int64_t ntiles = (B + kThreads - 1) / kThreads;
@@ -868,6 +934,11 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     }
     const float* xs = sol + b * sb;
     const float* gs = gsol + b * gsb;
+    if (fused && tile + gridDim.x < ntiles) {  // the next tile's latent row: in L2 by the time its prologue reads it
+      const int64_t bn = min(br + (int64_t)gridDim.x * kThreads, B - 1);
+      prefetch_l2(lat.z + bn * L);
+      prefetch_l2(lat.z + bn * L + L - 1);
+    }
     const float live = ok ? 1.0f : 0.0f;   // a masked-off thread carries zero cotangents: it only adds zeros
     V<NP> lam = vscale<NP>(vload<S>(gs + (int64_t)(T - 1) * gst), live);
 
@@ -889,28 +960,45 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
         if (METHOD == SLODE_METHOD_MIDPOINT) tfirst = tp + 0.5f * (t1 - tp);
       }
       pl.init(wt, tab, tfirst, dir, first);
-      if (METHOD == SLODE_METHOD_RK4) pl.eval(t1, Gc, Dc);
+      if (METHOD == SLODE_METHOD_RK4) pl.template eval<false>(t1, Gc, Dc);
     }
 
     float t_ahead = T > 1 ? __ldg(tgrid + T - 2) : t1;  // the grid is read one interval ahead of its use
+    // The state row the interval needs (sol[i]; sol[i+1] for the odeint_adjoint restart) and the cotangent row of
+    // grid point i are fetched ONE INTERVAL AHEAD with cp.async into the thread's own shared-memory column: read at
+    // the point of use they cost a full L2 round trip per interval (12 % of the sweep's stall samples;
+    // prefetch.global.L1 does not help the read-only path), forced early into registers they occupy 12 registers
+    // for a whole interval and make the evaluator's shared-memory waits wait for them too (shared scoreboards).
+    // Groups are committed in the order state(i), cotangent(i), state(i-1), ...: each read waits for all but the
+    // newest group.
+    constexpr int kStateAhead = (MODE == SLODE_BWD_DISCRETE) ? 0 : 1;
+    const float* px = xs + (int64_t)(T - 2 + kStateAhead) * st;   // running pointers: no 64-bit multiplies in the loop
+    const float* pg = gs + (int64_t)(T - 2) * gst;
+    if (T > 1) {
+      row_fetch<S>(rowx, px);
+      cp_commit();
+      row_fetch<S>(rowg, pg);
+      cp_commit();
+    }
 #pragma unroll 1
     for (int i = T - 2; i >= 0; --i) {
       const float t0 = t_ahead;
       if (i > 0) t_ahead = ld_early(tgrid + i - 1);
-      // state and cotangent rows of grid point i were pulled into L1 one interval ago; they are loaded where they
-      // are used (forcing the loads up here made the evaluator's first shared-memory wait also wait for them:
-      // loads issued together share a scoreboard)
-      const V<NP> x = vload<S>(xs + (int64_t)i * st);
-      if (i > 0) {  // next interval's state and cotangent rows: in L1 by the time they are read
-        vprefetch<S>(xs + (int64_t)(i - 1) * st);
-        vprefetch<S>(gs + (int64_t)(i - 1) * gst);
-      }
+      auto state_row = [&]() {  // the interval's state row; its slot is refilled for the next interval at once
+        cp_wait<1>();
+        const V<NP> r = row_read<S>(rowx);
+        px -= st;
+        if (i > 0) row_fetch<S>(rowx, px);
+        cp_commit();
+        return r;
+      };
       if (MODE == SLODE_BWD_DISCRETE) {
         const float dt = t1 - t0;
         if (METHOD == SLODE_METHOD_EULER) {
           V<NP> G, D;
           pl.seek(wt, tab, t0);
-          pl.eval(t0, G, D);
+          pl.template eval<false>(t0, G, D);
+          const V<NP> x = state_row();
           const V<NP> gk = vscale<NP>(lam, dt);
           sw.events(rec, tab, pdone, pl.pos);
           pdone = pl.pos;
@@ -922,9 +1010,10 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
           V<NP> G1, D1, G0, D0;
           pl.seek(wt, tab, tm);
           const int pm = pl.pos;
-          pl.eval(tm, G1, D1);
+          pl.template eval<false>(tm, G1, D1);
           pl.seek(wt, tab, t0);
-          pl.eval(t0, G0, D0);
+          pl.template eval<false>(t0, G0, D0);
+          const V<NP> x = state_row();
           const V<NP> ym = vaxpy<NP>(half_dt, rhs<NP>(G0, D0, x), x);
           V<NP> gk = vscale<NP>(lam, dt);  // dL/dk2
           sw.events(rec, tab, pdone, pm);
@@ -942,12 +1031,13 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
           V<NP> G2, D2, G1, D1, G0, D0;
           pl.seek(wt, tab, tb);
           const int pb = pl.pos;
-          pl.eval(tb, G2, D2);
+          pl.template eval<false>(tb, G2, D2);
           pl.seek(wt, tab, ta);
           const int pa = pl.pos;
-          pl.eval(ta, G1, D1);
+          pl.template eval<false>(ta, G1, D1);
           pl.seek(wt, tab, t0);
-          pl.eval(t0, G0, D0);
+          pl.template eval<false>(t0, G0, D0);
+          const V<NP> x = state_row();
           V<NP> Y2, Y3, Y4;
           {
             const V<NP> k1 = rhs<NP>(G0, D0, x);
@@ -991,11 +1081,11 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
         // [y, a, a_theta] from t1 down to t0, y restarted from the stored sol[i+1].  In reversed time s=-t the
         // step is ds = t1 - t0 > 0 with  Ky = D*y - A,  Ka = -a*D,  a_theta += w_m * a_m^T df/dtheta(t_m, y_m).
         const float ds = t1 - t0;
-        const V<NP> y = vload<S>(xs + (int64_t)(i + 1) * st);
+        const V<NP> y = state_row();
         if (METHOD == SLODE_METHOD_EULER) {
           V<NP> G, D;
           pl.seek(wt, tab, t1);
-          pl.eval(t1, G, D);
+          pl.template eval<false>(t1, G, D);
           const V<NP> v = vscale<NP>(lam, ds);
           sw.events(rec, tab, pdone, pl.pos);
           pdone = pl.pos;
@@ -1006,9 +1096,9 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
           const float tm = t1 - half;
           V<NP> G1, D1, Gm, Dm;
           pl.seek(wt, tab, t1);   // the stage at t1 has weight 0 in a_theta: its flips are recorded with the next
-          pl.eval(t1, G1, D1);
+          pl.template eval<false>(t1, G1, D1);
           pl.seek(wt, tab, tm);
-          pl.eval(tm, Gm, Dm);
+          pl.template eval<false>(tm, Gm, Dm);
           const V<NP> ym = vaxpy<NP>(-half, rhs<NP>(G1, D1, y), y);  // y + half*(D1*y - A1)
           const V<NP> am = vaxpy<NP>(half, vmul<NP>(lam, D1), lam);  // a + half*(-a*D1), D holds -sigmoid
           const V<NP> v = vscale<NP>(am, ds);
@@ -1022,12 +1112,12 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
           V<NP> G0, D0, G1, D1, G2, D2;
           pl.seek(wt, tab, ta);
           const int pa = pl.pos;
-          pl.eval(ta, G0, D0);
+          pl.template eval<false>(ta, G0, D0);
           pl.seek(wt, tab, tb);
           const int pb = pl.pos;
-          pl.eval(tb, G1, D1);
+          pl.template eval<false>(tb, G1, D1);
           pl.seek(wt, tab, t0);
-          pl.eval(t0, G2, D2);
+          pl.template eval<false>(t0, G2, D2);
           // stage 1 at t1 (carried evaluation)
           const V<NP> f1 = rhs<NP>(Gc, Dc, y);
           const V<NP> ka1 = vmul<NP>(lam, Dc);
@@ -1059,168 +1149,234 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
           Dc = D2;
         }
       }
-      lam = vadd<NP>(lam, vscale<NP>(vload<S>(gs + (int64_t)i * gst), live));
+      cp_wait<1>();
+      lam = vadd<NP>(lam, vscale<NP>(row_read<S>(rowg), live));
+      pg -= gst;
+      if (i > 0) row_fetch<S>(rowg, pg);
+      cp_commit();
       t1 = t0;
     }
 
-    // ---- end of the sweep: per hidden unit (uniform loop, all lanes busy) combine the recorded and the final
-    // prefix sums into the sums over the evaluations where the unit was active,
+    // ---- end of the sweep.  For every (trajectory, hidden unit) combine the recorded and the final prefix sums
+    // into the sums over the evaluations where the unit was active,
     //     active throughout: final      turned off: record      turned on: final - record      never: 0
-    // and turn them into dc_j (per trajectory), dw1t_j and dW_oj (warp reduction, one shared atomic per warp and
-    // value).  Units are taken in chunks of JC; each chunk's dc_j goes through the warp's transposition buffer
-    // into the fused small-net gradients.
-    constexpr int JC = SH::JC, JS = SH::JS;
+    // and turn them into dc_j (per trajectory), dw1t_j and dW_oj (sums over trajectories).  The warp switches
+    // from "lane = trajectory" to "lane = hidden unit": it walks its 32 trajectories one after the other with
+    // every lane holding ITS unit's sums in registers, so no cross-lane reduction is needed at all (round 1 and the
+    // first version of this kernel spent ~10 % of their instructions in shuffle reductions here).  What the lanes
+    // exchange goes through shared memory: each trajectory's final (P, Q) in the warp's key-table region (the walk
+    // is over), dc_j written IN PLACE over c_j (element (j, trajectory) of the c table, stride odd: conflict-free
+    // both ways), z rows in the warp's zT.
+    constexpr int JC = SH::JC, JS = SH::JS, PQS = SH::PQS;
     constexpr int KR = (2 * NQ + 1 <= 16) ? 16 : 32;
     static_assert(2 * NQ + 1 <= 32, "state dimension");
-    if (fused) {
-      // this warp's z rows -> zT[lane][l]
+    // head biases: total of the cotangents over all evaluations (P is still in registers)
+    {
+      float red[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) red[k] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) unpk(sw.P[q], red[2 * q], red[2 * q + 1]);
+      warp_reduce_to<KR>(red, lane, [&](int slot) -> float* {
+        if (slot >= 2 * NQ) return nullptr;
+        const int q = slot >> 1, h = slot & 1;
+        const bool growth = q < NP;
+        const int s = 2 * (growth ? q : q - NP) + h;
+        if (s >= S) return nullptr;
+        return acc + (growth ? GL::bg : GL::bd) + s;
+      });
+    }
+    __syncwarp();  // every lane is done with the key table: it becomes the (P, Q) exchange buffer
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float p0, p1, q0, q1;
+      unpk(sw.P[q], p0, p1);
+      unpk(sw.Q[q], q0, q1);
+      reinterpret_cast<float4*>(pqw + lane * PQS)[q] = make_float4(p0, p1, q0, q1);
+    }
+    if (fused) {  // this warp's z rows -> zT[lane][l]
       const float* zrow = lat.z + b * L;
       for (int l = 0; l < LQ; ++l) zT[lane * LQ + l] = l < L ? __ldg(zrow + l) : 0.0f;
     }
-    __syncwarp();  // (also: every lane is done with the key table before it is overwritten below)
+    __syncwarp();
 
     const float* recs = wt + SH::BIAS;
+    float* const cw = tab.c - lane;                 // element (j, trajectory bb of this warp) at cw[j * stride + bb]
+    const f2* const rec0 = rec - (size_t)lane * (H * 2 * NQ);  // thread bb's records start at rec0 + bb * H * 2NQ
+    // weight-gradient outer products of one chunk of units with the z rows: lane <-> unit j0 + lane,
+    //   gW[j][l] (row stride L) += sum_bb val(bb) * z[bb][l],   gb[j] += sum_bb val(bb)
+    auto outer = [&](int j0, auto val, float* gW, float* gb) {
+      for (int l0 = 0; l0 < L; l0 += 16) {
+        float a[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = 0.0f;
+        float sb_ = 0.0f;
+#pragma unroll 2
+        for (int bb_ = 0; bb_ < 32; ++bb_) {
+          const float d = val(bb_);
+          sb_ += d;
+          const float4* zr = reinterpret_cast<const float4*>(zT + bb_ * LQ + l0);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            if (l0 + 4 * k4 < L) {
+              const float4 zz = zr[k4];
+              a[4 * k4] = fmaf(d, zz.x, a[4 * k4]);
+              a[4 * k4 + 1] = fmaf(d, zz.y, a[4 * k4 + 1]);
+              a[4 * k4 + 2] = fmaf(d, zz.z, a[4 * k4 + 2]);
+              a[4 * k4 + 3] = fmaf(d, zz.w, a[4 * k4 + 3]);
+            }
+          }
+        }
+        if (lane < JC) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            if (l0 + k < L) atomicAdd(gW + (j0 + lane) * L + l0 + k, a[k]);
+          }
+          if (l0 == 0) atomicAdd(gb + j0 + lane, sb_);
+        }
+      }
+    };
+    // per trajectory (lane <-> trajectory): grad_z[b][l] (+)= sum_jj Wl[l][j0 + jj] * val(jj); the weight rows are
+    // read as float4 over the units (broadcast); partial sums of later chunks / the second net go through grad_z
+    // itself (the row stays in L1)
+    auto dz_from = [&](int j0, auto val, const float* Wl, bool accumulate) {
+      constexpr int JC4 = (JC + 3) / 4 * 4;
+      float d[JC4];
+#pragma unroll
+      for (int jj = 0; jj < JC4; ++jj) d[jj] = jj < JC ? val(jj) : 0.0f;
+      float* gzrow = grad_z + b * L;
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const float4* wr = reinterpret_cast<const float4*>(Wl + l * SH::HQ + j0);
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int q4 = 0; q4 < JC4 / 4; ++q4) {
+          const float4 ww = wr[q4];
+          a0 = fmaf(ww.x, d[4 * q4], a0);
+          a1 = fmaf(ww.y, d[4 * q4 + 1], a1);
+          a0 = fmaf(ww.z, d[4 * q4 + 2], a0);
+          a1 = fmaf(ww.w, d[4 * q4 + 3], a1);
+        }
+        if (ok) gzrow[l] = (accumulate ? gzrow[l] : 0.0f) + (a0 + a1);
+      }
+    };
+
 #pragma unroll 1
     for (int j0 = 0; j0 < H; j0 += JC) {
-      // ---- pass 1 of the chunk: dc_j per lane, weight-gradient sums over the warp
-#pragma unroll 1
-      for (int jj = 0; jj < JC; ++jj) {
-        const int j = j0 + jj;
-        bool f, fl;
+      // ---- dynamics part of the chunk, lane <-> unit
+      const bool act = lane < JC;
+      const int j = act ? j0 + lane : j0;   // idle lanes shadow unit j0 with zero weights
+      const float* wrec = recs + j * SH::UNIT;
+      f2 wq[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) wq[q] = act ? reinterpret_cast<const f2*>(wrec)[q] : 0ull;
+      const f2 wj = bc(act ? wrec[2 * NQ] : 0.0f);
+      f2 racc[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) racc[q] = 0ull;
+      float rw1t = 0.0f;
+      // status of unit j along trajectory bb: gate at the first evaluation, flipped since
+      auto flags = [&](int bb, bool& f, bool& fl) {
         if constexpr (SH::BIG) {
-          const uint8_t sbits = T > 1 ? tab.fs[(size_t)j * tab.stride] : 0;
+          const uint8_t sbits = T > 1 ? (tab.fs - lane)[(size_t)j * tab.ks + bb] : 0;
           f = sbits & 1;
           fl = sbits & 2;
         } else {
-          uint32_t fw = first[0], lw = sw.flipped[0];
+          uint32_t fw = __shfl_sync(0xffffffffu, first[0], bb), lw = __shfl_sync(0xffffffffu, sw.flipped[0], bb);
 #pragma unroll
           for (int ww = 1; ww < SH::NWR; ++ww) {
-            if ((j >> 5) == ww) { fw = first[ww]; lw = sw.flipped[ww]; }
+            const uint32_t fw2 = __shfl_sync(0xffffffffu, first[ww], bb);
+            const uint32_t lw2 = __shfl_sync(0xffffffffu, sw.flipped[ww], bb);
+            if ((j >> 5) == ww) { fw = fw2; lw = lw2; }
           }
           f = (fw >> (j & 31)) & 1u;
           fl = (lw >> (j & 31)) & 1u;
         }
-        const bool last = f != fl;
-        const f2 ar = bc(fl ? (f ? 1.0f : -1.0f) : 0.0f), af = bc(last ? 1.0f : 0.0f);
-        const float* wrec = recs + j * SH::UNIT;
-        const f2 wj = bc(wrec[2 * NQ]);
-        const f2 cj = bc(tab.c[(size_t)j * tab.stride]);
-        f2 s1 = 0ull, s2 = 0ull;
-        float red[KR];
-#pragma unroll
-        for (int k = 0; k < KR; ++k) red[k] = 0.0f;
-        const f2* src = rec + j * (2 * NQ);
+      };
+      // the record of unit j written by trajectory bb (zeros if the unit never flipped there)
+      auto fetch = [&](int bb, bool fl, ulonglong2 (&r)[NQ]) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(rec0 + ((size_t)bb * H + j) * (2 * NQ));
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          f2 rp = 0ull, rq = 0ull;
-          if (fl) {
-            rp = src[q];
-            rq = src[NQ + q];
-          }
-          const f2 pe = fma2(ar, rp, mul2(af, sw.P[q]));
-          const f2 qe = fma2(ar, rq, mul2(af, sw.Q[q]));
-          const f2 wq = reinterpret_cast<const f2*>(wrec)[q];
-          s1 = fma2(wq, pe, s1);
-          s2 = fma2(wq, qe, s2);
-          unpk(fma2(wj, qe, mul2(cj, pe)), red[2 * q], red[2 * q + 1]);
-        }
-        const float dc = kNegLn2 * (lo_of(s1) + hi_of(s1));   // packed head weights are scaled by -log2(e)
-        red[2 * NQ] = kNegLn2 * (lo_of(s2) + hi_of(s2));
-        if (fused) {
-          dcT[lane * JS + jj] = dc;
-        } else if (ok) {
-          grad_c[b * H + j] = dc;
-        }
-        warp_reduce_to<KR>(red, lane, [&](int slot) -> float* {
-          if (slot == 2 * NQ) return acc + GL::w1t + j;
-          if (slot > 2 * NQ) return nullptr;
-          const int q = slot >> 1, h = slot & 1;
-          const bool growth = q < NP;
-          const int s = 2 * (growth ? q : q - NP) + h;
-          if (s >= S) return nullptr;
-          return acc + (growth ? GL::Wg : GL::Wd) + s * H + j;
-        });
-      }
-      if (!fused) continue;
-      __syncwarp();
-      // ---- pass 2: lane <-> unit j0 + lane.  dW1z[j][l] += sum_b dc[b][j] z[b][l],  db1[j] += sum_b dc[b][j];
-      //      per trajectory (discrete mode) dz_l += sum_j W1z[l][j] dc_j
-      auto outer = [&](float* gW, float* gb) {
-        // gW[j][l] (row stride L) += sum_b buf[b][lane] * z[b][l]
-        for (int l0 = 0; l0 < L; l0 += 16) {
-          float a[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) a[k] = 0.0f;
-          float sb_ = 0.0f;
-#pragma unroll 2
-          for (int bb_ = 0; bb_ < 32; ++bb_) {
-            const float d = lane < JC ? dcT[bb_ * JS + lane] : 0.0f;
-            sb_ += d;
-            const float4* zr = reinterpret_cast<const float4*>(zT + bb_ * LQ + l0);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              if (l0 + 4 * k4 < L) {
-                const float4 zz = zr[k4];
-                a[4 * k4] = fmaf(d, zz.x, a[4 * k4]);
-                a[4 * k4 + 1] = fmaf(d, zz.y, a[4 * k4 + 1]);
-                a[4 * k4 + 2] = fmaf(d, zz.z, a[4 * k4 + 2]);
-                a[4 * k4 + 3] = fmaf(d, zz.w, a[4 * k4 + 3]);
-              }
-            }
-          }
-          if (lane < JC) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              if (l0 + k < L) atomicAdd(gW + (j0 + lane) * L + l0 + k, a[k]);
-            }
-            if (l0 == 0) atomicAdd(gb + j0 + lane, sb_);
-          }
+          r[q] = make_ulonglong2(0ull, 0ull);
+          if (fl) r[q] = src[q];
         }
       };
-      auto dz_from = [&](const float* Wl, bool accumulate) {
-        // grad_z[b][l] (+)= sum_jj Wl[l][j0 + jj] * buf[lane][jj]:  the trajectory's row of the buffer in registers,
-        // the weight rows read as float4 over the units (broadcast); partial sums of later chunks / the second net
-        // go through grad_z itself (the row stays in L1)
-        constexpr int JC4 = (JC + 3) / 4 * 4;
-        float d[JC4];
-#pragma unroll
-        for (int jj = 0; jj < JC4; ++jj) d[jj] = jj < JC ? dcT[lane * JS + jj] : 0.0f;
-        float* gzrow = grad_z + b * L;
+      bool f_next, fl_next;
+      ulonglong2 r_next[NQ];
+      flags(0, f_next, fl_next);
+      fetch(0, fl_next, r_next);
 #pragma unroll 1
-        for (int l = 0; l < L; ++l) {
-          const float4* wr = reinterpret_cast<const float4*>(Wl + l * SH::HQ + j0);
-          float a0 = 0.0f, a1 = 0.0f;
+      for (int bb = 0; bb < 32; ++bb) {
+        const bool f = f_next, fl = fl_next;
+        ulonglong2 r_cur[NQ];
 #pragma unroll
-          for (int q4 = 0; q4 < JC4 / 4; ++q4) {
-            const float4 ww = wr[q4];
-            a0 = fmaf(ww.x, d[4 * q4], a0);
-            a1 = fmaf(ww.y, d[4 * q4 + 1], a1);
-            a0 = fmaf(ww.z, d[4 * q4 + 2], a0);
-            a1 = fmaf(ww.w, d[4 * q4 + 3], a1);
-          }
-          if (ok) gzrow[l] = (accumulate ? gzrow[l] : 0.0f) + (a0 + a1);
+        for (int q = 0; q < NQ; ++q) r_cur[q] = r_next[q];
+        if (bb + 1 < 32) {  // the next trajectory's record is in flight while this one is processed
+          flags(bb + 1, f_next, fl_next);
+          fetch(bb + 1, fl_next, r_next);
         }
-      };
-      outer(acc + GL::W1z(L), acc + GL::b1(L));
-      // dz through c (discrete mode only: odeint_adjoint gives z no gradient through the dynamics)
-      if (MODE == SLODE_BWD_DISCRETE) {
-        dz_from(ls.Wz, j0 != 0);
-      } else if (j0 == 0 && ok) {
-        for (int l = 0; l < L; ++l) grad_z[b * L + l] = 0.0f;
+        const bool last = f != fl;
+        const f2 ar = bc(fl ? (f ? 1.0f : -1.0f) : 0.0f), af = bc(last ? 1.0f : 0.0f);
+        const f2 cj = bc(cw[(size_t)j * tab.cs + bb]);
+        const float4* pq4 = reinterpret_cast<const float4*>(pqw + bb * PQS);
+        f2 s1 = 0ull, s2 = 0ull;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 v = pq4[q];
+          const f2 pe = fma2(ar, r_cur[q].x, mul2(af, pk(v.x, v.y)));
+          const f2 qe = fma2(ar, r_cur[q].y, mul2(af, pk(v.z, v.w)));
+          s1 = fma2(wq[q], pe, s1);
+          s2 = fma2(wq[q], qe, s2);
+          racc[q] = fma2(wj, qe, fma2(cj, pe, racc[q]));
+        }
+        rw1t = fmaf(kNegLn2, lo_of(s2) + hi_of(s2), rw1t);  // packed head weights are scaled by -log2(e)
+        if (act) cw[(size_t)j * tab.cs + bb] = kNegLn2 * (lo_of(s1) + hi_of(s1));  // dc_j of trajectory bb, in place
+      }
+      if (act) {
+        atomicAdd(acc + GL::w1t + j, rw1t);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const bool growth = q < NP;
+          const int s0 = 2 * (growth ? q : q - NP);
+          float r0, r1;
+          unpk(racc[q], r0, r1);
+          atomicAdd(acc + (growth ? GL::Wg : GL::Wd) + s0 * H + j, r0);
+          if (s0 + 1 < S) atomicAdd(acc + (growth ? GL::Wg : GL::Wd) + (s0 + 1) * H + j, r1);
+        }
       }
       __syncwarp();
-      if (fx0) {
-        // ---- x0 net: da_j = [ha_j > 0] sum_s Wb[s][j] db_s,  db = dL/dx0 * x0 (1 - x0);  hr_j = relu(ha_j)
-        const V<NP> x0 = vload<S>(xs);
-        float db[S];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          float l0_, l1_, a0, a1;
-          unpk(lam.v[p], l0_, l1_);
-          unpk(x0.v[p], a0, a1);
-          db[2 * p] = l0_ * (a0 - a0 * a0);
-          if (2 * p + 1 < S) db[2 * p + 1] = l1_ * (a1 - a1 * a1);
+      if (fused) {
+        // dW1z[j][l] += sum_bb dc[bb][j] z[bb][l],  db1[j] += sum_bb dc[bb][j]
+        outer(j0, [&](int bb_) { return lane < JC ? cw[(size_t)(j0 + lane) * tab.cs + bb_] : 0.0f; },
+              acc + GL::W1z(L), acc + GL::b1(L));
+        // dz through c (discrete mode only: odeint_adjoint gives z no gradient through the dynamics)
+        if (MODE == SLODE_BWD_DISCRETE) {
+          dz_from(j0, [&](int jj) { return cw[(size_t)(j0 + jj) * tab.cs + lane]; }, ls.Wz, j0 != 0);
+        } else if (j0 == 0 && ok) {
+          for (int l = 0; l < L; ++l) grad_z[b * L + l] = 0.0f;
         }
+      } else if (ok) {
+#pragma unroll 4
+        for (int jj = 0; jj < JC; ++jj) grad_c[b * H + j0 + jj] = cw[(size_t)(j0 + jj) * tab.cs + lane];
+      }
+    }
+    __syncwarp();  // the (P, Q) exchange buffer is free: it serves as the x0 net's transposition buffer [32][JS]
+    if (fx0) {
+      // ---- x0 net: da_j = [ha_j > 0] sum_s Wb[s][j] db_s,  db = dL/dx0 * x0 (1 - x0);  hr_j = relu(ha_j)
+      float* const dcT = pqw;
+      const V<NP> x0 = vload<S>(xs);
+      float db[S];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        float l0_, l1_, a0, a1;
+        unpk(lam.v[p], l0_, l1_);
+        unpk(x0.v[p], a0, a1);
+        db[2 * p] = l0_ * (a0 - a0 * a0);
+        if (2 * p + 1 < S) db[2 * p + 1] = l1_ * (a1 - a1 * a1);
+      }
+#pragma unroll 1
+      for (int j0 = 0; j0 < H; j0 += JC) {
         float ha[JC];
         lat_chunk<JC>(ls.Wa, ls.ba, SH::HQ, j0, lat.z + b * L, L, ha);
         // da -> buffer
@@ -1232,8 +1388,8 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
           dcT[lane * JS + jj] = ha[jj] > 0.0f ? a * live : 0.0f;
         }
         __syncwarp();
-        outer(acc + GL::Wa(L), acc + GL::ba(L));
-        dz_from(ls.Wa, true);
+        outer(j0, [&](int bb_) { return lane < JC ? dcT[bb_ * JS + lane] : 0.0f; }, acc + GL::Wa(L), acc + GL::ba(L));
+        dz_from(j0, [&](int jj) { return dcT[lane * JS + jj]; }, ls.Wa, true);
         __syncwarp();
         // hr -> buffer;  dWb[s][j] += sum_b db[b][s] hr[b][j]
 #pragma unroll
@@ -1254,33 +1410,14 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
             for (int s = 0; s < S; ++s) atomicAdd(acc + GL::Wb(L) + s * H + j0 + lane, a[s]);
           }
         }
-        if (j0 == 0) {
-          float v[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = k < S ? db[k < S ? k : 0] * live : 0.0f;
-          warp_reduce_to<16>(v, lane, [&](int slot) -> float* { return slot < S ? acc + GL::bb(L) + slot : nullptr; });
-        }
         __syncwarp();
       }
-    }
-    // head biases: total of the cotangents over all evaluations
-    {
-      float red[KR];
+      {
+        float v[16];
 #pragma unroll
-      for (int k = 0; k < KR; ++k) red[k] = 0.0f;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) unpk(sw.P[q], red[2 * q], red[2 * q + 1]);
-      warp_reduce_to<KR>(red, lane, [&](int slot) -> float* {
-        if (slot >= 2 * NQ) return nullptr;
-        const int q = slot >> 1, h = slot & 1;
-        const bool growth = q < NP;
-        const int s = 2 * (growth ? q : q - NP) + h;
-        if (s >= S) return nullptr;
-        return acc + (growth ? GL::bg : GL::bd) + s;
-      });
-    }
-    if (fused && T <= 1 && ok && MODE == SLODE_BWD_DISCRETE && !fx0) {
-      // no evaluation at all: the loops above wrote zeros already
+        for (int k = 0; k < 16; ++k) v[k] = k < S ? db[k < S ? k : 0] * live : 0.0f;
+        warp_reduce_to<16>(v, lane, [&](int slot) -> float* { return slot < S ? acc + GL::bb(L) + slot : nullptr; });
+      }
     }
     if (!fx0) vstore<S>(grad_y0 + b * S, ok, lam);
     __syncwarp();  // the transposition buffer doubles as the next tile's key table
