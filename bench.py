@@ -57,25 +57,10 @@ def algorithmic_flops(method: str, T: int, H: int, S: int):
     return float(fwd), float(bwd)
 
 
-def algorithmic_bytes(T: int, H: int, S: int, method: str = "rk4", ckpt: bool = False):
+def algorithmic_bytes(T: int, H: int, S: int, method: str = "rk4"):
     """(forward, backward) HBM bytes per trajectory of the fused path: fwd reads z (L), writes sol (T*S);
-    bwd reads sol + grad_sol + z, writes grad_z.  With evaluation checkpoints the forward also writes, and the
-    reverse sweep reads, 2S floats per MLP evaluation."""
-    evals = {"euler": T - 1, "midpoint": 2 * (T - 1), "rk4": 3 * (T - 1) + 1}[method]
-    ck = 4.0 * evals * 2 * S if ckpt else 0.0
-    return 4.0 * (L + T * S) + ck, 4.0 * (2 * T * S + 2 * L) + ck
-
-
-def checkpointed_bwd_flops(method: str, T: int, H: int, S: int):
-    """Reverse sweep with evaluation checkpoints: hidden-layer gates (2H per evaluation), stage recompute from the
-    stored sigmoids, adjoint recurrences, prefix sums, epilogue -- no head products."""
-    steps = T - 1
-    stages = {"euler": 1, "midpoint": 2, "rk4": 4}[method]
-    evals = {"euler": steps, "midpoint": 2 * steps, "rk4": 3 * steps + 1}[method]
-    combine = {"euler": 2 * S, "midpoint": 4 * S, "rk4": 16 * S}[method]
-    return float(evals * 2 * H + steps * (stages * 2 * S + combine) + steps * stages * 24 * S + H * 2 * (14 * 2 * S)
-                 + 2 * (4 * L * H + 2 * H * S))
-
+    bwd reads sol + grad_sol + z, writes grad_z."""
+    return 4.0 * (L + T * S), 4.0 * (2 * T * S + 2 * L)
 
 
 def pl_flops(method: str, T: int, H: int, S: int):
@@ -94,11 +79,11 @@ def pl_flops(method: str, T: int, H: int, S: int):
     return float(fwd), float(bwd)
 
 
-def sfu_ops(method: str, T: int, S: int):
-    """MUFU lane-operations per trajectory and solve: 2S sigmoids per evaluation, each one ex2 and -- two
-    denominators sharing one reciprocal -- half an rcp."""
+def sfu_ops(method: str, T: int, S: int, merged: bool):
+    """MUFU lane-operations per trajectory and solve: 2S sigmoids per evaluation, each one ex2 and one rcp -- half an
+    rcp in the forward kernel, where two denominators share one reciprocal."""
     evals = {"euler": T - 1, "midpoint": 2 * (T - 1), "rk4": 3 * (T - 1) + 1}[method]
-    return float(evals * 3 * S)
+    return float(evals * (3 if merged else 4) * S)
 
 
 XU_PEAK_TOPS = 148 * 16 * 1.965e9 / 1e12  # 16 MUFU lanes per SM and clock
@@ -171,16 +156,20 @@ def seeded_port_model(method, adjoint):
     return slode_port.OdeModel(times, S, L, H, adjoint, method)
 
 
-def cpu_reference_step(model, heads_w, z, y):
-    """One fwd+bwd of the reference algorithm on the host: x0 net, torchdiffeq-style solve, q50 head, MSE, backward."""
+def cpu_reference_step(model, heads_w, z, y, backward=True):
+    """One step of the reference algorithm on the host: x0 net, torchdiffeq-style solve, q50 head, MSE (, backward)."""
     model.zero_grad()
+    if not backward:
+        with torch.no_grad():
+            sol = model.solve_ODE(z)
+            return float(((sol @ heads_w.t()) - y).square().mean())
     sol = model.solve_ODE(z)
     loss = ((sol @ heads_w.t()) - y).square().mean()
     loss.backward()
     return float(loss.detach())
 
 
-def time_cpu_reference(method, adjoint, B, reps, warmup=1):
+def time_cpu_reference(method, adjoint, B, reps, warmup=1, backward=True):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     model = seeded_port_model(method, adjoint)
@@ -189,13 +178,30 @@ def time_cpu_reference(method, adjoint, B, reps, warmup=1):
     y = torch.rand(B, T, O, generator=g)
     Wq = torch.randn(O, S, generator=g) * 0.3
     for _ in range(warmup):
-        cpu_reference_step(model, Wq, z, y)
+        cpu_reference_step(model, Wq, z, y, backward)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_reference_step(model, Wq, z, y)
+        cpu_reference_step(model, Wq, z, y, backward)
         times.append(time.perf_counter() - t0)
     return times, cores
+
+
+def cpu_baseline_table(method, budget_s=25.0):
+    """the port at B in {128, 4096, 65536}, forward only and forward+backward, both gradient
+    branches (adjoint_solver False = autograd through the solver, True = odeint_adjoint), within a time budget."""
+    rows, spent = [], 0.0
+    for B in (128, 4096, 65536):
+        for adjoint in (False, True):
+            for backward in (True, False):
+                if spent > budget_s:
+                    continue
+                t0 = time.perf_counter()
+                ts, cores = time_cpu_reference(method, adjoint, B, reps=2 if B < 65536 else 1, warmup=1, backward=backward)
+                spent += time.perf_counter() - t0
+                rows.append({"B": B, "adjoint_solver": adjoint, "pass": "fwd+bwd" if backward else "fwd",
+                             "s": round(min(ts), 5), "trajectory_steps_per_s": B * (T - 1) / min(ts)})
+    return rows
 
 
 def run_reference_arm(args):
@@ -208,7 +214,9 @@ def run_reference_arm(args):
     times, cores = time_cpu_reference(args.method, args.adjoint, B, args.steps, warmup=max(1, min(args.warmup, 2)))
     total = sum(times)
     value = B * (T - 1) * len(times) / total
-    sample = f"{B} of 2^20 trajectories per step, T={T}, {args.method}, fwd+bwd, {len(times)} steps"
+    sample = (f"{B} of 2^20 trajectories per step (per-trajectory-step rates are batch-size independent above ~4k rows: "
+              f"see cpu_baseline.table of the b200 arm), T={T}, {args.method}, fwd+bwd, {len(times)} steps; oracle PORT of the "
+              "reference classes (evaluates the hidden layer once per RHS call, the real classes twice: conservative)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -223,14 +231,34 @@ def run_reference_arm(args):
 
 def workload_config(args, B_per_gpu, n):
     return {"workload": "configs[1] blackbox: 2^20 trajectories/GPU x 100 obs times, fp32 rk4(3/8) fwd+bwd",
-            "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L, "sol_layout": getattr(args, "layout", "tbs"),
-            "ode_hidden_dim": H, "ode_state_dim": S, "solver": args.method,
+            "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L,
+            "sol_layout": getattr(args, "layout", "tbs"), "ode_hidden_dim": H, "ode_state_dim": S, "solver": args.method,
             "gradient": "odeint_adjoint emulation" if args.adjoint else "discrete adjoint (odeint + autograd parity)",
             "mlp_evaluation": "piecewise-linear heads (alpha t + beta per trajectory, updated at relu crossings)",
-            "reverse_sweep": ("reads the forward's evaluation checkpoints (12.5 GB per 2^20 x 100 solve)"
-                              if (getattr(args, "eval_ckpt", False) and not args.adjoint) else "re-evaluates the MLP"),
+            "reverse_sweep": "re-evaluates the heads from the stored grid states (nothing else is checkpointed)",
+            "thread_mapping": "one trajectory per thread, fp32x2 over state pairs",
             "parallelism": f"trajectory-sharded x{n}, one flat all-reduce of parameter gradients",
             "l2": "inputs larger than L2 (sol / grad_sol are 2.1 GB each per GPU vs 126 MB L2)"}
+
+
+def pin_to_gpu_numa_node(index):
+    """Bind this process to the CPUs NVML reports as local to the GPU BEFORE pinned buffers are allocated (first
+    touch then places them on that NUMA node); returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {index}"
+    except Exception as e:  # pragma: no cover
+        return "unavailable: " + repr(e)[:80]
+    return "unavailable"
 
 
 def main():
@@ -244,9 +272,8 @@ def main():
     ap.add_argument("--adjoint", action="store_true", help="odeint_adjoint gradient semantics instead of discrete")
     ap.add_argument("--ref-batch", type=int, default=8192, help="trajectories per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-epoch", action="store_true", help="skip the CVS training-epoch timing")
     ap.add_argument("--e2e-chunks", type=int, default=16)
-    ap.add_argument("--eval-ckpt", action="store_true",
-                    help="reverse sweep reads the forward's evaluation checkpoints instead of re-evaluating the MLP")
     ap.add_argument("--layout", default="tbs", choices=["tbs", "bts"],
                     help="storage of the resident step's solution: (T,B,S) torchdiffeq's, or (B,T,S) the decoder's")
     args = ap.parse_args()
@@ -260,8 +287,6 @@ def main():
     import structured_latent_odes_b200 as slode
     from structured_latent_odes_b200 import _cabi, sharding
     from structured_latent_odes_b200.torchdiffeq_api import KernelTimer
-    from structured_latent_odes_b200 import torchdiffeq_api as _api_cfg
-    _api_cfg.EVAL_CHECKPOINTS = bool(args.eval_ckpt)  # the library default (None) picks by state width
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -270,6 +295,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    numa = pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -304,7 +330,6 @@ def main():
     # upstream dL/dsol, resident, in the same storage layout as the solution
     G = (torch.randn(B, T, S, device=dev, generator=g) if args.layout == "bts"
          else torch.randn(T, B, S, device=dev, generator=g).permute(1, 0, 2))
-    launches = [0]
     lib = _cabi.lib()
 
     def step_resident():
@@ -322,7 +347,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     sync_all()
-    launches[0] = lib.slode_query(_cabi.Q_TOTAL_LAUNCHES)
+    launches0 = lib.slode_query(_cabi.Q_TOTAL_LAUNCHES)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks, KernelTimer() as kt:
         sync_all()
@@ -338,7 +363,8 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total = float(tmax.item())
     value = world * B * (T - 1) * args.steps / (ms_total * 1e-3)
-    n_launches = lib.slode_query(_cabi.Q_TOTAL_LAUNCHES) - launches[0]
+    n_launches = lib.slode_query(_cabi.Q_TOTAL_LAUNCHES) - launches0
+    del G
 
     # ---- end to end: pinned host inputs -> loss + gradients back on the host --------------------------------
     gc = torch.Generator().manual_seed(100 + rank)
@@ -394,31 +420,47 @@ def main():
         out_host[1:].copy_(flat, non_blocking=True)
         main.synchronize()  # the caller reads the loss: the step ends when it is on the host
 
+    def step_copy_only():
+        """The step's host->device bytes alone (same chunking, same pinned buffers): the bound e2e cannot beat."""
+        for i in range(nchunk):
+            lo, hi = bounds[i]
+            s = i & 1
+            zbuf[s][: hi - lo].copy_(z_host[lo:hi], non_blocking=True)
+            ybuf[s][: hi - lo].copy_(y_host[lo:hi], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
     for _ in range(3):
         step_e2e()
-    sync_all()
     model.layout = args.layout
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
-    sync_all()
-    t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * (T - 1) * args.steps / (float(t_e2e.item()) * 1e-3)
+    e2e_ms = timed(step_e2e, args.steps)
+    model.layout = args.layout
+    copy_ms = timed(step_copy_only, max(3, min(args.steps, 10)))   # all ranks copy at the same time, like the step
+    e2e_value = world * B * (T - 1) / (e2e_ms * 1e-3)
     h2d = z_host.numel() * 4 + y_host.numel() * 4
     d2h = out_host.numel() * 4
+    del z_host, y_host, zbuf, ybuf
+
+    # ---- the other half of BASELINE.json's metric: SLODE train-epoch time (CVS, reference batch sizes) ----------
+    epoch = None
+    if not args.no_epoch:
+        epoch = time_cvs_epoch(dev, rank, world, sync_all)
 
     if rank == 0:
-        from structured_latent_odes_b200 import torchdiffeq_api as _api
-        ckpt = bool(_api.EVAL_CHECKPOINTS) and not args.adjoint
         ff, fb = pl_flops(args.method, T, H, S)
-        if ckpt:
-            fb = checkpointed_bwd_flops(args.method, T, H, S)
-        xu_f = sfu_ops(args.method, T, S)
-        xu_b = 0.0 if ckpt else xu_f
-        bf, bb = algorithmic_bytes(T, H, S, args.method, ckpt)
+        xu_f, xu_b = sfu_ops(args.method, T, S, merged=True), sfu_ops(args.method, T, S, merged=False)
+        bf, bb = algorithmic_bytes(T, H, S, args.method)
         fwd_ms = sum(ktimes["fwd"]) / max(len(ktimes["fwd"]), 1)
         bwd_ms = sum(ktimes["bwd"]) / max(len(ktimes["bwd"]), 1)
         peaks = {}
@@ -427,82 +469,154 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic_map = {}
+        hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
+        counters, traffic_map = {}, {}
         try:
+            counters = json.load(open(os.path.join(ROOT, "profiles", "counters.json")))
             traffic_map = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
-        achieved_b = B * fb / (bwd_ms * 1e-3) / 1e12
-        achieved_f = B * ff / (fwd_ms * 1e-3) / 1e12
+        mid = {"euler": 0, "midpoint": 1, "rk4": 2}[args.method]
+        fp32_src = ("148 SM x 128 lanes x 2 x 1.965 GHz; FFMA2 micro-benchmark measured 74.0 "
+                    "(profiles/r01/fp32_pipes_microbench.jsonl); MEASURED_PEAKS.json has no fp32 entry")
+        xu_src = ("148 SM x 16 MUFU lanes x 1.965 GHz; ex2-only / rcp-only micro-benchmarks in "
+                  "profiles/r02/mufu_microbench.jsonl; MEASURED_PEAKS.json has no MUFU entry")
+
+        def roof(kernel_key, label, ms_launch, flop_alg, bytes_alg, xu_alg):
+            """One kernel under the three rooflines (HBM bytes, fp32 FMA-pipe flop, XU/MUFU operations); the largest
+            fraction is reported on top.  `executed` figures come from the ncu opcode counters of the same kernel at
+            the same size (profiles/counters.json, produced by profiles/tools/ncu_counters.py) divided by THIS run's
+            launch duration."""
+            c = counters.get(kernel_key, {})
+            sec = ms_launch * 1e-3
+            r = {"hbm": {"achieved": B * bytes_alg / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src},
+                 "fp32": {"achieved": B * flop_alg / sec / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "peak_source": fp32_src,
+                          "count": "algorithmic (flop model of the piecewise-linear formulation)"},
+                 "xu": {"achieved": B * xu_alg / sec / 1e12, "peak": XU_PEAK_TOPS, "unit": "T MUFU lane-op/s", "peak_source": xu_src}}
+            scale = B / float(1 << 20)   # counters were captured at 2^20 trajectories
+            if c:
+                r["fp32"] = {"achieved": scale * c["fp32_flop_executed"] / sec / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                             "peak_source": fp32_src, "count": "executed (ncu sass__inst_executed_per_opcode: FFMA2/FMUL2/FADD2/FFMA/FMUL/FADD)",
+                             "algorithmic_achieved": B * flop_alg / sec / 1e12}
+                r["xu"]["executed_achieved"] = scale * c["mufu_lane_ops_executed"] / sec / 1e12
+            for v in r.values():
+                v["frac"] = v["achieved"] / v["peak"]
+            bound = max(r, key=lambda k: r[k]["frac"])
+            top = r[bound]
+            out = {"bound": bound, "kernel": label, "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                   "frac": top["frac"], "traffic": traffic_map.get(kernel_key), "peak_source": top["peak_source"],
+                   "ms_per_launch": ms_launch, "algorithmic_flop_per_launch": B * flop_alg,
+                   "algorithmic_bytes_per_launch": B * bytes_alg}
+            for k in r:
+                if k != bound:
+                    out[k] = r[k]
+            if c:
+                out["ncu"] = {k: c.get(k) for k in (
+                    "inst_executed", "smsp__issue_active.avg.per_cycle_active", "launch__registers_per_thread",
+                    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "gpu__time_duration.sum", "report")}
+                # the packed fp32x2 forms with three register operands issue at 85 FMA/clk/SM, not 128
+                # (profiles/r01/fp32_pipes_microbench.jsonl: ffma2_rrr): the pipe's busy CYCLES are what bounds it
+                out["fma_pipe_cycles_active_frac"] = (c.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed") or 0) / 100.0
+            return out
+
+        mode = 1 if args.adjoint else 0
+        rl_b = roof(f"fixed_bwd_kernel<{H}, {S}, {mid}, {mode}>", "fixed_bwd_kernel (reverse sweep)", bwd_ms, fb, bb, xu_b)
+        rl_f = roof(f"fixed_fwd_kernel<{H}, {S}, {mid}>", "fixed_fwd_kernel (forward solve)", fwd_ms, ff, bf, xu_f)
+        xu_step_ms = B * (xu_f + xu_b) / (XU_PEAK_TOPS * 1e12) * 1e3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, B, world),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(t_e2e.item()) / args.steps,
+                    "ms_per_step": e2e_ms, "copy_bound_ms": copy_ms, "frac_of_copy_bound": copy_ms / e2e_ms,
+                    "copy_bound_gbs_per_gpu": h2d / (copy_ms * 1e-3) / 1e9, "pinned_numa": numa,
                     "what": f"pinned z (B,{L}) + observations (B,{O},{T}) -> solve -> q50 head (slode_heads) + MSE -> backward -> "
-                            f"loss + {reducer.numel} parameter gradients on the host; {nchunk} double-buffered chunks"},
+                            f"loss + {reducer.numel} parameter gradients on the host; {nchunk} double-buffered chunks; "
+                            "copy_bound_ms = the same pinned->device copies alone, all ranks at once"},
             "gpu_launches": n_launches,
+            "step_frac_of_xu_bound": xu_step_ms / (ms_total / args.steps),
         }
-        hbm_src = "measured" if peaks else "fallback"
-        rl_b = {"kernel": "mlp_fixed_bwd_kernel (reverse sweep" + (", evaluation checkpoints)" if ckpt else ")"),
-                "ms_per_launch": bwd_ms, "algorithmic_flop_per_launch": B * fb, "algorithmic_bytes_per_launch": B * bb,
-                "fp32": {"achieved": achieved_b, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_b / FP32_PEAK_TFLOPS},
-                "hbm": {"achieved": B * bb / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": B * bb / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
-                "xu": {"achieved": B * xu_b / (bwd_ms * 1e-3) / 1e12, "peak": XU_PEAK_TOPS, "unit": "T MUFU lane-op/s",
-                       "frac": B * xu_b / (bwd_ms * 1e-3) / 1e12 / XU_PEAK_TOPS, "sfu_ops_per_launch": B * xu_b}}
-        rl_f = {"kernel": "mlp_fixed_fwd_kernel", "ms_per_launch": fwd_ms, "algorithmic_flop_per_launch": B * ff,
-                "algorithmic_bytes_per_launch": B * bf,
-                "fp32": {"achieved": achieved_f, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_f / FP32_PEAK_TFLOPS},
-                "hbm": {"achieved": B * bf / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": B * bf / (fwd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
-                "xu": {"achieved": B * xu_f / (fwd_ms * 1e-3) / 1e12, "peak": XU_PEAK_TOPS, "unit": "T MUFU lane-op/s",
-                       "frac": B * xu_f / (fwd_ms * 1e-3) / 1e12 / XU_PEAK_TOPS, "sfu_ops_per_launch": B * xu_f}}
-        fp32_src = ("148 SM x 128 lanes x 2 x 1.965 GHz; FFMA2 micro-benchmark measured 74.0 "
-                    "(profiles/r01/fp32_pipes_microbench.jsonl); MEASURED_PEAKS.json has no fp32 entry")
-
-        xu_src = "148 SM x 16 MUFU lanes x 1.965 GHz (no MUFU entry in MEASURED_PEAKS.json)"
-
-        def flat(r, traffic_key):
-            """contract shape: the roofline that binds the kernel on top (largest fraction of its peak among HBM
-            bytes, fp32 FMA flop and XU/MUFU operations), the other two beside it"""
-            bound = max(("hbm", "fp32", "xu"), key=lambda k: r[k]["frac"])
-            top = r[bound]
-            out = {"bound": bound, "kernel": r["kernel"], "achieved": top["achieved"], "peak": top["peak"],
-                   "unit": top["unit"], "frac": top["frac"], "traffic": traffic_map.get(traffic_key),
-                   "peak_source": {"hbm": top.get("peak_source"), "fp32": fp32_src, "xu": xu_src}[bound],
-                   "ms_per_launch": r["ms_per_launch"], "algorithmic_flop_per_launch": r["algorithmic_flop_per_launch"],
-                   "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"], "note": r.get("note")}
-            for k in ("hbm", "fp32", "xu"):
-                if k != bound:
-                    out[k] = r[k]
-            return out
-
-        # measured context for the fractions above (ncu --set full of the same kernels, profiles/r01/INDEX.md)
-        rl_b["note"] = ("re-evaluating sweep: bound by none of the three rooflines -- warp-instruction issue/latency "
-                        "(ncu: 2.10e9 warp instructions, 0.41 issued per cycle and scheduler at 2 warps per scheduler, "
-                        "254 registers; XU 24 %, FMA 22 %, DRAM 20 % of peak)" if not ckpt else
-                        "checkpointed sweep: HBM read stream of the stored evaluations (ncu: DRAM 59 % of peak, "
-                        "long_scoreboard 23 % of stall samples)")
-        rl_f["note"] = ("piecewise-linear heads: 15 MUFU lane-operations per trajectory and evaluation; ncu: XU pipe "
-                        "55 % of peak, FMA 21 %, mio_throttle + short_scoreboard 1.3 stall cycles per issue")
-        tag = f"{args.method}_{int(args.adjoint)}" + ("_ckpt" if ckpt else "")
         dominant_is_bwd = bwd_ms >= fwd_ms
-        line["roofline"] = flat(rl_b if dominant_is_bwd else rl_f, ("bwd_" if dominant_is_bwd else "fwd_") + tag)
-        line["roofline_other"] = flat(rl_f if dominant_is_bwd else rl_b, ("fwd_" if dominant_is_bwd else "bwd_") + tag)
+        line["roofline"] = rl_b if dominant_is_bwd else rl_f
+        line["roofline_other"] = rl_f if dominant_is_bwd else rl_b
+        if epoch is not None:
+            line["epoch"] = epoch
         if not args.no_cpu_baseline and world == 1:
             reps = 3
             times, cores = time_cpu_reference(args.method, args.adjoint, args.ref_batch, reps)
             v = args.ref_batch * (T - 1) * reps / sum(times)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.ref_batch} of 2^20 trajectories, T={T}, {args.method}, fwd+bwd "
-                                              f"(x0 net, solve, q50 head + MSE, backward), best-effort all host threads, "
-                                              f"{reps} reps after 1 warm-up"}
+                                              f"(x0 net, solve, q50 head + MSE, backward), all host threads, "
+                                              f"{reps} reps after 1 warm-up; table: B in (128, 4096, 65536) x both "
+                                              "gradient branches x (fwd, fwd+bwd)",
+                                    "table": cpu_baseline_table(args.method)}
+            if epoch is not None:
+                line["cpu_baseline"]["epoch_s"] = time_cvs_epoch_cpu()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_cvs_epoch(dev, rank, world, sync_all):
+    """SLODE train-epoch time, CVS default config (810 / 90 series, batch 128, midpoint + odeint_adjoint, seed 12):
+    7 mini-batches x two objectives + the four evaluation passes (training_cvs.py:256-315).  With N ranks every
+    mini-batch's rows are sharded and the gradients summed by one flat all-reduce per optimiser step."""
+    import torch.distributed as dist
+    from structured_latent_odes_b200 import sharding, training_cvs as tc
+    cfg = tc.cvs_config()
+    data = tc.make_cvs_dataset(cfg, dev, generator=torch.Generator(device=dev).manual_seed(cfg.seed))
+    torch.manual_seed(cfg.seed)
+    model = tc.MechanisticModel(cfg, dev, torch.arange(0.0, cfg.seq_len, 1.0, device=dev)).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.learning_rate, betas=(0.9, 0.999), capturable=True)
+    shard = (rank, world) if world > 1 else None
+    reducer = sharding.FlatGradReducer(list(model.parameters())) if world > 1 else None
+    step = tc.GraphedTrainStep(model, opt, reducer, warmup=1)   # the two-objective training step replayed from CUDA graphs
+    evaluation = tc.GraphedEvaluation(model, data, cfg, shard)   # ... and the four evaluation passes
+    out = {}
+    for evaluate in (True, False):
+        best = None
+        for e in range(5):
+            sync_all()
+            t0 = time.perf_counter()
+            tc.train_epoch(model, opt, data, cfg, generator=torch.Generator().manual_seed(e), evaluate=evaluate,
+                           reducer=reducer, shard=shard, step=step, evaluation=evaluation)
+            sync_all()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if e >= 2:   # epochs 0 and 1 warm up / capture the graphs
+                best = float(dt.item()) if best is None else min(best, float(dt.item()))
+        out["s_per_epoch_with_eval" if evaluate else "s_per_epoch_train_steps_only"] = best
+    out["what"] = ("training_cvs.py default config on synthetic CVS data (810 train / 90 val series, batch 128, midpoint, "
+                   "odeint_adjoint semantics): 7 x 2 optimiser steps (+ 4 evaluation passes); best of 3 epochs after 1; "
+                   f"rows of every mini-batch sharded over {world} rank(s)")
+    return out
+
+
+def time_cvs_epoch_cpu():
+    """The same epoch through the CPU port of the reference decoder (all host threads), once after one warm-up."""
+    from oracle import slode_port
+    from structured_latent_odes_b200 import training_cvs as tc
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = tc.cvs_config()
+    data = tc.make_cvs_dataset(cfg, "cuda", generator=torch.Generator(device="cuda").manual_seed(cfg.seed))
+    data = {k: {kk: vv.cpu() for kk, vv in v.items()} for k, v in data.items()}
+    torch.manual_seed(cfg.seed)
+    model = tc.MechanisticModel(cfg, "cpu", torch.arange(0.0, cfg.seq_len, 1.0), decoder_cls=slode_port.Decoder)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.learning_rate, betas=(0.9, 0.999))
+    out = {}
+    for evaluate in (True, False):
+        ts = []
+        for e in range(2):
+            t0 = time.perf_counter()
+            tc.train_epoch(model, opt, data, cfg, generator=torch.Generator().manual_seed(e), evaluate=evaluate)
+            ts.append(time.perf_counter() - t0)
+        out["s_per_epoch_with_eval" if evaluate else "s_per_epoch_train_steps_only"] = ts[-1]
+    out["cores"] = os.cpu_count()
+    return out
 
 
 if __name__ == "__main__":

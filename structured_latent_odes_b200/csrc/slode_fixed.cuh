@@ -1436,15 +1436,16 @@ struct Plan {
   size_t ws_bytes;   // global scratch the caller provides: wide-layer tables (+ flip records, backward)
 };
 
+// Resident blocks per SM of a kernel at a dynamic shared-memory size, looked up once per (kernel, size, device):
+// the hot path then makes no CUDA runtime call except the launch itself (cheap at the reference's batch sizes, and
+// nothing that could be refused while a stream is being captured into a graph).
+int cached_blocks_per_sm(const void* kern, size_t smem, int* blocks_per_sm);  // slode_fixed_api.cu
+
 template <class K>
 int plan_grid(K kern, size_t smem, int64_t B, int sms, int* grid) {
-  SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 0;
-  SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem));
-  if (blocks_per_sm < 1) {
-    set_error("fixed-grid kernel does not fit on an SM (%zu bytes of shared memory)", smem);
-    return SLODE_EUNSUPPORTED;
-  }
+  const int rc = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), smem, &blocks_per_sm);
+  if (rc) return rc;
   const int64_t tiles = (B + kThreads - 1) / kThreads;
   // whole waves of resident blocks; tiles are handed out grid-stride
   *grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sms * blocks_per_sm));

@@ -7,7 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "slode_common.cuh"
 #include "slode_mlp_api.h"
@@ -32,6 +34,35 @@ int device_sms(int* sms) {
   *sms = cached[dev];
   return SLODE_OK;
 }
+
+namespace fx {
+int cached_blocks_per_sm(const void* kern, size_t smem, int* blocks_per_sm) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, size_t, int>, int> cache;
+  int dev = 0;
+  SLODE_CUDA_TRY(cudaGetDevice(&dev));
+  const auto key = std::make_tuple(kern, smem, dev);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    const auto it = cache.find(key);
+    if (it != cache.end()) {
+      *blocks_per_sm = it->second;
+      return SLODE_OK;
+    }
+  }
+  SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int n = 0;
+  SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, smem));
+  if (n < 1) {
+    set_error("fixed-grid kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+    return SLODE_EUNSUPPORTED;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  cache[key] = n;
+  *blocks_per_sm = n;
+  return SLODE_OK;
+}
+}  // namespace fx
 
 static int check_sizes(const char* who, int method, int mode, int64_t B, int T, int H, int S) {
   if (B < 0 || T < 1 || H < 1 || S < 1) {

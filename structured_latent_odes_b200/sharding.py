@@ -46,24 +46,24 @@ class FlatGradReducer:
         self.group = group
 
     def reduce(self, average: bool = False):
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat[o:o + n].zero_()
-            else:
-                self.flat[o:o + n].copy_(p.grad.reshape(-1))
-            o += n
+        # pack: one concatenation kernel instead of one copy per parameter
+        views = list(self.flat.split([p.numel() for p in self.params]))
+        have = [p.grad is not None for p in self.params]
+        if all(have):
+            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat)
+        else:
+            self.flat.zero_()
+            src = [p.grad.reshape(-1) for p, h in zip(self.params, have) if h]
+            if src:
+                torch._foreach_copy_([v for v, h in zip(views, have) if h], src)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             if average:
                 self.flat.div_(dist.get_world_size(self.group))
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = self.flat[o:o + n].view_as(p).clone()
-            else:
-                p.grad.copy_(self.flat[o:o + n].view_as(p))
-            o += n
+        # unpack: one multi-tensor copy
+        for p, v, h in zip(self.params, views, have):
+            if not h:
+                p.grad = torch.empty_like(p)
+        torch._foreach_copy_([p.grad.view(-1) if p.grad.is_contiguous() else p.grad for p in self.params],
+                             [v if p.grad.is_contiguous() else v.view_as(p) for p, v in zip(self.params, views)])
         return self.flat

@@ -106,6 +106,12 @@ def _bernoulli_logp(probs, y):
     return -torch.nn.functional.binary_cross_entropy(p, y, reduction="sum")
 
 
+def _sample_normal(loc, scale):
+    """loc + scale * eps.  (torch.normal(loc, scale) validates ``scale >= 0`` with a device->host sync, which also
+    makes it illegal inside CUDA-graph capture.)"""
+    return loc + scale * torch.randn_like(loc)
+
+
 def _normal_logp(x, loc, scale):
     return (-0.5 * ((x - loc) / scale) ** 2 - torch.log(scale) - 0.5 * math.log(2 * math.pi)).sum()
 
@@ -134,8 +140,7 @@ class MechanisticModel(nn.Module):
     @staticmethod
     def quantile_loglik(obs, mu, std, tau):
         """sum of the six masked Laplace sites of compute_likelihood (:180-211): weight tau where x >= mu."""
-        w = torch.where(obs >= mu, torch.as_tensor(tau, dtype=mu.dtype, device=mu.device),
-                        torch.as_tensor(1.0 - tau, dtype=mu.dtype, device=mu.device))
+        w = torch.where(obs >= mu, float(tau), float(1.0 - tau))  # python scalars: no host tensor (graph-capturable)
         return (w * (-torch.log(2.0 * std) - (obs - mu).abs() / std)).sum()
 
     # ---- the two objectives (negative ELBOs summed over the batch, as Trace_ELBO returns them) -----------------
@@ -174,7 +179,7 @@ class MechanisticModel(nn.Module):
     def classifier(self, observations):
         c = self.config
         loc_z, scale_z = self.encoder(observations)
-        z = torch.normal(loc_z, scale_z)
+        z = _sample_normal(loc_z, scale_z)
         a_i = self.q_iext_given_z_iext(z[:, :c.z_iext_dim])
         a_r = self.q_rtpr_given_z_rtpr(z[:, c.z_iext_dim:c.z_iext_dim + c.z_rtpr_dim])
         return {"iext": (a_i > 0.5).float(), "rtpr": (a_r > 0.5).float()}
@@ -184,12 +189,12 @@ class MechanisticModel(nn.Module):
         c = self.config
         if is_post:
             loc_z, scale_z = self.encoder(observations)
-            z = torch.normal(loc_z, scale_z)
+            z = _sample_normal(loc_z, scale_z)
         else:
             B = observations.shape[0]
             ze = torch.randn(B, c.z_epsilon_dim, device=observations.device)
-            zi = torch.normal(*self.p_z_iext_given_iext(iext))
-            zr = torch.normal(*self.p_z_rtprs_given_rtprs(rtpr))
+            zi = _sample_normal(*self.p_z_iext_given_iext(iext))
+            zr = _sample_normal(*self.p_z_rtprs_given_rtprs(rtpr))
             z = torch.cat((zi, zr, ze), dim=1)
         solution_xt, mu_75, mu_50, mu_25, std = self.decoder(z)
         return {"l1": (mu_50 - observations).abs().mean(), "solution_xt": solution_xt, "mu_75": mu_75, "mu_50": mu_50,
@@ -222,11 +227,27 @@ def make_cvs_dataset(config, device, generator=None):
     return {k: {"observations": obs[s], "iext": iext[s], "rtpr": rtpr[s]} for k, s in cut.items()}
 
 
-def batches(split, batch_size, shuffle, generator=None):
+def batches(split, batch_size, shuffle, generator=None, shard=None):
+    """Mini-batches of a split.  ``shard=(rank, world_size)`` hands this rank its contiguous row range of EVERY
+    mini-batch (same permutation on every rank: same generator seed), so that the ranks' summed gradients equal the
+    single-process step (the losses are sums over batch rows)."""
     n = split["observations"].shape[0]
-    idx = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+    from .sharding import shard_bounds
+    if not shuffle:  # plain row ranges: no index tensor, no host->device copy (graph-capturable)
+        for lo in range(0, n, batch_size):
+            hi = min(lo + batch_size, n)
+            if shard is not None:
+                a, b = shard_bounds(hi - lo, shard[0], shard[1])
+                lo, hi = lo + a, lo + b
+            yield {k: v[lo:hi] for k, v in split.items()}
+        return
+    idx = torch.randperm(n, generator=generator)
     for lo in range(0, n, batch_size):
-        sel = idx[lo:lo + batch_size].to(split["observations"].device)
+        sel = idx[lo:lo + batch_size]
+        if shard is not None:
+            a, b = shard_bounds(sel.numel(), shard[0], shard[1])
+            sel = sel[a:b]
+        sel = sel.to(split["observations"].device)
         yield {k: v[sel] for k, v in split.items()}
 
 
@@ -248,14 +269,89 @@ def run_batch(model, optimizer, batch, reducer=None):
     return out
 
 
+class GraphedTrainStep:
+    """``run_batch`` captured into a CUDA graph per mini-batch size and replayed (the latency
+    path).  At the reference's batch sizes (128 rows) a training step is ~50 small launches and launch latency is
+    all there is; the solver kernels keep no cross-call state and take their scratch from the torch allocator, so the
+    whole two-objective step (forward, reverse sweep, flat all-reduce, Adam) is capturable.  The first ``warmup``
+    steps of every batch size run eagerly (they are real training steps), the next one is captured, all later ones
+    are replays.  The optimiser must be constructed with ``capturable=True``."""
+
+    def __init__(self, model, optimizer, reducer=None, warmup=3):
+        self.model, self.opt, self.reducer, self.warmup = model, optimizer, reducer, warmup
+        self.seen, self.graphs = {}, {}
+
+    def __call__(self, batch):
+        n = batch["observations"].shape[0]
+        if n not in self.graphs:
+            self.seen[n] = self.seen.get(n, 0) + 1
+            if self.seen[n] <= self.warmup:
+                return run_batch(self.model, self.opt, batch, self.reducer)
+            self._capture(n, batch)
+        graph, static, losses = self.graphs[n]
+        for k, v in static.items():
+            v.copy_(batch[k])
+        graph.replay()
+        return [l.clone() / n for l in losses]
+
+    def _capture(self, n, batch):
+        static = {k: v.clone() for k, v in batch.items()}
+        graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            losses = []
+            for loss_fn in (self.model.loss_basic, self.model.loss_aux):
+                self.opt.zero_grad(set_to_none=True)
+                loss = loss_fn(static["observations"], static["iext"], static["rtpr"])
+                loss.backward()
+                if self.reducer is not None:
+                    self.reducer.reduce()
+                self.opt.step()
+                losses.append(loss.detach())
+        self.graphs[n] = (graph, static, losses)
+
+
+class GraphedEvaluation:
+    """The four evaluation passes of an epoch (val / train x posterior / prior, training_cvs.py:270-315) captured as
+    ONE CUDA graph: they only read the resident dataset and the current weights, so the graph needs no inputs.
+    First call eager (warm-up), second call captures, later calls replay."""
+
+    def __init__(self, model, data, config, shard=None):
+        self.model, self.data, self.config, self.shard = model, data, config, shard
+        self.calls, self.graph, self.static = 0, None, None
+
+    def _passes(self):
+        m, d, bs, sh = self.model, self.data, self.config.mini_batch_size, self.shard
+        return {"val_post": input_pred_stats(m, d["val"], True, shard=sh),
+                "val_prior": input_pred_stats(m, d["val"], False, shard=sh),
+                "train_post": input_pred_stats(m, d["train"], True, batch_size=bs, shard=sh),
+                "train_prior": input_pred_stats(m, d["train"], False, batch_size=bs, shard=sh)}
+
+    def __call__(self):
+        self.calls += 1
+        if self.calls == 1:
+            return self._passes()
+        if self.graph is None:
+            self.graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(self.graph):
+                self.static = self._passes()
+        self.graph.replay()
+        return {k: {kk: vv.clone() for kk, vv in v.items()} for k, v in self.static.items()}
+
+
 @torch.no_grad()
-def input_pred_stats(model, split, is_post, batch_size=None):
-    """One evaluation pass (training_cvs.py:44-144): both losses forward only, recon, classifier accuracy."""
+def input_pred_stats(model, split, is_post, batch_size=None, shard=None):
+    """One evaluation pass (training_cvs.py:44-144): both losses forward only, recon, classifier accuracy.  With
+    ``shard`` every rank evaluates its rows of each batch (the caller sums the statistics over ranks)."""
     n = split["observations"].shape[0]
     tot = [0.0, 0.0]
     l1 = 0.0
     hit_i = hit_r = 0.0
-    for b in batches(split, batch_size or n, shuffle=False):
+    for b in batches(split, batch_size or n, shuffle=False, shard=shard):
+        if b["observations"].shape[0] == 0:
+            continue
         o, i, r = b["observations"], b["iext"], b["rtpr"]
         tot[0] += model.loss_basic(o, i, r) / o.shape[0]
         tot[1] += model.loss_aux(o, i, r) / o.shape[0]
@@ -267,14 +363,21 @@ def input_pred_stats(model, split, is_post, batch_size=None):
     return {"iext": hit_i / n, "rtpr": hit_r / n, "l1": l1 / n, "elbo": torch.stack([torch.as_tensor(t) for t in tot])}
 
 
-def train_epoch(model, optimizer, data, config, generator=None, evaluate=True, reducer=None):
-    """One reference epoch: the mini-batch loop, then the four evaluation passes (training_cvs.py:256-315)."""
-    losses = [run_batch(model, optimizer, b, reducer)
-              for b in batches(data["train"], config.mini_batch_size, shuffle=True, generator=generator)]
+def train_epoch(model, optimizer, data, config, generator=None, evaluate=True, reducer=None, shard=None, step=None,
+                evaluation=None):
+    """One reference epoch: the mini-batch loop, then the four evaluation passes (training_cvs.py:256-315).
+    Multi-GPU: ``shard=(rank, world_size)`` + ``reducer`` (one flat all-reduce of the gradients per optimiser step).
+    ``step`` / ``evaluation``: a ``GraphedTrainStep`` / ``GraphedEvaluation`` to replay the training steps / the four
+    evaluation passes from CUDA graphs instead of launching them eagerly."""
+    do = step if step is not None else (lambda b: run_batch(model, optimizer, b, reducer))
+    losses = [do(b)
+              for b in batches(data["train"], config.mini_batch_size, shuffle=True, generator=generator, shard=shard)]
     stats = {}
-    if evaluate:
-        stats["val_post"] = input_pred_stats(model, data["val"], True)
-        stats["val_prior"] = input_pred_stats(model, data["val"], False)
-        stats["train_post"] = input_pred_stats(model, data["train"], True, batch_size=config.mini_batch_size)
-        stats["train_prior"] = input_pred_stats(model, data["train"], False, batch_size=config.mini_batch_size)
+    if evaluate and evaluation is not None:
+        stats = evaluation()
+    elif evaluate:
+        stats["val_post"] = input_pred_stats(model, data["val"], True, shard=shard)
+        stats["val_prior"] = input_pred_stats(model, data["val"], False, shard=shard)
+        stats["train_post"] = input_pred_stats(model, data["train"], True, batch_size=config.mini_batch_size, shard=shard)
+        stats["train_prior"] = input_pred_stats(model, data["train"], False, batch_size=config.mini_batch_size, shard=shard)
     return torch.stack([torch.stack(l) for l in losses]).mean(0), stats
