@@ -83,7 +83,7 @@ int slode_dopri5_supported(int H, int S);
 
 /*
  * Scratch memory of the fixed-grid entry points below, in bytes, for a call with these arguments (0 is
- * possible).  The caller allocates it on the device (any alignment cudaMalloc / the torch allocator gives),
+ * possible).  The caller allocates it on the device (16-byte aligned: anything cudaMalloc / the torch allocator gives),
  * passes it as `workspace` and may free or reuse it once the call's work on `stream` has finished.  Contents
  * need not be initialised and are not preserved.
  *   backward     0: slode_*_fixed_fwd, 1: slode_*_fixed_bwd (flip records of the reverse sweep: NQ*16 bytes

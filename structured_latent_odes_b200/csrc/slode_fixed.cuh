@@ -1482,6 +1482,10 @@ int launch_fwd(const FwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_onl
               p.ws_bytes);
     return SLODE_EINVAL;
   }
+  if (p.ws_bytes && (reinterpret_cast<uintptr_t>(a.ws) & 15)) {
+    set_error("fixed-grid forward: workspace must be 16-byte aligned");
+    return SLODE_EINVAL;
+  }
   fixed_fwd_kernel<H, S, METHOD><<<p.grid, kThreads, p.smem, a.stream>>>(
       a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb, w, w1t_stride, a.lat, static_cast<unsigned char*>(a.ws));
   SLODE_CUDA_TRY(cudaGetLastError());
@@ -1498,6 +1502,10 @@ int launch_bwd(const BwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_onl
   if (p.ws_bytes > a.ws_bytes || !a.ws) {
     set_error("fixed-grid backward: workspace of %zu bytes given, %zu needed (slode_fixed_workspace_bytes)", a.ws_bytes,
               p.ws_bytes);
+    return SLODE_EINVAL;
+  }
+  if (reinterpret_cast<uintptr_t>(a.ws) & 15) {
+    set_error("fixed-grid backward: workspace must be 16-byte aligned");
     return SLODE_EINVAL;
   }
   fixed_bwd_kernel<H, S, METHOD, MODE><<<p.grid, kThreads, p.smem, a.stream>>>(

@@ -38,26 +38,31 @@ int device_sms(int* sms) {
 namespace fx {
 int cached_blocks_per_sm(const void* kern, size_t smem, int* blocks_per_sm) {
   static std::mutex mu;
-  static std::map<std::tuple<const void*, size_t, int>, int> cache;
+  static std::map<std::tuple<const void*, size_t, int>, int> cache;   // (kernel, dynamic smem, device) -> blocks per SM
+  static std::map<std::pair<const void*, int>, bool> opted_in;        // kernels whose smem limit has been raised
   int dev = 0;
   SLODE_CUDA_TRY(cudaGetDevice(&dev));
   const auto key = std::make_tuple(kern, smem, dev);
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    const auto it = cache.find(key);
-    if (it != cache.end()) {
-      *blocks_per_sm = it->second;
-      return SLODE_OK;
-    }
+  std::lock_guard<std::mutex> lock(mu);
+  const auto it = cache.find(key);
+  if (it != cache.end()) {
+    *blocks_per_sm = it->second;
+    return SLODE_OK;
   }
-  SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!opted_in[{kern, dev}]) {
+    // once per kernel and device: allow the largest dynamic shared memory the device offers, so that launches with
+    // different sizes (different L, layouts, fused or not) never depend on the order in which they were first seen
+    int optin = 0;
+    SLODE_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SLODE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    opted_in[{kern, dev}] = true;
+  }
   int n = 0;
   SLODE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, smem));
   if (n < 1) {
     set_error("fixed-grid kernel does not fit on an SM (%zu bytes of shared memory)", smem);
     return SLODE_EUNSUPPORTED;
   }
-  std::lock_guard<std::mutex> lock(mu);
   cache[key] = n;
   *blocks_per_sm = n;
   return SLODE_OK;

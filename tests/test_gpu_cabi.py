@@ -84,3 +84,72 @@ def test_c_based_entry_points_match_the_fused_path(method, adjoint):
         if ".prod." in k or ".degr." in k:
             continue
         assert U.rel_err(v.grad, gr_f[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("shape,method,mode", [("cvs", "rk4", 0), ("cvs", "midpoint", 1), ("proc", "rk4", 0),
+                                               ("h64", "midpoint", 0), ("h128", "euler", 0)])
+@pytest.mark.parametrize("B", [1, 130])
+def test_no_write_outside_the_callers_buffers(shape, method, mode, B):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are hunted with guard bands: every
+    output and the workspace are carved out of one arena with canary words on both sides (and between them), the
+    fused entry points run on raw pointers, and the canaries must be intact afterwards.  Ragged B exercises the
+    masked tail threads."""
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    Ld, H, S, times = U.SHAPES[shape]
+    T = len(times)
+    o = U.make_oracle(shape, method, bool(mode))
+    p = U.make_product(o)
+    d, n0, n2 = p.dynamics, p.latent_to_ode_net[0], p.latent_to_ode_net[2]
+    lib = _cabi.lib()
+    mid = _cabi.METHODS[method]
+    ws_f = lib.slode_fixed_workspace_bytes(0, mid, mode, B, T, Ld, H, S, 2, 0)
+    ws_b = lib.slode_fixed_workspace_bytes(1, mid, mode, B, T, Ld, H, S, 2, 0)
+    assert ws_f >= 0 and ws_b > 0
+    n_par = H + 2 * (S * H + S) + 2 * (H * Ld + H) + S * H + S
+    GUARD = 256  # floats
+    r64 = lambda n: (n + 63) // 64 * 64  # noqa: E731  (views stay 256-byte aligned like allocator blocks)
+    sizes = {"sol": r64(T * B * S), "ws_f": r64((ws_f + 3) // 4), "ws_b": r64((ws_b + 3) // 4), "gz": r64(B * Ld),
+             "gp": r64(n_par)}
+    used = {"sol": T * B * S, "gz": B * Ld, "gp": n_par}
+    total = GUARD + sum(v + GUARD for v in sizes.values())
+    arena = torch.full((total,), 12345.678, device="cuda")
+    off, view = GUARD, {}
+    for k, v in sizes.items():
+        view[k] = arena[off:off + v]
+        off += v + GUARD
+    view["gp"][:n_par].zero_()
+    z = torch.randn(B, Ld, device="cuda")
+    G = torch.randn(T, B, S, device="cuda")
+    w = [x.detach().contiguous() for x in (d.dynamics_hidden.weight, d.dynamics_hidden.bias, d.dyanamics_growth.weight,
+                                           d.dyanamics_growth.bias, d.dyanmics_degradation.weight,
+                                           d.dyanmics_degradation.bias, n0.weight, n0.bias, n2.weight, n2.bias)]
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.slode_latent_fixed_fwd(mid, B, T, Ld, H, S, p.times.data_ptr(), z.data_ptr(), *[x.data_ptr() for x in w], None,
+                                    view["sol"].data_ptr(), B * S, S, view["ws_f"].data_ptr() if ws_f else None, ws_f, s)
+    assert rc == 0, lib.slode_last_error()
+    rc = lib.slode_latent_fixed_bwd(mid, mode, B, T, Ld, H, S, p.times.data_ptr(), z.data_ptr(), *[x.data_ptr() for x in w],
+                                    view["sol"].data_ptr(), B * S, S, G.data_ptr(), B * S, S, view["gz"].data_ptr(), None,
+                                    view["gp"].data_ptr(), view["ws_b"].data_ptr(), ws_b, s)
+    assert rc == 0, lib.slode_last_error()
+    torch.cuda.synchronize()
+    # canaries: everything that is not inside a view (for the outputs: not inside the part the call owns)
+    mask = torch.ones(total, dtype=torch.bool, device="cuda")
+    off = GUARD
+    for k, v in sizes.items():
+        mask[off:off + used.get(k, v)] = False
+        off += v + GUARD
+    assert bool((arena[mask] == 12345.678).all()), "a kernel wrote outside the buffers it was given"
+    # and the results are the Python API's
+    sol_ref = p.solve_ODE(z).detach().permute(1, 0, 2)
+    assert torch.equal(view["sol"][:T * B * S].view(T, B, S), sol_ref)
+    assert torch.isfinite(view["gz"][:B * Ld]).all() and torch.isfinite(view["gp"][:n_par]).all()
+    # a workspace that is too small is refused, not overrun
+    rc = lib.slode_latent_fixed_bwd(mid, mode, B, T, Ld, H, S, p.times.data_ptr(), z.data_ptr(), *[x.data_ptr() for x in w],
+                                    view["sol"].data_ptr(), B * S, S, G.data_ptr(), B * S, S, view["gz"].data_ptr(), None,
+                                    view["gp"].data_ptr(), view["ws_b"].data_ptr(), ws_b - 1, s)
+    assert rc == 1 and b"workspace" in lib.slode_last_error()
+    rc = lib.slode_latent_fixed_bwd(mid, mode, B, T, Ld, H, S, p.times.data_ptr(), z.data_ptr(), *[x.data_ptr() for x in w],
+                                    view["sol"].data_ptr(), B * S, S, G.data_ptr(), B * S, S, view["gz"].data_ptr(), None,
+                                    view["gp"].data_ptr(), view["ws_b"].data_ptr() + 4, ws_b, s)
+    assert rc == 1 and b"aligned" in lib.slode_last_error()
