@@ -107,6 +107,31 @@ def cvs_mech(B, T=100):
           flush=True)
 
 
+def tensor_core_proxy(B, Hw, S=5, T=100):
+    """BASELINE configs[4] asks where the dense head contraction should move from the FMA pipe to tcgen05.  The kernels
+    do not run that contraction at all any more (piecewise-linear heads: O(S) per evaluation + O(S) per relu crossing),
+    so the question becomes: how long would the dense contraction ALONE take on the tensor cores?  Measured with
+    cuBLAS as the tensor-core proxy (library code, used here only as a yardstick): per MLP evaluation one
+    [B x H] . [H x 16] product (2S = 10 head outputs padded to 16), TF32 (x3 for the error-compensated 3xTF32 split a
+    1e-5 parity needs) and plain fp32, times the 3(T-1)+1 evaluations of an rk4 solve.  The hidden activations
+    relu(w1t t + c) would still have to be produced per evaluation (B x H FMAs and a B x H x 4 byte operand write): the
+    figure is a LOWER bound on a tensor-core forward."""
+    A = torch.randn(B, Hw, device=dev)
+    W = torch.randn(Hw, 16, device=dev)
+    evals = 3 * (T - 1) + 1
+    out = {"case": f"configs[4] dense-head contraction on tensor cores (cuBLAS proxy), H={Hw}", "B": B, "H": Hw,
+           "evals_per_rk4_solve": evals}
+    for name, tf32 in (("tf32", True), ("fp32", False)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        ms = timed(lambda: torch.matmul(A, W))
+        out[f"gemm_{name}_ms"] = round(ms, 4)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["dense_heads_3xtf32_ms_per_solve_lower_bound"] = round(3 * out["gemm_tf32_ms"] * evals, 2)
+    out["dense_heads_tf32_relaxed_ms_per_solve_lower_bound"] = round(out["gemm_tf32_ms"] * evals, 2)
+    out["dense_heads_fp32_ms_per_solve_lower_bound"] = round(out["gemm_fp32_ms"] * evals, 2)
+    print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
     big = 1 << 20
     blackbox("configs[0] CVS default", 128, 86, 15, 25, 5, "midpoint", True)
@@ -121,9 +146,11 @@ if __name__ == "__main__":
     for ns in (1, 200, 4096):
         for method in ("midpoint", "rk4"):
             blackbox(f"configs[3] proc 312 wells x {ns} samples", 312 * ns, 100, 50, 25, 8, method, method == "midpoint", times=tt)
-    for Hw in (16, 32, 64):  # configs[4]: hidden-width sweep on the FMA path (compiled widths)
+    for Hw in (16, 25, 32, 64, 128, 256, 512):  # configs[4]: hidden-width sweep (every compiled width)
         Sw = 4 if Hw == 16 else 5
         for B in (1 << 10, 1 << 16, big):
             blackbox(f"configs[4] width sweep H={Hw}", B, 100, 15, Hw, Sw, "rk4", False)
+        if Hw >= 64:
+            tensor_core_proxy(big, Hw)
     blackbox("configs[1] blackbox rk4 (bench.py workload)", big, 100, 15, 25, 5, "rk4", False)
     blackbox("configs[1] blackbox midpoint adjoint", big, 100, 15, 25, 5, "midpoint", True)

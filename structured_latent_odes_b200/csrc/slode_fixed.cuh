@@ -37,6 +37,10 @@
 #ifndef SLODE_FX_BWD_MINB
 #define SLODE_FX_BWD_MINB 4      // resident blocks per SM the reverse sweep is compiled for (euler, midpoint: 128 registers)
 #endif
+#ifndef SLODE_FX_BWD_MINB_WIDE
+#define SLODE_FX_BWD_MINB_WIDE 3 // state dimensions above 5 (proc: S = 8, four register pairs per vector): euler and
+                                 // midpoint fit 168 registers, rk4 needs the full 255 (2 blocks)
+#endif
 #ifndef SLODE_FX_BWD_MINB_RK4
 #define SLODE_FX_BWD_MINB_RK4 3  // rk4 holds three evaluations at once: 168 registers (at 128 it spills in the time loop)
 #endif
@@ -881,7 +885,7 @@ __host__ __device__ constexpr size_t bwd_smem_bytes(int L, bool lat) {
 }
 
 template <int H, int S, int METHOD, int MODE>
-__global__ void __launch_bounds__(kThreads, (Shape<H, S>::BIG || S > 5) ? 2 : (METHOD == SLODE_METHOD_RK4 ? SLODE_FX_BWD_MINB_RK4 : SLODE_FX_BWD_MINB))
+__global__ void __launch_bounds__(kThreads, Shape<H, S>::BIG ? 2 : (S > 5 ? (METHOD == SLODE_METHOD_RK4 ? 2 : SLODE_FX_BWD_MINB_WIDE) : (METHOD == SLODE_METHOD_RK4 ? SLODE_FX_BWD_MINB_RK4 : SLODE_FX_BWD_MINB)))
 fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                  const float* __restrict__ sol, int64_t st, int64_t sb, const float* __restrict__ gsol, int64_t gst,
                  int64_t gsb, float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,
