@@ -206,8 +206,7 @@ int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S,
  *                  (emit[0] = 1: sol[0] is y0 itself)
  *   ckpt_y         the checkpoints written by the forward call
  *   grad_* as for slode_mlp_fixed_bwd (grad_w accumulated into; caller zero-fills).
- * The torchdiffeq.odeint_adjoint variant of dopri5 (an ADAPTIVE backward solve whose error norm spans the
- * parameter adjoints) is not provided.
+ * (The torchdiffeq.odeint_adjoint variant of dopri5 is slode_mlp_dopri5_adjoint_bwd below.)
  */
 int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S,
                          const float* t, const float* c,
@@ -218,6 +217,41 @@ int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S,
                          const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
                          float* grad_y0, float* grad_c, float* grad_w,
                          void* stream);
+
+/*
+ * Backward pass of torchdiffeq.odeint_adjoint(func=OdeFunc, y0, t, method="dopri5", rtol, atol)
+ * (models/blackbox_ode.py:40-42 with config.solver = "dopri5"; adjoint_solver=True is the shipped default of every
+ * config).  torchdiffeq semantics are kept: for i = T-1 .. 1 a FRESH adaptive dopri5 solve of the augmented system
+ * [y, a, a_theta] from t[i] down to t[i-1] (time flipped, Hairer initial step per interval, one step size for the
+ * whole augmented state, mixed error norm = the largest per-tensor RMS among y, a and each parameter tensor's
+ * adjoint, float64 controller time, FSAL, the interval's end value from the 4th-order interpolant), then y is
+ * reset to the stored forward value sol[i-1] and a += grad_sol[i-1].  Gradients go to y0 and to
+ * func.parameters() = (dynamics_hidden, dyanamics_growth, dyanmics_degradation) only: OdeFunc.constants (z) gets
+ * none.  One persistent cooperative kernel; the step sequence is deterministic.
+ *   t (T) increasing output times; z (B,L); c (B,H) = z W1[:,1:]^T + b1
+ *   W1 (H, L+1) dynamics_hidden.weight (column 0 multiplies t); Wg,Wd (S,H); bg,bd (S)
+ *   sol / grad_sol indexing as in slode_mlp_fixed_bwd (sol = the forward solve's output)
+ *   grad_y0 (B,S) written; grad_params written, flat in func.parameters() order:
+ *       [ dW1 (H*(L+1)) | db1 (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) ]
+ *   step_log optional (log_capacity, 4) float64: interval index i, -t at the start of the attempt, step size,
+ *       accepted(1/0), one row per attempted step; NULL to skip
+ *   stats    device int64[4]: accepted, rejected, RHS evaluations per trajectory, status (0 ok, 1 dt underflow,
+ *       2 max_attempts exceeded)
+ *   workspace: slode_mlp_dopri5_adjoint_workspace_bytes(B, L, H, S) bytes, 256-byte aligned, caller-owned
+ * ode_state_dim in {4, 5, 8}; hidden width limited by shared memory (about 150 for L = 15).
+ */
+int64_t slode_mlp_dopri5_adjoint_workspace_bytes(int64_t B, int L, int H, int S);
+
+int slode_mlp_dopri5_adjoint_bwd(int64_t B, int T, int L, int H, int S,
+                                 const float* t, const float* z, const float* c,
+                                 const float* W1, const float* Wg, const float* bg,
+                                 const float* Wd, const float* bd,
+                                 const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                                 const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
+                                 double rtol, double atol, int64_t max_attempts,
+                                 float* grad_y0, float* grad_params,
+                                 double* step_log, int64_t log_capacity, int64_t* stats,
+                                 void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Decoder heads on the latent trajectories; replaces, for all heads at once,

@@ -21,7 +21,10 @@ This file therefore restates the published torchdiffeq 0.2.x algorithm:
   and cast to ``y.dtype`` at each RHS call, 4th-order dense output fitted through the
   ``DPS_C_MID`` midpoint;
 * ``odeint_adjoint``: forward under ``no_grad``; backward integrates the augmented system
-  ``[vjp_t, y, adj_y, adj_params]`` from ``t[i]`` to ``t[i-1]`` with the same method, resets
+  ``[vjp_t, y, adj_y, adj_params]`` from ``t[i]`` to ``t[i-1]`` with the same method (for dopri5: a
+  fresh adaptive solve per output interval, error norm = torchdiffeq's mixed norm over the tuple, i.e.
+  the largest per-tensor RMS of err/tol among y, adj_y and each parameter's adjoint; ``vjp_t`` is
+  identically zero because the reference's time grid does not require grad), resets
   ``y`` to the stored forward value and adds ``grad_y[i-1]``; ``adjoint_params`` defaults to
   ``tuple(func.parameters())`` (so plain-tensor attributes such as ``OdeFunc.constants``
   get no gradient -- SURVEY.md F5).
@@ -60,6 +63,9 @@ class SolverStats:
 
 
 last_stats = SolverStats()
+# backward pass of the last odeint_adjoint call with an adaptive method: one (interval index i, accepted[], dts[])
+# entry per output interval, in the order they were solved (i = T-1 .. 1); test aid, not in torchdiffeq
+last_adjoint_intervals = []
 
 
 # ----------------------------------------------------------------------------------------
@@ -185,13 +191,20 @@ def _dopri5_rk_step(func, y0, f0, t0, dt, t1):
     return y1, f1, y1_error, kk
 
 
-def _select_initial_step(func, t0, y0, order, rtol, atol, f0):
+def _mixed_norm(tensors):
+    """torchdiffeq ``_mixed_norm``: the largest RMS norm among the tensors of a tuple state."""
+    if len(tensors) == 0:
+        return 0.0
+    return max(_rms_norm(x) for x in tensors)
+
+
+def _select_initial_step(func, t0, y0, order, rtol, atol, f0, norm=_rms_norm):
     dtype = y0.dtype
     t_dtype = t0.dtype
     t0 = t0.to(dtype)
     scale = atol + torch.abs(y0) * rtol
-    d0 = _rms_norm(y0 / scale)
-    d1 = _rms_norm(f0 / scale)
+    d0 = norm(y0 / scale)
+    d1 = norm(f0 / scale)
     if d0 < 1e-5 or d1 < 1e-5:
         h0 = torch.tensor(1e-6, dtype=dtype, device=y0.device)
     else:
@@ -199,7 +212,7 @@ def _select_initial_step(func, t0, y0, order, rtol, atol, f0):
     y1 = y0 + h0 * f0
     f1 = func(t0 + h0, y1)
     last_stats.n_rhs += 1
-    d2 = _rms_norm((f1 - f0) / scale) / h0
+    d2 = norm((f1 - f0) / scale) / h0
     if d1 <= 1e-15 and d2 <= 1e-15:
         h1 = torch.max(torch.tensor(1e-6, dtype=dtype, device=y0.device), h0 * 1e-3)
     else:
@@ -251,6 +264,7 @@ def _integrate_dopri5(func, y0, t, rtol, atol, options):
     dfactor = opts.pop("dfactor", 0.2)
     max_num_steps = opts.pop("max_num_steps", 2 ** 31 - 1)
     first_step = opts.pop("first_step", None)
+    norm = opts.pop("norm", _rms_norm)  # torchdiffeq options["norm"]; a tuple state gets the mixed norm (_odeint_tuple)
     tdtype = torch.promote_types(opts.pop("dtype", torch.float64), y0.dtype)
     if opts:
         raise ValueError(f"unsupported dopri5 options {sorted(opts)}")
@@ -265,7 +279,7 @@ def _integrate_dopri5(func, y0, t, rtol, atol, options):
     f0 = func(t[0].to(y0.dtype), y0)
     last_stats.n_rhs += 1
     if first_step is None:
-        dt = _select_initial_step(func, t[0], y0, order - 1, rtol, atol, f0)
+        dt = _select_initial_step(func, t[0], y0, order - 1, rtol, atol, f0, norm)
     else:
         dt = torch.as_tensor(first_step, dtype=tdtype, device=dev)
     st_y, st_f, st_t0, st_t1, st_dt = y0, f0, t[0], t[0], dt
@@ -283,7 +297,7 @@ def _integrate_dopri5(func, y0, t, rtol, atol, options):
             assert a_t0 + a_dt > a_t0, "underflow in dt {}".format(a_dt.item())
             y1, f1, y1_error, k = _dopri5_rk_step(func, st_y, st_f, a_t0, a_dt, a_t1)
             error_tol = atol + rtol * torch.max(st_y.abs(), y1.abs())
-            error_ratio = _rms_norm(y1_error / error_tol).abs()
+            error_ratio = norm(y1_error / error_tol).abs()
             accept = bool(error_ratio <= 1)
             last_stats.accepted.append(accept)
             last_stats.dts.append(float(a_dt.detach()))
@@ -361,20 +375,25 @@ class _OdeintAdjoint(torch.autograd.Function):
                 yy = y_aug[1]
                 adj_y = y_aug[2]
                 with torch.enable_grad():
-                    tt_ = tt.detach().requires_grad_(True)
+                    # torchdiffeq evaluates func at the DETACHED time unless t itself requires grad (it never does
+                    # in the reference: OdeModel.times is a plain tensor), so vjp_t is identically zero
+                    tt_ = tt.detach()
                     yy = yy.detach().requires_grad_(True)
                     f = func(tt_, yy)
-                    vjp_t, vjp_y, *vjp_params = torch.autograd.grad(
-                        f, (tt_, yy) + adjoint_params, -adj_y, allow_unused=True, retain_graph=True)
-                vjp_t = torch.zeros_like(tt) if vjp_t is None else vjp_t
+                    vjp_y, *vjp_params = torch.autograd.grad(
+                        f, (yy,) + adjoint_params, -adj_y, allow_unused=True, retain_graph=True)
+                vjp_t = torch.zeros_like(tt)
                 vjp_y = torch.zeros_like(yy) if vjp_y is None else vjp_y
                 vjp_params = [torch.zeros_like(p) if v is None else v
                               for p, v in zip(adjoint_params, vjp_params)]
                 return (vjp_t, f, vjp_y, *vjp_params)
 
+            del last_adjoint_intervals[:]
             for i in range(len(t) - 1, 0, -1):
                 aug = _odeint_tuple(augmented_dynamics, tuple(aug), t[i - 1:i + 1].flip(0),
                                     ctx.method, ctx.rtol, ctx.atol, ctx.options)
+                if ctx.method in ADAPTIVE_METHODS:
+                    last_adjoint_intervals.append((i, list(last_stats.accepted), list(last_stats.dts)))
                 aug = [a[1] for a in aug]
                 aug[1] = y[i - 1]
                 aug[2] = aug[2] + grad_y[i - 1]
@@ -399,6 +418,12 @@ def _odeint_tuple(func, y0_tuple, t, method, rtol, atol, options):
     def flat_func(tt, v):
         return torch.cat([f.reshape(-1) for f in func(tt, unflat(v))])
 
+    # torchdiffeq wraps the norm of a tuple state so that it sees the tuple: by default the mixed norm (the largest
+    # per-tensor RMS); odeint_adjoint's default_adjoint_norm max(|t|, rms(y), rms(adj_y), mixed(adj_params)) is the
+    # same thing for a single-tensor y
+    if method in ADAPTIVE_METHODS:
+        options = dict(options or {})
+        options.setdefault("norm", lambda v: _mixed_norm(unflat(v)))
     sol = odeint(flat_func, flat0, t, rtol=rtol, atol=atol, method=method, options=options)
     return unflat(sol)
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(CSRC, "libslode_b200.so")
-SOURCES = ["slode_host.cu", "slode_mlp.cu", "slode_fixed_api.cu", "slode_cvs.cu", "slode_heads.cu",
+SOURCES = ["slode_host.cu", "slode_mlp.cu", "slode_fixed_api.cu", "slode_cvs.cu", "slode_heads.cu", "slode_dopri5_adj.cu",
            "slode_mlp_25_5.cu", "slode_mlp_25_8.cu", "slode_mlp_16_4.cu", "slode_mlp_32_5.cu", "slode_mlp_64_5.cu",
            "slode_fixed_25_5.cu", "slode_fixed_25_8.cu", "slode_fixed_16_4.cu", "slode_fixed_32_5.cu",
            "slode_fixed_64_5.cu", "slode_fixed_128_5.cu", "slode_fixed_256_5.cu", "slode_fixed_512_5.cu"]

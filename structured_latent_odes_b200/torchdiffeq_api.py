@@ -512,6 +512,78 @@ class _MlpDopri5Solve(torch.autograd.Function):
         return grad_y0, grad_c, gw1t, gWg, gbg, gWd, gbd, None, None, None, None, None
 
 
+class _MlpDopri5AdjointSolve(torch.autograd.Function):
+    """``odeint_adjoint(..., method="dopri5")``: the forward is the plain adaptive solve; the backward is
+    torchdiffeq's adjoint -- one fresh adaptive solve of [y, a, a_theta] per output interval, backwards in time,
+    restarted from the stored forward state (``slode_mlp_dopri5_adjoint_bwd``).  Gradients: ``y0`` and
+    ``func.parameters()``; ``func.constants`` gets none."""
+
+    @staticmethod
+    def forward(ctx, y0, z, W1, b1, Wg, bg, Wd, bd, t, rtol, atol, options, layout):
+        zc = z.detach().to(torch.float32).contiguous()
+        W1c, b1c = W1.detach().contiguous(), b1.detach().contiguous()
+        c = torch.addmm(b1c, zc, W1c[:, 1:].t()).contiguous()
+        hw = [x.detach().contiguous() for x in (Wg, bg, Wd, bd)]
+        sol, _, _ = _dopri5_forward(y0.detach().contiguous(), c, [W1c[:, 0].contiguous()] + hw, t, rtol, atol, options,
+                                    layout, want_ckpt=False)
+        ctx.save_for_backward(zc, c, W1c, *hw, t, sol)
+        opts = dict(options or {})
+        ctx.cfg = (float(rtol), float(atol), int(opts.get("max_num_steps", 1 << 20)), bool(opts.get("log_steps", False)))
+        return sol
+
+    @staticmethod
+    def backward(ctx, grad_sol):
+        zc, c, W1, Wg, bg, Wd, bd, t, sol = ctx.saved_tensors
+        rtol, atol, max_steps, log_steps = ctx.cfg
+        T, B, S = sol.shape
+        H, L = W1.shape[0], zc.shape[1]
+        strides = _dense_tbs_strides(grad_sol)
+        if strides is None or grad_sol.dtype != torch.float32:
+            grad_sol = grad_sol.to(torch.float32).contiguous()
+            strides = (grad_sol.stride(0), grad_sol.stride(1))
+        dev = sol.device
+        lib = _cabi.lib()
+        n = lib.slode_mlp_dopri5_adjoint_workspace_bytes(B, L, H, S)
+        if n < 0:
+            _cabi.check(2, "slode_mlp_dopri5_adjoint_workspace_bytes")
+        P = H * (L + 1) + H + 2 * (S * H + S)
+        grad_y0 = torch.empty((B, S), device=dev, dtype=torch.float32)
+        gp = torch.empty(P, device=dev, dtype=torch.float32)
+        stats = torch.zeros(4, device=dev, dtype=torch.int64)
+        log_cap = 1 << 16 if log_steps else 0
+        log = torch.zeros((log_cap, 4), device=dev, dtype=torch.float64) if log_cap else None
+        with torch.cuda.device(dev), _timed("bwd"):
+            ws = torch.empty(max(n, 256), device=dev, dtype=torch.uint8)
+            rc = lib.slode_mlp_dopri5_adjoint_bwd(
+                B, T, L, H, S, _ptr(t), _ptr(zc), _ptr(c), _ptr(W1), _ptr(Wg), _ptr(bg), _ptr(Wd), _ptr(bd), _ptr(sol),
+                sol.stride(0), sol.stride(1), _ptr(grad_sol), strides[0], strides[1], rtol, atol, max_steps,
+                _ptr(grad_y0), _ptr(gp), _ptr(log), log_cap, _ptr(stats), _ptr(ws), ws.numel(),
+                torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_mlp_dopri5_adjoint_bwd")
+        n_acc, n_rej, n_rhs, status = (int(v) for v in stats.tolist())
+        if status != 0:
+            raise _cabi.SlodeError(f"dopri5 adjoint: {_DOPRI5_STATUS.get(status, status)} after {n_acc + n_rej} attempted steps")
+        st = last_dopri5_adjoint_stats
+        st.n_accept, st.n_reject, st.n_rhs = n_acc, n_rej, n_rhs
+        st.steps = log[: min(n_acc + n_rej, log_cap)].cpu() if log is not None else None
+        o = 0
+
+        def take(*shape):
+            nonlocal o
+            k = 1
+            for d in shape:
+                k *= d
+            v = gp[o:o + k].view(*shape)
+            o += k
+            return v
+
+        gW1, gb1, gWg, gbg, gWd, gbd = take(H, L + 1), take(H), take(S, H), take(S), take(S, H), take(S)
+        return grad_y0, None, gW1, gb1, gWg, gbg, gWd, gbd, None, None, None, None, None
+
+
+last_dopri5_adjoint_stats = SolverStats()   # backward pass of the last odeint_adjoint(method="dopri5") call
+
+
 def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
     z, hid, gro, deg = _check_blackbox(func)
     B, S = y0.shape
@@ -527,10 +599,11 @@ def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
                                               or any(p.requires_grad for p in func.parameters()))
     if needs_grad:
         if mode == _cabi.BWD_TDE_ADJOINT:
-            raise NotImplementedError(
-                "odeint_adjoint with dopri5 (an adaptive backward solve whose error norm spans the parameter "
-                "adjoints) is not provided: use odeint (exact gradient of the accepted steps) or a fixed-grid "
-                "solver as every shipped config does")
+            bad = sorted(set(options or {}) & {"first_step", "replay_steps"})
+            if bad:
+                raise NotImplementedError(f"odeint_adjoint with dopri5: options {bad} (the reference passes none)")
+            return _MlpDopri5AdjointSolve.apply(y0, z, hid.weight, hid.bias, gro.weight, gro.bias, deg.weight,
+                                                deg.bias, t, rtol, atol, options, layout)
         W1g = hid.weight
         cg = torch.addmm(hid.bias, z.to(torch.float32), W1g[:, 1:].t())
         return _MlpDopri5Solve.apply(y0, cg, W1g[:, 0], gro.weight, gro.bias, deg.weight, deg.bias, t, rtol, atol,

@@ -36,6 +36,15 @@ def make_oracle(shape, method, adjoint, seed=12, dtype=torch.float32):
     return m
 
 
+def make_oracle_like(oracle_model, dtype):
+    """A copy of an oracle model (same weights, grid and solver settings) in another dtype."""
+    d = oracle_model.dynamics
+    m = slode_port.OdeModel(oracle_model.times.to(dtype), d.n_outputs, d.n_inputs, d.dynamics_hidden.out_features,
+                            oracle_model.adjoint_solver, oracle_model.solver).to(dtype)
+    m.load_state_dict({k: v.to(dtype) for k, v in oracle_model.state_dict().items()})
+    return m
+
+
 def make_product(oracle_model, device="cuda", layout="tbs"):
     import structured_latent_odes_b200 as slode
 

@@ -158,7 +158,8 @@ def test_errors():
         one = slode.odeint(f, y0, p.times[:1], method="dopri5", rtol=1e-5, atol=1e-6)
         assert torch.equal(one[0], y0)
     with pytest.raises(NotImplementedError, match="odeint_adjoint with dopri5"):
-        slode.odeint_adjoint(f, y0.requires_grad_(True), p.times, method="dopri5", rtol=1e-5, atol=1e-6)
+        slode.odeint_adjoint(f, y0.requires_grad_(True), p.times, method="dopri5", rtol=1e-5, atol=1e-6,
+                             options={"first_step": 0.1})
 
 
 @pytest.mark.parametrize("shape,B,rtol,atol", [("cvs", 40, 1e-5, 1e-6), ("proc", 30, 1e-4, 1e-5), ("small", 129, 1e-6, 1e-7)])

@@ -197,3 +197,65 @@ def test_invalid_inputs():
         tde.odeint(f, y0, torch.tensor([0.0, 1.0], dtype=torch.float64), method="rk45")
     with pytest.raises(ValueError):
         tde.odeint_adjoint(lambda t, y: y, y0, torch.tensor([0.0, 1.0], dtype=torch.float64), method="rk4")
+
+
+def test_dopri5_adjoint_gradient_and_mixed_norm():
+    """odeint_adjoint with dopri5: (i) at tight tolerances its gradient is the true gradient (compared with autograd
+    through a tight dopri5 solve: signs and structure of the augmented system); (ii) one fresh adaptive solve per
+    output interval is logged; (iii) the step controller uses torchdiffeq's MIXED norm over the augmented tuple (the
+    largest per-tensor RMS), not one RMS over the flattened state: a parameter adjoint whose error dominates must
+    shrink the steps although it is a single element among many state components."""
+    torch.manual_seed(0)
+
+    class F(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor([0.8, -0.3], dtype=torch.float64))
+
+        def forward(self, t, y):
+            return torch.sigmoid(self.w[0] * t + self.w[1]) - torch.sigmoid(self.w[0]) * y
+
+    t = torch.linspace(0.0, 3.0, 7, dtype=torch.float64)
+    G = torch.cos(torch.arange(7, dtype=torch.float64))[:, None, None]
+    grads = []
+    for solve in (tde.odeint, tde.odeint_adjoint):
+        f = F()
+        y0 = torch.tensor([[0.5], [0.1], [0.9]], dtype=torch.float64, requires_grad=True)
+        sol = solve(f, y0, t, method="dopri5", rtol=1e-10, atol=1e-12)
+        (sol * G).sum().backward()
+        grads.append((y0.grad.clone(), f.w.grad.clone()))
+    assert torch.allclose(grads[0][0], grads[1][0], rtol=1e-7, atol=1e-9)
+    assert torch.allclose(grads[0][1], grads[1][1], rtol=1e-7, atol=1e-9)
+    assert [i for i, _, _ in tde.last_adjoint_intervals] == [6, 5, 4, 3, 2, 1]
+    assert all(sum(acc) >= 1 for _, acc, _ in tde.last_adjoint_intervals)
+    # mixed norm: largest per-tensor RMS
+    a, b = torch.tensor([3.0, 4.0]), torch.tensor([[10.0]])
+    assert float(tde._mixed_norm((a, b))) == pytest.approx(10.0)
+    assert float(tde._mixed_norm((a,))) == pytest.approx(math.sqrt(12.5))
+
+    # a wide state (many well-resolved components) next to ONE stiff parameter adjoint: under a flattened RMS the
+    # parameter's error would be diluted by 1/sqrt(n) and fewer steps taken
+    class Wide(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.k = torch.nn.Parameter(torch.tensor(3.0, dtype=torch.float64))
+
+        def forward(self, t, y):
+            return -0.01 * y + 1e-3 * torch.sin(self.k * 40.0 * t)
+
+    counts = {}
+    for name in ("mixed", "flat"):
+        f = Wide()
+        y0 = torch.ones(64, 1, dtype=torch.float64, requires_grad=True)
+        tt = torch.tensor([0.0, 1.0], dtype=torch.float64)
+        if name == "flat":
+            saved = tde._mixed_norm
+            tde._mixed_norm = lambda ts: tde._rms_norm(torch.cat([x.reshape(-1) for x in ts]))
+        try:
+            sol = tde.odeint_adjoint(f, y0, tt, method="dopri5", rtol=1e-6, atol=1e-8)
+            sol[-1].sum().backward()
+        finally:
+            if name == "flat":
+                tde._mixed_norm = saved
+        counts[name] = sum(len(acc) for _, acc, _ in tde.last_adjoint_intervals)
+    assert counts["mixed"] > counts["flat"]
