@@ -199,6 +199,33 @@ int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S,
                          int64_t* stats, void* stream);
 
 /*
+ * The same solve advanced ONE PASS PER CALL, for a batch that is sharded over several devices / processes
+ * (SURVEY.md section 8(e)): torchdiffeq's controller is batch-global, so every shard has to see the error norm of the
+ * WHOLE batch.  Each call runs one pass over this shard (Hairer's two initial-step passes, then one attempted step
+ * per call), writes the shard's sums of squares to out_sums[2] and returns; the host adds out_sums over the shards
+ * (NCCL all-reduce) into ext_sums[2] and calls again.  All shards then take the accept / reject decisions and step
+ * sizes of the unsharded solve.  Controller state and trajectory state live in the caller's workspace between calls.
+ *   n_global   trajectories over all shards (the norms divide by n_global * S)
+ *   restart    1 on the first call of a solve, 0 afterwards
+ *   stats      device int64[5]: as for slode_mlp_dopri5_fwd, plus [4] = phase after this call (5 = solve finished;
+ *              stop calling).  A shard may not be empty.  replay_steps are not supported here.
+ *   workspace  slode_mlp_dopri5_step_workspace_bytes(B, S) bytes, 256-byte aligned, caller-owned, kept between calls
+ */
+int64_t slode_mlp_dopri5_step_workspace_bytes(int64_t B, int S);
+
+int slode_mlp_dopri5_fwd_step(int64_t B, int T, int H, int S,
+                              const float* t, const float* c, const float* y0,
+                              const float* w1t, const float* Wg, const float* bg,
+                              const float* Wd, const float* bd,
+                              double rtol, double atol, double first_step, int64_t max_attempts,
+                              int64_t n_global, int restart,
+                              const double* ext_sums, double* out_sums,
+                              float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                              float* ckpt_y, int64_t ckpt_capacity,
+                              double* step_log, int64_t log_capacity,
+                              int64_t* stats, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Reverse-mode gradient of slode_mlp_dopri5_fwd: exact gradient of the accepted-step sequence (what autograd
  * through torchdiffeq.odeint(method="dopri5") gives; step sizes and accept/reject decisions carry no gradient).
  *   accepted_steps (n_accepted, 2) float64: t0, dt of every accepted step (rows of step_log with accepted = 1)
@@ -235,8 +262,10 @@ int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S,
  *       [ dW1 (H*(L+1)) | db1 (H) | dWg (S*H) | dbg (S) | dWd (S*H) | dbd (S) ]
  *   step_log optional (log_capacity, 4) float64: interval index i, -t at the start of the attempt, step size,
  *       accepted(1/0), one row per attempted step; NULL to skip
+ *   replay_steps optional (n_replay, 4) float64 rows in the step_log format: take exactly these step sizes and
+ *       accept/reject decisions (parity tests against a reference step sequence); NULL for the adaptive solve
  *   stats    device int64[4]: accepted, rejected, RHS evaluations per trajectory, status (0 ok, 1 dt underflow,
- *       2 max_attempts exceeded)
+ *       2 max_attempts exceeded, 4 replay too short)
  *   workspace: slode_mlp_dopri5_adjoint_workspace_bytes(B, L, H, S) bytes, 256-byte aligned, caller-owned
  * ode_state_dim in {4, 5, 8}; hidden width limited by shared memory (about 150 for L = 15).
  */
@@ -249,6 +278,7 @@ int slode_mlp_dopri5_adjoint_bwd(int64_t B, int T, int L, int H, int S,
                                  const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
                                  const float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
                                  double rtol, double atol, int64_t max_attempts,
+                                 const double* replay_steps, int64_t n_replay,
                                  float* grad_y0, float* grad_params,
                                  double* step_log, int64_t log_capacity, int64_t* stats,
                                  void* workspace, int64_t workspace_bytes, void* stream);

@@ -38,10 +38,13 @@ SIGNATURES = {
                                + [_p, _p, _p, _p, _i64, _p]),
     "slode_mlp_dopri5_fwd": (_i, [_i64, _i, _i, _i] + [_p] * 8 + [ctypes.c_double] * 3 + [_i64, _p, _i64]
                              + [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p]),
+    "slode_mlp_dopri5_step_workspace_bytes": (_i64, [_i64, _i]),
+    "slode_mlp_dopri5_fwd_step": (_i, [_i64, _i, _i, _i] + [_p] * 8 + [ctypes.c_double] * 3 + [_i64, _i64, _i, _p, _p]
+                                  + [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p]),
     "slode_mlp_dopri5_bwd": (_i, [_i64, _i, _i, _i] + [_p] * 7 + [_i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "slode_mlp_dopri5_adjoint_workspace_bytes": (_i64, [_i64, _i, _i, _i]),
     "slode_mlp_dopri5_adjoint_bwd": (_i, [_i64, _i, _i, _i, _i] + [_p] * 8 + [_p, _i64, _i64, _p, _i64, _i64]
-                                     + [ctypes.c_double, ctypes.c_double, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p]),
+                                     + [ctypes.c_double, ctypes.c_double, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p]),
     "slode_heads_fwd": (_i, [_i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _p, _p]),
     "slode_heads_bwd": (_i, [_i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p]),
     "slode_cvs_fixed_fwd": (_i, [_i, _i, _i64, _i, _i] + [_p] * 5 + [_p, _i64, _i64, _p]),

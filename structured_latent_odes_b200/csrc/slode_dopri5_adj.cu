@@ -53,7 +53,7 @@ __device__ constexpr float kCMid[7] = {
     (float)(-2691868925.0 / 45128329728.0 / 2), (float)(187940372067.0 / 1594534317056.0 / 2),
     (float)(-1776094331.0 / 19743644256.0 / 2), (float)(11237099.0 / 235043384.0 / 2)};
 
-enum { kStatusOk = 0, kStatusUnderflow = 1, kStatusMaxSteps = 2 };
+enum { kStatusOk = 0, kStatusUnderflow = 1, kStatusMaxSteps = 2, kStatusReplayShort = 4 };
 enum { kPassF0 = 0, kPassProbe = 1, kPassAttempt = 2 };
 enum { kS = 0, kE = 1, kM = 2, kK = 3 };  // combinations: step increment, error, midpoint, last stage alone
 
@@ -67,6 +67,8 @@ struct Args {
   int64_t gst, gsb;
   float rtol, atol;
   int64_t max_attempts;
+  const double* replay;  // optional (n_replay, 4) rows in the step_log format: take these step sizes and decisions
+  int64_t n_replay;
   float *gy0, *gparams;
   double* step_log;  // (log_cap, 4): interval index i, s0 = -t at the start of the attempt, ds, accepted
   int64_t log_cap;
@@ -598,12 +600,16 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
     // ---- adaptive steps until one passes the interval's end ------------------------------------------------
     while (s_end > s_cur) {
       if (attempt >= p.max_attempts) { status = kStatusMaxSteps; break; }
+      if (p.replay) {  // prescribed step sequence (parity tests against a reference step log)
+        if (attempt >= p.n_replay) { status = kStatusReplayShort; break; }
+        ds = p.replay[attempt * 4 + 2];
+      }
       const double a_s0 = s_cur, a_ds = ds, a_s1 = a_s0 + a_ds;
       if (!(a_s1 > a_s0)) { status = kStatusUnderflow; break; }
       const float s0f = (float)a_s0, dsf = (float)a_ds, s1f = (float)a_s1;
       run_pass(kPassAttempt, iv, s0f, dsf, s1f, norms);
       const float ratio = mixed(norms);
-      const bool accept = ratio <= 1.0f;
+      const bool accept = p.replay ? (p.replay[attempt * 4 + 3] != 0.0) : (ratio <= 1.0f);
       if (blockIdx.x == 0 && tid == 0 && p.step_log && attempt < p.log_cap) {
         p.step_log[attempt * 4 + 0] = (double)iv;
         p.step_log[attempt * 4 + 1] = a_s0;
@@ -778,7 +784,7 @@ extern "C" int slode_mlp_dopri5_adjoint_bwd(int64_t B, int T, int L, int H, int 
                                             const float* Wd, const float* bd, const float* sol, int64_t sol_stride_t,
                                             int64_t sol_stride_b, const float* grad_sol, int64_t gsol_stride_t,
                                             int64_t gsol_stride_b, double rtol, double atol, int64_t max_attempts,
-                                            float* grad_y0, float* grad_params, double* step_log, int64_t log_capacity,
+                                            const double* replay_steps, int64_t n_replay, float* grad_y0, float* grad_params, double* step_log, int64_t log_capacity,
                                             int64_t* stats, void* workspace, int64_t workspace_bytes, void* stream_) {
   if (B < 0 || T < 1 || L < 1 || H < 1 || S < 1) {
     set_error("slode_mlp_dopri5_adjoint_bwd: bad sizes B=%lld T=%d L=%d H=%d S=%d", (long long)B, T, L, H, S);
@@ -810,6 +816,7 @@ extern "C" int slode_mlp_dopri5_adjoint_bwd(int64_t B, int T, int L, int H, int 
   a.sol = sol; a.st = sol_stride_t; a.sb = sol_stride_b;
   a.gsol = grad_sol; a.gst = gsol_stride_t; a.gsb = gsol_stride_b;
   a.rtol = (float)rtol; a.atol = (float)atol; a.max_attempts = max_attempts;
+  a.replay = replay_steps; a.n_replay = replay_steps ? n_replay : 0;
   a.gy0 = grad_y0; a.gparams = grad_params; a.step_log = step_log; a.log_cap = step_log ? log_capacity : 0;
   a.stats = stats;
   size_t need = 0;

@@ -152,93 +152,31 @@ __global__ void __launch_bounds__(kBlock, 1)
 dopri5_fwd_kernel(Dopri5Args p) {
   __shared__ double sm_red[32];
   const int64_t ntiles = ((p.B + 1) / 2 + kBlock - 1) / kBlock;
-  const double nelem = (double)p.B * S;
+  const double nelem = (double)(p.n_global > 0 ? p.n_global : p.B) * S;
   const f2 rtol2 = bc(p.rtol), atol2 = bc(p.atol);
 
   auto cload = [&](const PairIdx& pi) {
     return [=](int j) { return pk(__ldg(p.c + pi.b0 * H + j), __ldg(p.c + pi.b1 * H + j)); };
   };
 
-  // ---- f0 = func(t[0], y0); sol[0] = y0; norms d0, d1 of Hairer's initial step ---------------------------
-  const double t_start = (double)__ldg(p.t);
-  {
-    double part[2] = {0.0, 0.0};
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const PairIdx pi = pair_index(tile, p.B);
-      Vec<S> y, A[1], D[1];
-      Gate<H> ng[1];
-      vload_rows<S>(p.y0, pi, y);
-      const float te[1] = {(float)t_start};
-      mlp_eval<H, S, 1, false, 0>(te, cload(pi), A, D, ng);
-      const Vec<S> f = rhs<S>(A[0], D[0], y);
-      vstore_rows<S>(p.ys, pi, y);
-      vstore_rows<S>(p.fs, pi, f);
-      vstore2<S>(p.sol + pi.b0 * p.sb, pi.ok0, p.sol + pi.b1 * p.sb, pi.ok1, y);
-      Vec<S> scale;
-      const Vec<S> ay = vabs<S>(y);
-#pragma unroll
-      SLODE_FOR_S scale.v[s] = fma2(ay.v[s], rtol2, atol2);
-      part[0] += sumsq_ratio<S>(y, scale, pi);
-      part[1] += sumsq_ratio<S>(f, scale, pi);
-    }
-    block_partials<2>(part, p.partial, 0, sm_red);
-  }
-  grid_barrier(p.barrier);
-  double dt;
-  int64_t n_rhs = 1;
-  if (p.T < 2) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      p.stats[0] = 0; p.stats[1] = 0; p.stats[2] = n_rhs; p.stats[3] = kDopriStatusOk;
-    }
-    return;
-  }
-  if (p.replay) {
-    dt = p.n_replay > 0 ? p.replay[1] : 0.0;
-  } else if (p.first_step > 0.0) {
-    dt = p.first_step;
+  // The solve is a small state machine over "passes" (one sweep over the trajectories that ends in batch-wide
+  // sums).  In the classic mode the kernel loops until the last output time; in STEPPER mode (p.ctrl given: a
+  // trajectory-sharded solve) it runs ONE pass per launch, hands its local sums to the host in
+  // p.out_sums, and the next launch continues from the controller state in p.ctrl with the sums of ALL shards in
+  // p.ext_sums -- so every shard takes the accept / reject decisions and step sizes of the unsharded solve.
+  const bool stepper = p.ctrl != nullptr;
+  Dopri5Ctrl c;
+  if (stepper && !p.restart) {
+    c = *p.ctrl;
   } else {
-    double tot[2];
-    grid_totals<2>(tot, p.partial, 0, sm_red);
-    const float d0 = sqrtf((float)(tot[0] / nelem)), d1 = sqrtf((float)(tot[1] / nelem));
-    const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : __fdiv_rn(__fmul_rn(0.01f, d0), d1);
-    double part[1] = {0.0};
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const PairIdx pi = pair_index(tile, p.B);
-      Vec<S> y, f, A[1], D[1];
-      Gate<H> ng[1];
-      vload_rows<S>(p.ys, pi, y);
-      vload_rows<S>(p.fs, pi, f);
-      const float te[1] = {__fadd_rn((float)t_start, h0)};
-      mlp_eval<H, S, 1, false, 1>(te, cload(pi), A, D, ng);
-      const Vec<S> y1 = vaxpy<S>(h0, f, y);
-      const Vec<S> f1 = rhs<S>(A[0], D[0], y1);
-      Vec<S> scale;
-      const Vec<S> ay = vabs<S>(y);
-#pragma unroll
-      SLODE_FOR_S scale.v[s] = fma2(ay.v[s], rtol2, atol2);
-      part[0] += sumsq_ratio<S>(vsub<S>(f1, f), scale, pi);
-    }
-    block_partials<1>(part, p.partial, 1, sm_red);
-    grid_barrier(p.barrier);
-    double tot2[1];
-    grid_totals<1>(tot2, p.partial, 1, sm_red);
-    n_rhs += 1;
-    const float d2 = __fdiv_rn(sqrtf((float)(tot2[0] / nelem)), h0);
-    float h1;
-    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, __fmul_rn(h0, 1e-3f));
-    else h1 = powf(__fdiv_rn(0.01f, fmaxf(d1, d2)), 1.0f / 5.0f);
-    dt = (double)fminf(__fmul_rn(100.0f, h0), h1);
+    c.phase = kPhStart; c.status = kDopriStatusOk; c.out_idx = 1; c.prev_acc = 0; c.emit_lo = c.emit_hi = 0; c.buf = 0;
+    c.attempt = c.n_acc = c.n_rej = c.n_rhs = 0;
+    c.t_cur = (double)__ldg(p.t); c.dt = 0.0; c.pv_t0 = c.pv_t1 = c.pv_dt = c.a_t0 = c.a_dt = 0.0;
+    c.d1 = c.h0 = 0.0f;
   }
-
-  // ---- adaptive loop ---------------------------------------------------------------------------------------
-  double t_cur = t_start;           // end time of the last accepted step
-  int out_idx = 1;                  // next output time to produce
-  int64_t attempt = 0, n_acc = 0, n_rej = 0;
-  int status = kDopriStatusOk;
-  bool prev_acc = false;            // the previous attempt was accepted and still has to be committed
-  double pv_t0 = 0.0, pv_t1 = 0.0, pv_dt = 0.0;
-  int emit_lo = 0, emit_hi = 0;
-  int buf = 0;
+  const double t_start = (double)__ldg(p.t);
+  double sums[2] = {0.0, 0.0};   // the batch-wide sums the phase in hand consumes
+  if (stepper && !p.restart) { sums[0] = p.ext_sums[0]; sums[1] = p.ext_sums[1]; }
 
   // commit an accepted step for one trajectory pair: interpolated outputs, checkpoint, state <- candidate
   auto commit = [&](const PairIdx& pi, Vec<S>& y, Vec<S>& f) {
@@ -246,9 +184,9 @@ dopri5_fwd_kernel(Dopri5Args p) {
     vload_rows<S>(p.cy1, pi, y1);
     vload_rows<S>(p.cf1, pi, f1);
     vload_rows<S>(p.cym, pi, ym);
-    if (p.ckpt_y) vstore_rows<S>(p.ckpt_y + (size_t)(n_acc - 1) * p.B * S, pi, y);
-    if (emit_hi > emit_lo) {
-      const float dtf = (float)pv_dt;
+    if (p.ckpt_y) vstore_rows<S>(p.ckpt_y + (size_t)(c.n_acc - 1) * p.B * S, pi, y);
+    if (c.emit_hi > c.emit_lo) {
+      const float dtf = (float)c.pv_dt;
       const f2 d2 = bc(dtf);
       Vec<S> ca, cb, cc, cd;
 #pragma unroll
@@ -265,8 +203,8 @@ dopri5_fwd_kernel(Dopri5Args p) {
                             mul2(bc(5.0f), y1.v[s])), mul2(bc(16.0f), ym.v[s]));
         cd.v[s] = mul2(d2, f.v[s]);
       }
-      const float ft0 = (float)pv_t0, ft1 = (float)pv_t1;
-      for (int i = emit_lo; i < emit_hi; ++i) {
+      const float ft0 = (float)c.pv_t0, ft1 = (float)c.pv_t1;
+      for (int i = c.emit_lo; i < c.emit_hi; ++i) {
         const float x = __fdiv_rn(__fsub_rn(__ldg(p.t + i), ft0), __fsub_rn(ft1, ft0));
         const f2 x1 = bc(x);
         Vec<S> o;
@@ -289,88 +227,112 @@ dopri5_fwd_kernel(Dopri5Args p) {
     vstore_rows<S>(p.ys, pi, y);
     vstore_rows<S>(p.fs, pi, f);
   };
-
-  while (out_idx < p.T) {
-    if (attempt >= p.max_attempts) { status = kDopriStatusMaxSteps; break; }
-    if (p.replay) {  // prescribed step sequence (tests / replaying a logged solve): dt and the decision are given
-      if (attempt >= p.n_replay) { status = kDopriStatusReplayShort; break; }
-      dt = p.replay[attempt * 3 + 1];
+  auto write_stats = [&]() {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      p.stats[0] = c.n_acc; p.stats[1] = c.n_rej; p.stats[2] = c.n_rhs; p.stats[3] = c.status;
+      if (stepper) *p.ctrl = c;
     }
-    const double a_t0 = t_cur, a_dt = dt, a_t1 = a_t0 + a_dt;
-    if (!(a_t1 > a_t0)) { status = kDopriStatusUnderflow; break; }
-    if (p.ckpt_y && n_acc >= p.ckpt_cap) { status = kDopriStatusCkptFull; break; }
-    const float ft0 = (float)a_t0, fdt = (float)a_dt, ft1 = (float)a_t1;
-    float te[5];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) te[e] = __fadd_rn(ft0, __fmul_rn(kDpAlpha[e], fdt));
-    te[4] = ft1;
-
-    double part[1] = {0.0};
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const PairIdx pi = pair_index(tile, p.B);
-      Vec<S> y, k[7];
-      vload_rows<S>(p.ys, pi, y);
-      vload_rows<S>(p.fs, pi, k[0]);
-      if (prev_acc) commit(pi, y, k[0]);
-      Vec<S> A[5], D[5];
-      Gate<H> ng[5];
-      mlp_eval<H, S, 5, false, 0>(te, cload(pi), A, D, ng);
-      Vec<S> yi;
-      yi = combine<S, 1>(y, k, kDpBeta[0], fdt); k[1] = rhs<S>(A[0], D[0], yi);
-      yi = combine<S, 2>(y, k, kDpBeta[1], fdt); k[2] = rhs<S>(A[1], D[1], yi);
-      yi = combine<S, 3>(y, k, kDpBeta[2], fdt); k[3] = rhs<S>(A[2], D[2], yi);
-      yi = combine<S, 4>(y, k, kDpBeta[3], fdt); k[4] = rhs<S>(A[3], D[3], yi);
-      yi = combine<S, 5>(y, k, kDpBeta[4], fdt); k[5] = rhs<S>(A[4], D[4], yi);
-      const Vec<S> y1 = combine<S, 6>(y, k, kDpBeta[5], fdt);
-      k[6] = rhs<S>(A[4], D[4], y1);
-      // error estimate and tolerance
-      Vec<S> err, tol;
-      {
-        Vec<S> zero;
-#pragma unroll
-        SLODE_FOR_S zero.v[s] = 0ull;
-        err = combine<S, 7>(zero, k, kDpCErr, fdt);
-        const Vec<S> a0 = vabs<S>(y), a1 = vabs<S>(y1);
-#pragma unroll
-        SLODE_FOR_S {
-          float p0, p1, q0, q1;
-          unpk(a0.v[s], p0, p1);
-          unpk(a1.v[s], q0, q1);
-          tol.v[s] = fma2(pk(fmaxf(p0, q0), fmaxf(p1, q1)), rtol2, atol2);
-        }
-      }
-      part[0] += sumsq_ratio<S>(err, tol, pi);
-      vstore_rows<S>(p.cy1, pi, y1);
-      vstore_rows<S>(p.cf1, pi, k[6]);
-      vstore_rows<S>(p.cym, pi, combine<S, 7>(y, k, kDpCMid, fdt));
-    }
-    block_partials<1>(part, p.partial, buf, sm_red);
+  };
+  // the local sums of a finished pass -> (classic) consumed as they are / (stepper) handed to the host
+  auto finish_pass = [&](double (&part)[2]) {
+    block_partials<2>(part, p.partial, c.buf, sm_red);
     grid_barrier(p.barrier);
-    double tot[1];
-    grid_totals<1>(tot, p.partial, buf, sm_red);
-    buf ^= 1;
-    n_rhs += 6;
-    const float ratio = sqrtf((float)(tot[0] / nelem));
-    const bool accept = p.replay ? (p.replay[attempt * 3 + 2] != 0.0) : (ratio <= 1.0f);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && p.step_log && attempt < p.log_cap) {
-      p.step_log[attempt * 3 + 0] = a_t0;
-      p.step_log[attempt * 3 + 1] = a_dt;
-      p.step_log[attempt * 3 + 2] = accept ? 1.0 : 0.0;
-    }
-    ++attempt;
-    if (accept) {
-      ++n_acc;
-      pv_t0 = a_t0; pv_t1 = a_t1; pv_dt = a_dt;
-      t_cur = a_t1;
-      emit_lo = out_idx;
-      while (out_idx < p.T && (double)__ldg(p.t + out_idx) <= a_t1) ++out_idx;
-      emit_hi = out_idx;
-    } else {
-      ++n_rej;
-    }
-    prev_acc = accept;
-    // torchdiffeq _optimal_step_size (float64)
-    {
+    grid_totals<2>(sums, p.partial, c.buf, sm_red);
+    c.buf ^= 1;
+  };
+
+  for (;;) {
+    bool handed_over = false;   // a pass ended whose sums the next phase needs
+    if (c.phase == kPhStart) {
+      // ---- f0 = func(t[0], y0); sol[0] = y0; norms d0, d1 of Hairer's initial step -------------------------
+      double part[2] = {0.0, 0.0};
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const PairIdx pi = pair_index(tile, p.B);
+        Vec<S> y, A[1], D[1];
+        Gate<H> ng[1];
+        vload_rows<S>(p.y0, pi, y);
+        const float te[1] = {(float)t_start};
+        mlp_eval<H, S, 1, false, 0>(te, cload(pi), A, D, ng);
+        const Vec<S> f = rhs<S>(A[0], D[0], y);
+        vstore_rows<S>(p.ys, pi, y);
+        vstore_rows<S>(p.fs, pi, f);
+        vstore2<S>(p.sol + pi.b0 * p.sb, pi.ok0, p.sol + pi.b1 * p.sb, pi.ok1, y);
+        Vec<S> scale;
+        const Vec<S> ay = vabs<S>(y);
+#pragma unroll
+        SLODE_FOR_S scale.v[s] = fma2(ay.v[s], rtol2, atol2);
+        part[0] += sumsq_ratio<S>(y, scale, pi);
+        part[1] += sumsq_ratio<S>(f, scale, pi);
+      }
+      finish_pass(part);
+      c.n_rhs = 1;
+      if (p.T < 2) {
+        c.phase = kPhDone;
+      } else if (p.replay) {
+        c.dt = p.n_replay > 0 ? p.replay[1] : 0.0;
+        c.phase = kPhAttempt;
+      } else if (p.first_step > 0.0) {
+        c.dt = p.first_step;
+        c.phase = kPhAttempt;
+      } else {
+        c.phase = kPhProbe;
+        handed_over = true;
+      }
+    } else if (c.phase == kPhProbe) {
+      const float d0 = sqrtf((float)(sums[0] / nelem)), d1 = sqrtf((float)(sums[1] / nelem));
+      const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : __fdiv_rn(__fmul_rn(0.01f, d0), d1);
+      c.d1 = d1;
+      c.h0 = h0;
+      double part[2] = {0.0, 0.0};
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const PairIdx pi = pair_index(tile, p.B);
+        Vec<S> y, f, A[1], D[1];
+        Gate<H> ng[1];
+        vload_rows<S>(p.ys, pi, y);
+        vload_rows<S>(p.fs, pi, f);
+        const float te[1] = {__fadd_rn((float)t_start, h0)};
+        mlp_eval<H, S, 1, false, 1>(te, cload(pi), A, D, ng);
+        const Vec<S> y1 = vaxpy<S>(h0, f, y);
+        const Vec<S> f1 = rhs<S>(A[0], D[0], y1);
+        Vec<S> scale;
+        const Vec<S> ay = vabs<S>(y);
+#pragma unroll
+        SLODE_FOR_S scale.v[s] = fma2(ay.v[s], rtol2, atol2);
+        part[0] += sumsq_ratio<S>(vsub<S>(f1, f), scale, pi);
+      }
+      finish_pass(part);
+      c.n_rhs += 1;
+      c.phase = kPhFirstDt;
+      handed_over = true;
+    } else if (c.phase == kPhFirstDt) {
+      const float d1 = c.d1, h0 = c.h0;
+      const float d2 = __fdiv_rn(sqrtf((float)(sums[0] / nelem)), h0);
+      float h1;
+      if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, __fmul_rn(h0, 1e-3f));
+      else h1 = powf(__fdiv_rn(0.01f, fmaxf(d1, d2)), 1.0f / 5.0f);
+      c.dt = (double)fminf(__fmul_rn(100.0f, h0), h1);
+      c.phase = kPhAttempt;
+    } else if (c.phase == kPhDecide) {
+      // ---- accept / reject the attempt in hand and choose the next step size (torchdiffeq _optimal_step_size) --
+      const float ratio = sqrtf((float)(sums[0] / nelem));
+      const bool accept = p.replay ? (p.replay[c.attempt * 3 + 2] != 0.0) : (ratio <= 1.0f);
+      if (blockIdx.x == 0 && threadIdx.x == 0 && p.step_log && c.attempt < p.log_cap) {
+        p.step_log[c.attempt * 3 + 0] = c.a_t0;
+        p.step_log[c.attempt * 3 + 1] = c.a_dt;
+        p.step_log[c.attempt * 3 + 2] = accept ? 1.0 : 0.0;
+      }
+      ++c.attempt;
+      if (accept) {
+        ++c.n_acc;
+        c.pv_t0 = c.a_t0; c.pv_t1 = c.a_t0 + c.a_dt; c.pv_dt = c.a_dt;
+        c.t_cur = c.pv_t1;
+        c.emit_lo = c.out_idx;
+        while (c.out_idx < p.T && (double)__ldg(p.t + c.out_idx) <= c.pv_t1) ++c.out_idx;
+        c.emit_hi = c.out_idx;
+      } else {
+        ++c.n_rej;
+      }
+      c.prev_acc = accept ? 1 : 0;
       double factor;
       if (ratio == 0.0f) {
         factor = 10.0;
@@ -378,22 +340,101 @@ dopri5_fwd_kernel(Dopri5Args p) {
         const double dfac = (ratio < 1.0f) ? 1.0 : 0.2;
         factor = fmin(10.0, fmax(0.9 / pow((double)ratio, 0.2), dfac));
       }
-      dt = a_dt * factor;
+      c.dt = c.a_dt * factor;
+      c.phase = kPhAttempt;
+    } else if (c.phase == kPhAttempt) {
+      bool stop = !(c.out_idx < p.T);
+      if (!stop && c.attempt >= p.max_attempts) { c.status = kDopriStatusMaxSteps; stop = true; }
+      if (!stop && p.replay) {  // prescribed step sequence (tests / replaying a logged solve): dt and the decision are given
+        if (c.attempt >= p.n_replay) { c.status = kDopriStatusReplayShort; stop = true; }
+        else c.dt = p.replay[c.attempt * 3 + 1];
+      }
+      const double a_t0 = c.t_cur, a_dt = c.dt, a_t1 = a_t0 + a_dt;
+      if (!stop && !(a_t1 > a_t0)) { c.status = kDopriStatusUnderflow; stop = true; }
+      if (!stop && p.ckpt_y && c.n_acc >= p.ckpt_cap) { c.status = kDopriStatusCkptFull; stop = true; }
+      if (stop) {
+        if (c.prev_acc) {  // commit the last accepted step
+          for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const PairIdx pi = pair_index(tile, p.B);
+            Vec<S> y, f;
+            vload_rows<S>(p.ys, pi, y);
+            vload_rows<S>(p.fs, pi, f);
+            commit(pi, y, f);
+          }
+          c.prev_acc = 0;
+        }
+        c.phase = kPhDone;
+      } else {
+        const float ft0 = (float)a_t0, fdt = (float)a_dt, ft1 = (float)a_t1;
+        float te[5];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) te[e] = __fadd_rn(ft0, __fmul_rn(kDpAlpha[e], fdt));
+        te[4] = ft1;
+        double part[2] = {0.0, 0.0};
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          const PairIdx pi = pair_index(tile, p.B);
+          Vec<S> y, k[7];
+          vload_rows<S>(p.ys, pi, y);
+          vload_rows<S>(p.fs, pi, k[0]);
+          if (c.prev_acc) commit(pi, y, k[0]);
+          Vec<S> A[5], D[5];
+          Gate<H> ng[5];
+          mlp_eval<H, S, 5, false, 0>(te, cload(pi), A, D, ng);
+          Vec<S> yi;
+          yi = combine<S, 1>(y, k, kDpBeta[0], fdt); k[1] = rhs<S>(A[0], D[0], yi);
+          yi = combine<S, 2>(y, k, kDpBeta[1], fdt); k[2] = rhs<S>(A[1], D[1], yi);
+          yi = combine<S, 3>(y, k, kDpBeta[2], fdt); k[3] = rhs<S>(A[2], D[2], yi);
+          yi = combine<S, 4>(y, k, kDpBeta[3], fdt); k[4] = rhs<S>(A[3], D[3], yi);
+          yi = combine<S, 5>(y, k, kDpBeta[4], fdt); k[5] = rhs<S>(A[4], D[4], yi);
+          const Vec<S> y1 = combine<S, 6>(y, k, kDpBeta[5], fdt);
+          k[6] = rhs<S>(A[4], D[4], y1);
+          // error estimate and tolerance
+          Vec<S> err, tol;
+          {
+            Vec<S> zero;
+#pragma unroll
+            SLODE_FOR_S zero.v[s] = 0ull;
+            err = combine<S, 7>(zero, k, kDpCErr, fdt);
+            const Vec<S> a0 = vabs<S>(y), a1 = vabs<S>(y1);
+#pragma unroll
+            SLODE_FOR_S {
+              float p0, p1, q0, q1;
+              unpk(a0.v[s], p0, p1);
+              unpk(a1.v[s], q0, q1);
+              tol.v[s] = fma2(pk(fmaxf(p0, q0), fmaxf(p1, q1)), rtol2, atol2);
+            }
+          }
+          part[0] += sumsq_ratio<S>(err, tol, pi);
+          vstore_rows<S>(p.cy1, pi, y1);
+          vstore_rows<S>(p.cf1, pi, k[6]);
+          vstore_rows<S>(p.cym, pi, combine<S, 7>(y, k, kDpCMid, fdt));
+        }
+        c.prev_acc = 0;   // committed above
+        finish_pass(part);
+        c.n_rhs += 6;
+        c.a_t0 = a_t0;
+        c.a_dt = a_dt;
+        c.phase = kPhDecide;
+        handed_over = true;
+      }
     }
+    if (c.phase == kPhDone) break;
+    if (stepper && handed_over) break;
   }
-  // commit the last accepted step
-  if (prev_acc) {
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const PairIdx pi = pair_index(tile, p.B);
-      Vec<S> y, f;
-      vload_rows<S>(p.ys, pi, y);
-      vload_rows<S>(p.fs, pi, f);
-      commit(pi, y, f);
-    }
+  if (stepper && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.out_sums[0] = sums[0];
+    p.out_sums[1] = sums[1];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    p.stats[0] = n_acc; p.stats[1] = n_rej; p.stats[2] = n_rhs; p.stats[3] = status;
-  }
+  write_stats();
+  if (stepper && blockIdx.x == 0 && threadIdx.x == 0) p.stats[4] = c.phase;
+}
+
+// bytes of scratch of a forward solve: state arrays, per-block partial sums (sized for the largest grid a device of
+// `sms` SMs can hold), barrier counter, controller state
+inline size_t dopri5_scratch_bytes(int64_t B, int S, int sms) {
+  const size_t nstate = (size_t)B * S;
+  return (sizeof(float) * 5 * nstate + 255) / 256 * 256 + (sizeof(double) * 6 * (size_t)sms * 4 + 255) / 256 * 256 + 256 +
+         (sizeof(Dopri5Ctrl) + 255) / 256 * 256;
 }
 
 template <int H, int S>
@@ -408,11 +449,21 @@ int launch_dopri5_fwd(Dopri5Args a, const PackSrc& w, float* staging, cudaStream
     blocks_per_sm = std::max(n, 1);
   }
   const int64_t tiles = ((a.B + 1) / 2 + kBlock - 1) / kBlock;
-  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * blocks_per_sm);
-  // scratch: 5 state arrays, partial sums, barrier counter
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::min(blocks_per_sm, 4));
+  // scratch: 5 state arrays, partial sums, barrier counter (+ the controller state in stepper mode, where the
+  // caller owns the workspace because it has to survive between the launches of one solve)
   const size_t nstate = (size_t)a.B * S;
-  const size_t bytes = sizeof(float) * 5 * nstate + 256 + sizeof(double) * 6 * (size_t)grid + 256;
-  char* ws = reinterpret_cast<char*>(flip_workspace(bytes));
+  const size_t bytes = dopri5_scratch_bytes(a.B, S, sms);
+  char* ws;
+  if (a.step_ws) {
+    if (a.step_ws_bytes < bytes || (reinterpret_cast<uintptr_t>(a.step_ws) & 255)) {
+      set_error("dopri5 stepper: workspace of %zu bytes given (256-byte aligned?), %zu needed", a.step_ws_bytes, bytes);
+      return SLODE_EINVAL;
+    }
+    ws = static_cast<char*>(a.step_ws);
+  } else {
+    ws = reinterpret_cast<char*>(flip_workspace(bytes));
+  }
   if (!ws) return SLODE_ECUDA;
   a.ys = reinterpret_cast<float*>(ws);
   a.fs = a.ys + nstate;
@@ -421,8 +472,10 @@ int launch_dopri5_fwd(Dopri5Args a, const PackSrc& w, float* staging, cudaStream
   a.cym = a.cf1 + nstate;
   size_t off = (sizeof(float) * 5 * nstate + 255) / 256 * 256;
   a.partial = reinterpret_cast<double*>(ws + off);
-  off += (sizeof(double) * 6 * (size_t)grid + 255) / 256 * 256;
+  off += (sizeof(double) * 6 * (size_t)sms * 4 + 255) / 256 * 256;
   a.barrier = reinterpret_cast<unsigned long long*>(ws + off);
+  off += 256;
+  if (a.step_ws) a.ctrl = reinterpret_cast<Dopri5Ctrl*>(ws + off);
   SLODE_CUDA_TRY(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned long long), stream));
   void* args[] = {&a};
   SLODE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kBlock), args, 0, stream));

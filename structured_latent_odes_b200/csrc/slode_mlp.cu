@@ -34,6 +34,13 @@ const FixedShapeEntry* find_fixed_shape(int H, int S) {
   return nullptr;
 }
 
+// mirrors dopri5_scratch_bytes of slode_dopri5_kernels.cuh (that header is only included by the shape units)
+static size_t dopri5_scratch_bytes_host(int64_t B, int S, int sms) {
+  const size_t nstate = (size_t)B * S;
+  return (sizeof(float) * 5 * nstate + 255) / 256 * 256 + (sizeof(double) * 6 * (size_t)sms * 4 + 255) / 256 * 256 + 256 +
+         (sizeof(Dopri5Ctrl) + 255) / 256 * 256;
+}
+
 static int check_common(const char* who, int64_t B, int T, int H, int S) {
   if (B < 0 || T < 1 || H < 1 || S < 1) {
     set_error("%s: bad sizes B=%lld T=%d H=%d S=%d", who, (long long)B, T, H, S);
@@ -79,33 +86,28 @@ extern "C" int slode_query(int what) {
   return -1;
 }
 
-extern "C" int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S, const float* t, const float* c, const float* y0,
-                                    const float* w1t, const float* Wg, const float* bg, const float* Wd,
-                                    const float* bd, double rtol, double atol, double first_step,
-                                    int64_t max_attempts, const double* replay_steps, int64_t n_replay, float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
-                                    float* ckpt_y, int64_t ckpt_capacity, double* step_log, int64_t log_capacity,
-                                    int64_t* stats, void* stream_) {
-  int rc = check_common("slode_mlp_dopri5_fwd", B, T, H, S);
+static int dopri5_fwd_common(const char* who, int64_t B, int T, int H, int S, const float* t, const float* c,
+                             const float* y0, const float* w1t, const float* Wg, const float* bg, const float* Wd,
+                             const float* bd, double rtol, double atol, double first_step, int64_t max_attempts,
+                             const double* replay_steps, int64_t n_replay, float* sol, int64_t sol_stride_t,
+                             int64_t sol_stride_b, float* ckpt_y, int64_t ckpt_capacity, double* step_log,
+                             int64_t log_capacity, int64_t* stats, Dopri5Args step, cudaStream_t stream) {
+  int rc = check_common(who, B, T, H, S);
   if (rc) return rc;
   if (!(rtol >= 0.0) || !(atol >= 0.0) || (rtol == 0.0 && atol == 0.0) || max_attempts < 1 || ckpt_capacity < 0 ||
       log_capacity < 0) {
-    set_error("slode_mlp_dopri5_fwd: bad tolerances / capacities (rtol=%g atol=%g max_attempts=%lld)", rtol, atol,
+    set_error("%s: bad tolerances / capacities (rtol=%g atol=%g max_attempts=%lld)", who, rtol, atol,
               (long long)max_attempts);
     return SLODE_EINVAL;
   }
   if (!t || !w1t || !Wg || !bg || !Wd || !bd || !stats || (B > 0 && (!c || !y0 || !sol))) {
-    set_error("slode_mlp_dopri5_fwd: null pointer");
+    set_error("%s: null pointer", who);
     return SLODE_EINVAL;
   }
   g_fwd_launches = 0;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (B == 0) {
-    if (cudaMemsetAsync(stats, 0, 4 * sizeof(int64_t), stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "memset");
-    return SLODE_OK;
-  }
   PackGuard guard(stream);
   if (guard.status) return guard.status;
-  Dopri5Args a{};
+  Dopri5Args a = step;
   a.B = B; a.T = T; a.t = t; a.c = c; a.y0 = y0; a.sol = sol; a.st = sol_stride_t; a.sb = sol_stride_b;
   a.rtol = (float)rtol; a.atol = (float)atol; a.first_step = first_step; a.max_attempts = max_attempts;
   a.replay = replay_steps; a.n_replay = replay_steps ? n_replay : 0;
@@ -114,6 +116,61 @@ extern "C" int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S, const float*
   rc = find_shape(H, S)->dopri5_fwd(a, w, guard.staging, stream, guard.sms);
   if (rc == SLODE_OK) g_fwd_launches = 2;
   return rc;
+}
+
+extern "C" int slode_mlp_dopri5_fwd(int64_t B, int T, int H, int S, const float* t, const float* c, const float* y0,
+                                    const float* w1t, const float* Wg, const float* bg, const float* Wd,
+                                    const float* bd, double rtol, double atol, double first_step,
+                                    int64_t max_attempts, const double* replay_steps, int64_t n_replay, float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                                    float* ckpt_y, int64_t ckpt_capacity, double* step_log, int64_t log_capacity,
+                                    int64_t* stats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (B == 0) {
+    if (!stats) {
+      set_error("slode_mlp_dopri5_fwd: null pointer");
+      return SLODE_EINVAL;
+    }
+    if (cudaMemsetAsync(stats, 0, 4 * sizeof(int64_t), stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "memset");
+    return SLODE_OK;
+  }
+  return dopri5_fwd_common("slode_mlp_dopri5_fwd", B, T, H, S, t, c, y0, w1t, Wg, bg, Wd, bd, rtol, atol, first_step,
+                           max_attempts, replay_steps, n_replay, sol, sol_stride_t, sol_stride_b, ckpt_y, ckpt_capacity,
+                           step_log, log_capacity, stats, Dopri5Args{}, stream);
+}
+
+extern "C" int64_t slode_mlp_dopri5_step_workspace_bytes(int64_t B, int S) {
+  if (B < 1 || S < 1) {
+    set_error("slode_mlp_dopri5_step_workspace_bytes: bad sizes");
+    return -1;
+  }
+  int sms = 0;
+  if (device_sms(&sms)) return -1;
+  return (int64_t)dopri5_scratch_bytes_host(B, S, sms);
+}
+
+extern "C" int slode_mlp_dopri5_fwd_step(int64_t B, int T, int H, int S, const float* t, const float* c,
+                                         const float* y0, const float* w1t, const float* Wg, const float* bg,
+                                         const float* Wd, const float* bd, double rtol, double atol,
+                                         double first_step, int64_t max_attempts, int64_t n_global, int restart,
+                                         const double* ext_sums, double* out_sums, float* sol, int64_t sol_stride_t,
+                                         int64_t sol_stride_b, float* ckpt_y, int64_t ckpt_capacity, double* step_log,
+                                         int64_t log_capacity, int64_t* stats, void* workspace, int64_t workspace_bytes,
+                                         void* stream_) {
+  if (B < 1 || n_global < B || !ext_sums || !out_sums || !workspace) {
+    set_error("slode_mlp_dopri5_fwd_step: needs a non-empty shard (B=%lld of n_global=%lld), ext_sums, out_sums and a "
+              "workspace", (long long)B, (long long)n_global);
+    return SLODE_EINVAL;
+  }
+  Dopri5Args step{};
+  step.restart = restart ? 1 : 0;
+  step.n_global = n_global;
+  step.ext_sums = ext_sums;
+  step.out_sums = out_sums;
+  step.step_ws = workspace;
+  step.step_ws_bytes = (size_t)workspace_bytes;
+  return dopri5_fwd_common("slode_mlp_dopri5_fwd_step", B, T, H, S, t, c, y0, w1t, Wg, bg, Wd, bd, rtol, atol,
+                           first_step, max_attempts, nullptr, 0, sol, sol_stride_t, sol_stride_b, ckpt_y, ckpt_capacity,
+                           step_log, log_capacity, stats, step, (cudaStream_t)stream_);
 }
 
 extern "C" int slode_mlp_dopri5_bwd(int64_t B, int T, int H, int S, const float* t, const float* c, const float* w1t,

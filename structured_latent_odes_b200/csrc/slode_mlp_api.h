@@ -54,6 +54,16 @@ struct BwdArgs {
   size_t ws_bytes;
 };
 
+// Controller state of a dopri5 solve that is advanced one pass per launch (stepper mode: trajectory-sharded solves
+// whose batch-wide sums are combined across shards by the host between launches)
+struct Dopri5Ctrl {
+  int phase, status, out_idx, prev_acc, emit_lo, emit_hi, buf, pad_;
+  long long attempt, n_acc, n_rej, n_rhs;
+  double t_cur, dt, pv_t0, pv_t1, pv_dt, a_t0, a_dt;
+  float d1, h0;
+};
+enum { kPhStart = 0, kPhProbe = 1, kPhFirstDt = 2, kPhAttempt = 3, kPhDecide = 4, kPhDone = 5 };
+
 // dopri5 forward (slode_dopri5_kernels.cuh); scratch pointers are filled in by the launcher
 struct Dopri5Args {
   int64_t B;
@@ -76,6 +86,15 @@ struct Dopri5Args {
   double* step_log;     // (log_cap, 3): t0, dt, accepted(1/0) of every attempted step
   int64_t log_cap;
   int64_t* stats;       // [0] accepted, [1] rejected, [2] RHS evaluations per trajectory, [3] status (0 ok)
+                        // (stepper mode: [4] phase after this launch, kPhDone when the solve is over)
+  // stepper mode (ctrl != null): caller-owned workspace, one pass per launch
+  Dopri5Ctrl* ctrl;
+  int restart;             // 1: first launch of a solve (ctrl is initialised by the kernel)
+  int64_t n_global;        // trajectories over ALL shards (the norms' element count); 0: B
+  const double* ext_sums;  // [2] sums over all shards of the previous launch's out_sums
+  double* out_sums;        // [2] this shard's sums of the pass this launch ran
+  void* step_ws;           // caller workspace holding the state arrays, partial sums, barrier and ctrl
+  size_t step_ws_bytes;
 };
 
 // dopri5 reverse sweep; flip_ws is filled in by the launcher

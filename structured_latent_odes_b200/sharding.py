@@ -67,3 +67,26 @@ class FlatGradReducer:
         torch._foreach_copy_([p.grad.view(-1) if p.grad.is_contiguous() else p.grad for p in self.params],
                              [v if p.grad.is_contiguous() else v.view_as(p) for p, v in zip(self.params, views)])
         return self.flat
+
+
+def dopri5_shard_options(local_batch: int, group=None, device=None, options=None):
+    """``options`` for ``odeint(..., method="dopri5")`` on ONE shard of a trajectory-sharded batch.
+
+    torchdiffeq's dopri5 takes one step size for the whole batch (error norm over all B*S elements),
+    so a sharded solve has a real exchange step: per attempted step one all-reduce of two float64 sums.  The returned
+    options make the solver run one pass per launch and sum the batch-wide norms over ``group`` in between
+    (``torchdiffeq_api.Dopri5ShardSolve``); every rank then takes the step sequence of the unsharded solve."""
+    n = torch.tensor([int(local_batch)], dtype=torch.int64, device=device)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world > 1:
+        dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+
+    def reducer(x):
+        if world > 1:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+        return x
+
+    out = dict(options or {})
+    out["shard_reducer"] = reducer
+    out["global_batch"] = int(n.item())
+    return out

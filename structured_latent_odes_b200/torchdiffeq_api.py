@@ -384,29 +384,111 @@ _DOPRI5_STATUS = {1: "underflow in dt", 2: "max_num_steps exceeded", 3: "checkpo
                   4: "replay_steps ended before the last output time"}
 
 
+class Dopri5ShardSolve:
+    """One shard of a dopri5 forward solve whose batch is split over several devices / processes
+    (``slode_mlp_dopri5_fwd_step``).  torchdiffeq's controller is batch-global: ``step()`` runs ONE pass over this
+    shard and leaves the shard's sums of squares in ``self.out`` (device float64[2]); the caller adds ``out`` over all
+    shards, hands the total back through ``self.ext`` and steps again until ``step()`` returns True.  Every shard then
+    takes the accept / reject decisions and the step sizes of the unsharded solve."""
+
+    def __init__(self, y0, c, w, t, rtol, atol, n_global, first_step=None, max_num_steps=1 << 20, log_cap=0,
+                 ckpt_cap=0, layout="tbs"):
+        B, S = y0.shape
+        if B < 1:
+            raise ValueError("a dopri5 shard may not be empty (give every rank at least one trajectory)")
+        dev = y0.device
+        self.args = (y0, c, w, t)
+        self.B, self.S, self.H, self.T = B, S, c.shape[1], t.numel()
+        self.cfg = (float(rtol), float(atol), float(first_step) if first_step is not None else -1.0, int(max_num_steps),
+                    int(n_global))
+        if layout == "bts":
+            self.sol = torch.empty((B, self.T, S), device=dev, dtype=torch.float32).permute(1, 0, 2)
+        else:
+            self.sol = torch.empty((self.T, B, S), device=dev, dtype=torch.float32)
+        self.ckpt = torch.empty((ckpt_cap, B, S), device=dev, dtype=torch.float32) if ckpt_cap else None
+        self.log = torch.zeros((log_cap, 3), device=dev, dtype=torch.float64) if log_cap else None
+        self.stats = torch.zeros(5, device=dev, dtype=torch.int64)
+        self.ext = torch.zeros(2, device=dev, dtype=torch.float64)
+        self.out = torch.zeros(2, device=dev, dtype=torch.float64)
+        n = _cabi.lib().slode_mlp_dopri5_step_workspace_bytes(B, S)
+        if n < 0:
+            raise _cabi.SlodeError("slode_mlp_dopri5_step_workspace_bytes: "
+                                   + _cabi.lib().slode_last_error().decode("utf-8", "replace"))
+        self.ws = torch.empty(n, device=dev, dtype=torch.uint8)
+        self.restart = 1
+        self.done = False
+
+    def step(self):
+        y0, c, w, t = self.args
+        rtol, atol, first_step, max_steps, n_global = self.cfg
+        with torch.cuda.device(y0.device), _timed("fwd"):
+            rc = _cabi.lib().slode_mlp_dopri5_fwd_step(
+                self.B, self.T, self.H, self.S, _ptr(t), _ptr(c), _ptr(y0), *[_ptr(x) for x in w], rtol, atol, first_step,
+                max_steps, n_global, self.restart, _ptr(self.ext), _ptr(self.out), _ptr(self.sol), self.sol.stride(0),
+                self.sol.stride(1), _ptr(self.ckpt), self.ckpt.shape[0] if self.ckpt is not None else 0, _ptr(self.log),
+                self.log.shape[0] if self.log is not None else 0, _ptr(self.stats), _ptr(self.ws), self.ws.numel(),
+                torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_mlp_dopri5_fwd_step")
+        self.restart = 0
+        self.done = int(self.stats[4].item()) == 5   # the host has to know when to stop: one small read per pass
+        return self.done
+
+    def result(self):
+        n_acc, n_rej, n_rhs, status = (int(v) for v in self.stats[:4].tolist())
+        return n_acc, n_rej, n_rhs, status
+
+
 def _dopri5_forward(y0, c, w, t, rtol, atol, options, layout, want_ckpt):
-    """Runs slode_mlp_dopri5_fwd; returns (sol, ckpt or None, steps (n,3) float64 device tensor or None)."""
+    """Runs slode_mlp_dopri5_fwd; returns (sol, ckpt or None, steps (n,3) float64 device tensor or None).
+
+    ``options["shard_reducer"]`` (a callable that sums a device float64 tensor over all shards in place, e.g.
+    ``lambda x: dist.all_reduce(x)``) together with ``options["global_batch"]`` switches to the sharded solve: one
+    pass per launch with the batch-wide sums combined across the shards (``Dopri5ShardSolve``)."""
     opts = dict(options or {})
     first_step = opts.pop("first_step", None)
     max_num_steps = int(opts.pop("max_num_steps", 1 << 20))
     log_steps = bool(opts.pop("log_steps", False)) or want_ckpt
     replay = opts.pop("replay_steps", None)
+    reducer = opts.pop("shard_reducer", None)
+    n_global = opts.pop("global_batch", None)
     if replay is not None:
         replay = torch.as_tensor(replay, dtype=torch.float64).reshape(-1, 3).to(y0.device).contiguous()
     if opts:
         raise NotImplementedError(f"dopri5 options {sorted(opts)} are not supported (supported: first_step, "
-                                  "max_num_steps, log_steps, replay_steps)")
+                                  "max_num_steps, log_steps, replay_steps, shard_reducer + global_batch)")
+    if (reducer is None) != (n_global is None):
+        raise ValueError("shard_reducer and global_batch go together")
+    if reducer is not None and replay is not None:
+        raise NotImplementedError("replay_steps in a sharded dopri5 solve")
     B, S = y0.shape
     H = c.shape[1]
     T = t.numel()
     dev = y0.device
+    cap = 64 if want_ckpt else 0
+    log_cap = 4096 if log_steps else 0
+    if reducer is not None:
+        while True:
+            sh = Dopri5ShardSolve(y0, c, w, t, rtol, atol, n_global, first_step, max_num_steps, log_cap, cap, layout)
+            while not sh.step():
+                sh.ext.copy_(sh.out)
+                reducer(sh.ext)
+            n_acc, n_rej, n_rhs, status = sh.result()
+            if status == 3 or (log_cap and n_acc + n_rej > log_cap):   # identical on every shard: all of them re-run
+                cap = max(2 * cap, 64) if want_ckpt else 0
+                log_cap = max(2 * log_cap, n_acc + n_rej) if log_cap else 0
+                continue
+            if status != 0:
+                raise _cabi.SlodeError(f"dopri5: {_DOPRI5_STATUS.get(status, status)} after {n_acc + n_rej} attempted steps")
+            break
+        last_dopri5_stats.n_accept, last_dopri5_stats.n_reject, last_dopri5_stats.n_rhs = n_acc, n_rej, n_rhs
+        steps = sh.log[: n_acc + n_rej] if sh.log is not None else None
+        last_dopri5_stats.steps = steps.cpu() if steps is not None else None
+        return sh.sol, (sh.ckpt[:n_acc] if sh.ckpt is not None else None), steps
     if layout == "bts":
         sol = torch.empty((B, T, S), device=dev, dtype=torch.float32).permute(1, 0, 2)
     else:
         sol = torch.empty((T, B, S), device=dev, dtype=torch.float32)
     stats = torch.zeros(4, device=dev, dtype=torch.int64)
-    cap = 64 if want_ckpt else 0
-    log_cap = 4096 if log_steps else 0
     while True:
         ckpt = torch.empty((cap, B, S), device=dev, dtype=torch.float32) if cap else None
         log = torch.zeros((log_cap, 3), device=dev, dtype=torch.float64) if log_cap else None
@@ -524,10 +606,15 @@ class _MlpDopri5AdjointSolve(torch.autograd.Function):
         W1c, b1c = W1.detach().contiguous(), b1.detach().contiguous()
         c = torch.addmm(b1c, zc, W1c[:, 1:].t()).contiguous()
         hw = [x.detach().contiguous() for x in (Wg, bg, Wd, bd)]
-        sol, _, _ = _dopri5_forward(y0.detach().contiguous(), c, [W1c[:, 0].contiguous()] + hw, t, rtol, atol, options,
+        fwd_opts = {k: v for k, v in (options or {}).items() if k != "adjoint_replay_steps"}
+        sol, _, _ = _dopri5_forward(y0.detach().contiguous(), c, [W1c[:, 0].contiguous()] + hw, t, rtol, atol, fwd_opts,
                                     layout, want_ckpt=False)
         ctx.save_for_backward(zc, c, W1c, *hw, t, sol)
         opts = dict(options or {})
+        replay = opts.get("adjoint_replay_steps")   # (n,4) rows of a backward step log to take instead of controlling
+        if replay is not None:
+            replay = torch.as_tensor(replay, dtype=torch.float64).reshape(-1, 4).to(sol.device).contiguous()
+        ctx.replay = replay
         ctx.cfg = (float(rtol), float(atol), int(opts.get("max_num_steps", 1 << 20)), bool(opts.get("log_steps", False)))
         return sol
 
@@ -557,7 +644,7 @@ class _MlpDopri5AdjointSolve(torch.autograd.Function):
             rc = lib.slode_mlp_dopri5_adjoint_bwd(
                 B, T, L, H, S, _ptr(t), _ptr(zc), _ptr(c), _ptr(W1), _ptr(Wg), _ptr(bg), _ptr(Wd), _ptr(bd), _ptr(sol),
                 sol.stride(0), sol.stride(1), _ptr(grad_sol), strides[0], strides[1], rtol, atol, max_steps,
-                _ptr(grad_y0), _ptr(gp), _ptr(log), log_cap, _ptr(stats), _ptr(ws), ws.numel(),
+                _ptr(ctx.replay), ctx.replay.shape[0] if ctx.replay is not None else 0, _ptr(grad_y0), _ptr(gp), _ptr(log), log_cap, _ptr(stats), _ptr(ws), ws.numel(),
                 torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "slode_mlp_dopri5_adjoint_bwd")
         n_acc, n_rej, n_rhs, status = (int(v) for v in stats.tolist())
@@ -599,7 +686,7 @@ def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
                                               or any(p.requires_grad for p in func.parameters()))
     if needs_grad:
         if mode == _cabi.BWD_TDE_ADJOINT:
-            bad = sorted(set(options or {}) & {"first_step", "replay_steps"})
+            bad = sorted(set(options or {}) & {"first_step", "shard_reducer", "global_batch"})
             if bad:
                 raise NotImplementedError(f"odeint_adjoint with dopri5: options {bad} (the reference passes none)")
             return _MlpDopri5AdjointSolve.apply(y0, z, hid.weight, hid.bias, gro.weight, gro.bias, deg.weight,

@@ -213,3 +213,69 @@ def test_free_running_gradient_is_consistent():
     fd = 0.5 * ((a - b).double() * G.double()).sum()
     an = (y0.grad.double() * v.double()).sum()
     assert abs(fd - an) < 1e-4 * max(abs(fd), 1.0)
+
+
+@pytest.mark.parametrize("shape,B,split", [("cvs", 300, (120, 180)), ("chal", 35, (1, 34)), ("proc", 90, (30, 30, 30))])
+def test_sharded_solve_takes_the_step_sequence_of_the_unsharded_one(shape, B, split):
+    """the controller is batch-global, so a trajectory-sharded solve must combine the error norm
+    over the shards at every attempted step.  Several shards are stepped in lockstep here on one device (the sum of
+    their ``out`` sums plays the all-reduce): accepted / rejected decisions and step sizes must be those of the
+    unsharded solve, and every shard's trajectories those rows of it."""
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    import structured_latent_odes_b200 as slode
+    o, p = _pair(shape)
+    L = U.SHAPES[shape][0]
+    z = torch.randn(B, L, generator=torch.Generator().manual_seed(31)).cuda()
+    rtol, atol = 1e-4, 1e-5
+    with torch.no_grad():
+        y0 = p.initialize_state(z).contiguous()
+        full = slode.odeint(p.gen_dynamics(z), y0, p.times, method="dopri5", rtol=rtol, atol=atol,
+                            options={"log_steps": True})
+        steps_full = api.last_dopri5_stats.steps.clone()
+        d = p.dynamics
+        W1 = d.dynamics_hidden.weight.detach()
+        c = torch.addmm(d.dynamics_hidden.bias.detach(), z, W1[:, 1:].t()).contiguous()
+        w = [x.detach().contiguous() for x in (W1[:, 0], d.dyanamics_growth.weight, d.dyanamics_growth.bias,
+                                               d.dyanmics_degradation.weight, d.dyanmics_degradation.bias)]
+        shards, lo = [], 0
+        for n in split:
+            shards.append(api.Dopri5ShardSolve(y0[lo:lo + n].contiguous(), c[lo:lo + n].contiguous(), w, p.times, rtol,
+                                               atol, n_global=B, log_cap=4096))
+            lo += n
+        for _ in range(100000):
+            done = [sh.step() for sh in shards]
+            assert all(done) or not any(done)      # every shard finishes at the same pass
+            if all(done):
+                break
+            total = shards[0].out.clone()
+            for sh in shards[1:]:
+                total += sh.out
+            for sh in shards:
+                sh.ext.copy_(total)
+    for sh in shards:
+        n_acc, n_rej, _, status = sh.result()
+        assert status == 0
+        assert torch.equal(sh.log[: n_acc + n_rej].cpu(), steps_full)     # bit-identical step log
+    got = torch.cat([sh.sol for sh in shards], dim=1)
+    assert U.rel_err(got, full) < 1e-6
+
+
+def test_sharded_options_through_odeint_with_gradients():
+    """odeint(..., options=dopri5_shard_options(...)) on a single shard (world size 1) equals the plain solve, forward
+    and backward: the pass-per-launch path and the persistent kernel run the same state machine."""
+    import structured_latent_odes_b200 as slode
+    from structured_latent_odes_b200 import sharding
+    o, p = _pair("cvs")
+    g = torch.Generator().manual_seed(32)
+    z = torch.randn(50, 15, generator=g).cuda()
+    G = torch.randn(86, 50, 5, generator=g).cuda()
+    outs = []
+    for opts in (None, sharding.dopri5_shard_options(50, device="cuda")):
+        p.zero_grad()
+        zz = z.clone().requires_grad_(True)
+        sol = slode.odeint(p.gen_dynamics(zz), p.initialize_state(zz), p.times, method="dopri5", rtol=1e-4, atol=1e-5,
+                           options=opts)
+        (sol * G).sum().backward()
+        outs.append((sol.detach(), zz.grad.clone(), p.dynamics.dynamics_hidden.weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
