@@ -41,6 +41,9 @@
 #define SLODE_FX_BWD_MINB_WIDE 3 // state dimensions above 5 (proc: S = 8, four register pairs per vector): euler and
                                  // midpoint fit 168 registers, rk4 needs the full 255 (2 blocks)
 #endif
+#ifndef SLODE_FX_BWD_UNROLL
+#define SLODE_FX_BWD_UNROLL 1    // time-loop unrolling of the reverse sweep
+#endif
 #ifndef SLODE_FX_BWD_MINB_RK4
 #define SLODE_FX_BWD_MINB_RK4 3  // rk4 holds three evaluations at once: 168 registers (at 128 it spills in the time loop)
 #endif
@@ -132,6 +135,7 @@ __device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gs
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int kThreads = 128;
+constexpr int kBwdUnroll = SLODE_FX_BWD_UNROLL;
 constexpr int kWarps = kThreads / 32;
 constexpr float kNegLn2 = -0.6931471805599453f;  // unscaled weight = packed weight * kNegLn2
 
@@ -859,9 +863,14 @@ struct Sweep {
   __device__ __forceinline__ void events(f2* __restrict__ rec, const Tab& tab, int p0, int p1) {
     for (int p = p0; p < p1; ++p) {
       const int j = (int)(tab.k[(size_t)p * tab.ks] & SH::IMASK);
-      ulonglong2* dst = reinterpret_cast<ulonglong2*>(rec + j * (2 * NQ));
+      // record: [q] -> (P[q], Q[q]).  Two 8-byte stores per q: one 16-byte store would tie P[q] and Q[q] to an aligned
+      // register quad for the whole sweep and the time loop would end in ~24 register copies per interval
+      f2* dst = rec + j * (2 * NQ);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) dst[q] = make_ulonglong2(P[q], Q[q]);  // record: [q] -> (P[q], Q[q])
+      for (int q = 0; q < NQ; ++q) {
+        dst[2 * q] = P[q];
+        dst[2 * q + 1] = Q[q];
+      }
       if constexpr (SH::BIG) {
         tab.fs[(size_t)j * tab.ks] |= 2;
       } else {
@@ -1007,7 +1016,7 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     }
     V<NP> G0, D0, G1, D1, G2, D2;   // rk4: the three evaluations of the interval in hand
     int pa = 0, pb = 0;             // rk4: walk positions after the first two seeks of the interval
-#pragma unroll 1
+#pragma unroll kBwdUnroll
     for (int i = T - 2; i >= 0; --i) {
       const float t0 = t_ahead;
       if (i > 0) t_ahead = ld_early(tgrid + i - 1);
