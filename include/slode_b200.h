@@ -72,6 +72,7 @@ extern "C" {
 #define SLODE_Q_FWD_LAUNCHES 10  /* kernels launched by the last forward entry-point call of the process */
 #define SLODE_Q_BWD_LAUNCHES 11
 #define SLODE_Q_TOTAL_LAUNCHES 12 /* kernels launched by this library since it was loaded (all threads) */
+#define SLODE_Q_SOURCE_HASH 13    /* 31-bit digest of the sources this binary was built from (_build.source_hash) */
 
 int slode_query(int what);
 const char* slode_last_error(void);

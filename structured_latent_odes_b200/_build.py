@@ -33,17 +33,36 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def source_hash():
+    """31-bit digest of every source the library is built from (the .cu / .cuh / .h files and the public header).
+    It is compiled into the library (``slode_query(SLODE_Q_SOURCE_HASH)``), so a prebuilt .so that travelled with the
+    tree can be told apart from one built from the sources beside it."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    for f in files:
+        h.update(f.encode())
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "slode_b200.h"), "rb").read())
+    return int(h.hexdigest()[:8], 16) & 0x7FFFFFFF
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "slode_b200.h"))
     nvcc = _nvcc()
+    digest = source_hash()
+    stamp = os.path.join(OBJ, "source_hash.txt")
+    old = open(stamp).read().strip() if os.path.isfile(stamp) else ""
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
-        if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+        # slode_mlp.cu carries the digest: it is rebuilt whenever any source changed
+        extra = [f"-DSLODE_SOURCE_HASH={digest}"] if src == "slode_mlp.cu" else []
+        if force or _stale(o, [s] + headers) or (extra and old != str(digest)):
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,6 +77,8 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    with open(stamp, "w") as f:
+        f.write(str(digest))
     return LIB
 
 

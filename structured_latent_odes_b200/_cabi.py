@@ -19,7 +19,7 @@ METHODS = {"euler": METHOD_EULER, "midpoint": METHOD_MIDPOINT, "rk4": METHOD_RK4
 BWD_DISCRETE, BWD_TDE_ADJOINT = 0, 1
 F32, F64 = 0, 1
 Q_VERSION, Q_SM_ARCH, Q_MAX_HIDDEN, Q_MAX_STATE, Q_N_SHAPES = 0, 1, 2, 3, 4
-Q_FWD_LAUNCHES, Q_BWD_LAUNCHES, Q_TOTAL_LAUNCHES, Q_SHAPE_BASE = 10, 11, 12, 100
+Q_FWD_LAUNCHES, Q_BWD_LAUNCHES, Q_TOTAL_LAUNCHES, Q_SOURCE_HASH, Q_SHAPE_BASE = 10, 11, 12, 13, 100
 
 _i, _i64, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
 

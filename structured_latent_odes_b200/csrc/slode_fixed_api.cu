@@ -107,14 +107,6 @@ static int check_latent(const char* who, int L, const float* z, const float* W1,
   return SLODE_OK;
 }
 
-// round-1 kernels, kept reachable for A/B measurements: SLODE_IMPL=r1 in the environment of the process
-static bool use_r1() {
-  static const bool v = [] {
-    const char* e = getenv("SLODE_IMPL");
-    return e && strcmp(e, "r1") == 0;
-  }();
-  return v;
-}
 
 }  // namespace slode
 
@@ -124,7 +116,7 @@ extern "C" int64_t slode_fixed_workspace_bytes(int backward, int method, int mod
                                                int S, int fused, int rows_in_time) {
   if (check_sizes("slode_fixed_workspace_bytes", method, mode, B, T, H, S)) return -1;
   if (fused < 0 || fused > 2 || (fused && L < 1)) return -1;
-  if (B == 0 || use_r1()) return 0;
+  if (B == 0) return 0;
   int sms = 0;
   if (device_sms(&sms)) return -1;
   // only the sizes and the null-ness of the latent pointers enter the launch plan
@@ -155,26 +147,6 @@ static int run_fwd(const char* who, int H, int S, FwdArgs& a, const PackSrc& w, 
   g_fwd_launches = 0;
   if (a.B == 0) return SLODE_OK;
   int rc;
-  if (use_r1()) {
-    const ShapeEntry* e = find_shape(H, S);
-    if (!e) {
-      set_error("%s: SLODE_IMPL=r1 has no kernel for (hidden=%d, state=%d)", who, H, S);
-      return SLODE_EUNSUPPORTED;
-    }
-    PackGuard guard(a.stream);
-    if (guard.status) return guard.status;
-    a.sms = guard.sms;
-    PackSrc w2 = w;
-    if (w1t_stride != 1) {  // W1[:,0] -> contiguous copy in the device staging area (behind the packed weights)
-      float* w1t = guard.staging + 12288;
-      SLODE_CUDA_TRY(cudaMemcpy2DAsync(w1t, sizeof(float), w.w1t, sizeof(float) * w1t_stride, sizeof(float), H,
-                                       cudaMemcpyDeviceToDevice, a.stream));
-      w2.w1t = w1t;
-    }
-    rc = e->fwd(a, w2, guard.staging);
-    if (rc == SLODE_OK) g_fwd_launches = 2;
-    return rc;
-  }
   rc = device_sms(&a.sms);
   if (rc) return rc;
   size_t need = 0;
@@ -187,29 +159,6 @@ static int run_bwd(const char* who, int H, int S, BwdArgs& a, const PackSrc& w, 
   g_bwd_launches = 0;
   if (a.B == 0) return SLODE_OK;
   int rc;
-  if (use_r1()) {
-    const ShapeEntry* e = find_shape(H, S);
-    if (!e) {
-      set_error("%s: SLODE_IMPL=r1 has no kernel for (hidden=%d, state=%d)", who, H, S);
-      return SLODE_EUNSUPPORTED;
-    }
-    PackGuard guard(a.stream);
-    if (guard.status) return guard.status;
-    a.sms = guard.sms;
-    PackSrc w2 = w;
-    if (w1t_stride != 1) {
-      float* w1t = guard.staging + 12288;
-      SLODE_CUDA_TRY(cudaMemcpy2DAsync(w1t, sizeof(float), w.w1t, sizeof(float) * w1t_stride, sizeof(float), H,
-                                       cudaMemcpyDeviceToDevice, a.stream));
-      w2.w1t = w1t;
-    }
-    a.w1t = w2.w1t;
-    a.Wg = w2.Wg;
-    a.Wd = w2.Wd;
-    rc = e->bwd(a, w2, guard.staging);
-    if (rc == SLODE_OK) g_bwd_launches = 2;
-    return rc;
-  }
   rc = device_sms(&a.sms);
   if (rc) return rc;
   size_t need = 0;

@@ -9,7 +9,7 @@
 namespace slode {
 
 static const ShapeEntry kShapes[] = {
-#define X(h, s) {h, s, mlp_fwd_##h##_##s, mlp_bwd_##h##_##s, dopri5_fwd_##h##_##s, dopri5_bwd_##h##_##s},
+#define X(h, s) {h, s, dopri5_fwd_##h##_##s, dopri5_bwd_##h##_##s},
     SLODE_SHAPES(X)
 #undef X
 };
@@ -78,6 +78,11 @@ extern "C" int slode_query(int what) {
     case SLODE_Q_FWD_LAUNCHES: return g_fwd_launches;
     case SLODE_Q_BWD_LAUNCHES: return g_bwd_launches;
     case SLODE_Q_TOTAL_LAUNCHES: return (int)(g_total_launches.load() & 0x7fffffff);
+#ifdef SLODE_SOURCE_HASH
+    case SLODE_Q_SOURCE_HASH: return (int)(SLODE_SOURCE_HASH);
+#else
+    case SLODE_Q_SOURCE_HASH: return 0;
+#endif
   }
   if (what >= SLODE_Q_SHAPE_BASE && what < SLODE_Q_SHAPE_BASE + 2 * kNumFixedShapes) {
     const int i = (what - SLODE_Q_SHAPE_BASE) / 2;

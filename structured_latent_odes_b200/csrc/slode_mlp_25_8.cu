@@ -1,8 +1,7 @@
-// Fixed-grid forward / reverse-sweep kernels for (ode_hidden_dim=25, ode_state_dim=8); see slode_mlp_kernels.cuh.
+// dopri5 forward / discrete backward kernels for (ode_hidden_dim=25, ode_state_dim=8); see slode_dopri5_kernels.cuh.
 #define SLODE_PACK_SYM slode_c_pack_25_8
 #include "slode_mlp_kernels.cuh"
 #include "slode_dopri5_kernels.cuh"
 
-SLODE_DEFINE_SHAPE(25, 8)
 SLODE_DEFINE_DOPRI5(25, 8)
 SLODE_DEFINE_DOPRI5_BWD(25, 8)

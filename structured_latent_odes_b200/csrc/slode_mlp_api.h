@@ -1,5 +1,6 @@
-// Host-side interface between the C-ABI dispatcher (slode_mlp.cu) and the per-shape translation units
-// (slode_mlp_<H>_<S>.cu), each of which owns its own packed-weight buffer in constant memory.
+// Host-side interface between the C-ABI dispatchers (slode_mlp.cu, slode_fixed_api.cu) and the per-shape translation
+// units: slode_fixed_<H>_<S>.cu (fixed-grid kernels) and slode_mlp_<H>_<S>.cu (dopri5 kernels, each of which owns its
+// packed-weight buffer in constant memory).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -31,7 +32,6 @@ struct FwdArgs {
   cudaStream_t stream;
   int sms;
   LatentSrc lat;
-  float* eval_ckpt;  // round-1 kernels only: every MLP evaluation (A, -D) of the solve
   void* ws;          // caller-provided scratch (slode_fixed_workspace_bytes), may be null when 0 bytes are needed
   size_t ws_bytes;
 };
@@ -49,7 +49,6 @@ struct BwdArgs {
   int sms;
   LatentSrc lat;
   float* gz;  // (B,L), fused mode only
-  const float* eval_ckpt;  // round-1 kernels only
   void* ws;                // caller-provided scratch: flip records (+ wide-layer tables)
   size_t ws_bytes;
 };
@@ -116,13 +115,11 @@ struct Dopri5BwdArgs {
 // plan_only nothing is launched and *ws_need receives the scratch bytes a launch with these arguments needs
 typedef int (*fixed_fwd_fn)(const FwdArgs&, const PackSrc&, int w1t_stride, bool plan_only, size_t* ws_need);
 typedef int (*fixed_bwd_fn)(const BwdArgs&, const PackSrc&, int w1t_stride, bool plan_only, size_t* ws_need);
-typedef int (*mlp_fwd_fn)(const FwdArgs&, const PackSrc&, float* staging);
-typedef int (*mlp_bwd_fn)(const BwdArgs&, const PackSrc&, float* staging);
 typedef int (*dopri5_fwd_fn)(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 typedef int (*dopri5_bwd_fn)(const Dopri5BwdArgs&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 
 // (25,5): CVS / challenge configs; (25,8): proc config; the rest serve tests and the width sweep.
-// SLODE_SHAPES: shapes of the round-1 translation units (dopri5; the round-1 fixed-grid kernels kept for A/B runs)
+// SLODE_SHAPES: shapes of the dopri5 translation units (slode_mlp_<H>_<S>.cu)
 #define SLODE_SHAPES(X) X(25, 5) X(25, 8) X(16, 4) X(32, 5) X(64, 5)
 // SLODE_FIXED_SHAPES: shapes of the fixed-grid kernels (slode_fixed.cuh, one unit slode_fixed_<H>_<S>.cu each)
 #ifndef SLODE_FIXED_SHAPES
@@ -130,8 +127,6 @@ typedef int (*dopri5_bwd_fn)(const Dopri5BwdArgs&, const PackSrc&, float* stagin
 #endif
 
 #define SLODE_DECLARE_SHAPE(H, S)                                         \
-  int mlp_fwd_##H##_##S(const FwdArgs&, const PackSrc&, float* staging);  \
-  int mlp_bwd_##H##_##S(const BwdArgs&, const PackSrc&, float* staging);  \
   int dopri5_fwd_##H##_##S(const Dopri5Args&, const PackSrc&, float* staging, cudaStream_t stream, int sms); \
   int dopri5_bwd_##H##_##S(const Dopri5BwdArgs&, const PackSrc&, float* staging, cudaStream_t stream, int sms);
 SLODE_SHAPES(SLODE_DECLARE_SHAPE)
@@ -144,8 +139,6 @@ SLODE_FIXED_SHAPES(SLODE_DECLARE_FIXED_SHAPE)
 
 struct ShapeEntry {
   int H, S;
-  mlp_fwd_fn fwd;
-  mlp_bwd_fn bwd;
   dopri5_fwd_fn dopri5_fwd;
   dopri5_bwd_fn dopri5_bwd;
 };
@@ -154,7 +147,7 @@ struct FixedShapeEntry {
   fixed_fwd_fn fwd;
   fixed_bwd_fn bwd;
 };
-const ShapeEntry* find_shape(int H, int S);             // round-1 units (dopri5)
+const ShapeEntry* find_shape(int H, int S);             // dopri5 units
 const FixedShapeEntry* find_fixed_shape(int H, int S);  // fixed-grid kernels
 int device_sms(int* sms);                               // SM count of the current device (cached)
 

@@ -77,3 +77,10 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_cabi.SlodeError, match="no fallback"):
         _cabi.lib()
+
+
+def test_library_was_built_from_the_sources_in_the_tree(handle):
+    """slode_query(SLODE_Q_SOURCE_HASH) is the digest of csrc/ + the public header at build time: a prebuilt .so that
+    no longer matches the sources is detected (and __graft_entry__.build() rebuilds the unit that carries it)."""
+    from structured_latent_odes_b200 import _build, _cabi
+    assert handle.slode_query(_cabi.Q_SOURCE_HASH) == _build.source_hash()
