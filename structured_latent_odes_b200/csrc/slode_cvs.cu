@@ -35,6 +35,15 @@ template <class R> struct Theta {
 template <class R> __device__ __forceinline__ R rexp(R x);
 template <> __device__ __forceinline__ float rexp<float>(float x) { return __expf(x); }
 template <> __device__ __forceinline__ double rexp<double>(double x) { return exp(x); }
+// 1/x: float32 = MUFU.RCP + one Newton step (about 1 ulp; the IEEE division is a ~10-instruction sequence with a
+// subroutine call for the slow path, twice per RHS evaluation, and these kernels are bound by exactly that latency
+// chain); float64 (the data generator) keeps the exact division
+template <class R> __device__ __forceinline__ R rrcp(R x);
+template <> __device__ __forceinline__ float rrcp<float>(float x) {
+  const float r = rcp_approx(x);
+  return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+template <> __device__ __forceinline__ double rrcp<double>(double x) { return 1.0 / x; }
 
 template <class R> struct V4 { R v[4]; };
 
@@ -50,12 +59,12 @@ __device__ __forceinline__ V4<R> rhs(const V4<R>& x, R ie, R rm, const Theta<R>&
   const R pa = R(100) * x.v[0], pv = R(10) * x.v[1], s = x.v[2], sv = R(100) * x.v[3];
   const R fhr = fma(s, th.dF, th.fmin);
   const R r = fma(s, th.dR, th.rmin) - rm;
-  const R dva = sv * fhr - (pa - pv) / r;
+  const R dva = sv * fhr - (pa - pv) * rrcp<R>(r);
   const R e = rexp<R>(-th.k * (pa - th.pset));
   V4<R> f;
   f.v[0] = dva * th.ica;
   f.v[1] = (ie - dva) * th.icv;
-  f.v[2] = (R(1) - R(1) / (R(1) + e) - s) * th.itau;
+  f.v[2] = (R(1) - rrcp<R>(R(1) + e) - s) * th.itau;
   f.v[3] = ie * th.svm;
   return f;
 }
@@ -68,11 +77,11 @@ __device__ __forceinline__ V4<R> vjp(const V4<R>& x, R ie, R rm, const Theta<R>&
   const R dF = th.dF, dR = th.dR;
   const R fhr = fma(s, dF, th.fmin);
   const R r = fma(s, dR, th.rmin) - rm;
-  const R rinv = R(1) / r;
+  const R rinv = rrcp<R>(r);
   const R q = (pa - pv) * rinv;
   const R dva = sv * fhr - q;
   const R e = rexp<R>(-th.k * (pa - th.pset));
-  const R sg = R(1) / (R(1) + e);
+  const R sg = rrcp<R>(R(1) + e);
   const R ica = th.ica, icv = th.icv, itau = th.itau;
   const R g_dva = g.v[0] * ica - g.v[1] * icv;
   const R g_r = g_dva * q * rinv;          // d(-q)/dr = q/r
@@ -291,7 +300,7 @@ cvs_fwd_kernel(int64_t B, int T, int nsub, const R* __restrict__ tgrid, const R*
     V4<R> Y[4];
     for (int i = 0; i + 1 < T; ++i) {
       const R t1 = tgrid[i + 1];
-      const R h = (t1 - t0) / R(nsub);
+      const R h = nsub == 1 ? (t1 - t0) : (t1 - t0) / R(nsub);   // the common case pays no division
       for (int k = 0; k < nsub; ++k) y = step<R, METHOD>(y, h, ie, rm, th, Y);
       out += st;
       store4<R>(out, y);
@@ -329,7 +338,7 @@ cvs_bwd_kernel(int64_t B, int T, int nsub, const R* __restrict__ tgrid, const R*
     }
     for (int i = T - 2; i >= 0; --i) {
       const R t0 = tgrid[i];
-      const R h = (t1 - t0) / R(nsub);
+      const R h = nsub == 1 ? (t1 - t0) : (t1 - t0) / R(nsub);   // the common case pays no division
       const V4<R> g = g_ahead, xrow = x_ahead;
       if (i > 0) {
         g_ahead = load4<R>(gs + (int64_t)(i - 1) * gst);
