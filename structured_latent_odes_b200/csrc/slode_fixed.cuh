@@ -569,9 +569,26 @@ struct LatSmem {
   }
 };
 
-// acc[j0 .. j0+JC) = bias + sum_l W[l][j] z_l  for one chunk of units (z row read through L1: 60-200 bytes, hit
-// after the first chunk).  Two units per instruction: the staged rows are zero-padded to a multiple of four floats
-// and 16-byte aligned, so a row is read as 16-byte vectors of two weight pairs each.
+// The warp's 32 latent rows are ONE contiguous run of 32*L floats of z: they are copied into shared memory with
+// coalesced loads once per tile (zT[row][LQ], LQ = L rounded up to four, padding zero).  Read row by row straight
+// from global memory (first version) every load of the L-step loop was an uncoalesced L2 round trip one short
+// iteration ahead of its use: 7 % of the forward's and 5 % of the reverse sweep's stall samples.
+__device__ __forceinline__ void stage_z_rows(float* __restrict__ zT, int LQ, const float* __restrict__ z, int L,
+                                             int64_t row0, int64_t B, int lane) {
+  __syncwarp();   // every lane is done with the rows of the tile before
+  const int n = 32 * L;
+  for (int idx = lane; idx < n; idx += 32) {
+    const int r = idx / L, col = idx - r * L;
+    const int64_t gr = min(row0 + r, B - 1);   // tail rows repeat trajectory B-1 (their stores are masked off)
+    zT[r * LQ + col] = __ldg(z + gr * L + col);
+  }
+  for (int col = L; col < LQ; ++col) zT[lane * LQ + col] = 0.0f;
+  __syncwarp();
+}
+
+// acc[j0 .. j0+JC) = bias + sum_l W[l][j] z_l  for one chunk of units; zrow = this thread's staged latent row (16-byte
+// aligned, zero-padded to a multiple of four).  Two units per instruction: the staged weight rows are zero-padded to
+// a multiple of four floats and 16-byte aligned, so a row is read as 16-byte vectors of two weight pairs each.
 template <int JC>
 __device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const float* __restrict__ bias, int HQ, int j0,
                                           const float* __restrict__ zrow, int L, float (&acc)[JC]) {
@@ -584,17 +601,22 @@ __device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const flo
     a2[2 * q] = v.x;
     a2[2 * q + 1] = v.y;
   }
-  float znext = L > 0 ? __ldg(zrow) : 0.0f;
 #pragma unroll 1
-  for (int l = 0; l < L; ++l) {
-    const f2 zl = bc(znext);
-    if (l + 1 < L) znext = ld_early(zrow + l + 1);
-    const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(W + l * HQ + j0);
+  for (int l0 = 0; l0 < L; l0 += 4) {
+    const float4 z4 = *reinterpret_cast<const float4*>(zrow + l0);
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-    for (int q = 0; q < J4; ++q) {
-      const ulonglong2 v = w4[q];
-      a2[2 * q] = fma2(v.x, zl, a2[2 * q]);
-      a2[2 * q + 1] = fma2(v.y, zl, a2[2 * q + 1]);
+    for (int k = 0; k < 4; ++k) {
+      if (l0 + k < L) {
+        const f2 zl = bc(zz[k]);
+        const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(W + (l0 + k) * HQ + j0);
+#pragma unroll
+        for (int q = 0; q < J4; ++q) {
+          const ulonglong2 v = w4[q];
+          a2[2 * q] = fma2(v.x, zl, a2[2 * q]);
+          a2[2 * q + 1] = fma2(v.y, zl, a2[2 * q + 1]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -617,7 +639,7 @@ __host__ __device__ constexpr size_t fwd_smem_bytes(int L, bool lat, bool rows_i
   using SH = Shape<H, S>;
   size_t n = SH::WT;
   if (!SH::BIG) n += table_floats<H, S>();
-  if (lat) n += LatSmem<H, S>::floats(L);
+  if (lat) n += LatSmem<H, S>::floats(L) + (size_t)kThreads * ((L + 3) / 4 * 4);   // staged nets + the warps' z rows
   if (rows_in_time) n += (size_t)kThreads * kStageT * S;
   return n * sizeof(float);
 }
@@ -653,11 +675,11 @@ __device__ __forceinline__ Tab make_tab(float* smem_tables, unsigned char* ws, i
 // c_j into the thread's table (from z through the staged W1[:,1:], or from the given (B,H) array); returns x0
 template <int H, int S, bool WANT_X0>
 __device__ __forceinline__ void prologue(const LatSmem<H, S>& ls, const LatentSrc& lat, const float* __restrict__ cin,
-                                         int64_t b, const Tab& tab, V<(S + 1) / 2>& x0) {
+                                         const float* __restrict__ zrow, int64_t b, const Tab& tab,
+                                         V<(S + 1) / 2>& x0) {
   using SH = Shape<H, S>;
   constexpr int JC = SH::JC;
   if (lat.z) {
-    const float* zrow = lat.z + b * lat.L;
     float xa[S];
     if (WANT_X0) {
 #pragma unroll
@@ -710,7 +732,10 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
   LatSmem<H, S> ls{};
   stage_weights<H, S>(wt, w.w1t, w1t_stride, w.Wg, w.bg, w.Wd, w.bd);
   if (lat.z) ls.stage(lat_base, lat);
-  float* const ostage = lat_base + (lat.z ? LatSmem<H, S>::floats(lat.L) : 0) + (size_t)tid * kStageT * S;
+  const int LQ = (lat.L + 3) / 4 * 4;
+  float* const zT = lat_base + LatSmem<H, S>::floats(lat.L) + (size_t)warp * 32 * LQ;   // this warp's z rows (lat.z only)
+  float* const ostage = lat_base + (lat.z ? LatSmem<H, S>::floats(lat.L) + (size_t)kThreads * LQ : 0) +
+                        (size_t)tid * kStageT * S;
   __syncthreads();
   const Tab tab = make_tab<H, S>(tables, ws, warp, lane);
   const float dir = (T < 2 || __ldg(tgrid + T - 1) >= __ldg(tgrid)) ? 1.0f : -1.0f;
@@ -720,10 +745,11 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     const bool ok = br < B;
     const int64_t b = ok ? br : B - 1;  // tail threads redo trajectory B-1 with their stores masked off
     V<NP> x;
+    if (lat.z) stage_z_rows(zT, LQ, lat.z, lat.L, tile * kThreads + warp * 32, B, lane);
     if (lat.z && lat.Wa) {
-      prologue<H, S, true>(ls, lat, cin, b, tab, x);
+      prologue<H, S, true>(ls, lat, cin, zT + lane * LQ, b, tab, x);
     } else {
-      prologue<H, S, false>(ls, lat, cin, b, tab, x);
+      prologue<H, S, false>(ls, lat, cin, zT + lane * LQ, b, tab, x);
       x = vload<S>(y0 + b * S);
     }
     float* out = sol + b * sb;
@@ -961,9 +987,10 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     const int64_t br = tile * kThreads + tid;
     const bool ok = br < B;
     const int64_t b = ok ? br : B - 1;
+    if (fused) stage_z_rows(zT, LQ, lat.z, L, tile * kThreads + warp * 32, B, lane);
     {
       V<NP> dummy;
-      prologue<H, S, false>(ls, lat, cin, b, tab, dummy);
+      prologue<H, S, false>(ls, lat, cin, zT + lane * LQ, b, tab, dummy);
     }
     const float* xs = sol + b * sb;
     const float* gs = gsol + b * gsb;
@@ -1233,11 +1260,7 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
       unpk(sw.Q[q], q0, q1);
       reinterpret_cast<float4*>(pqw + lane * PQS)[q] = make_float4(p0, p1, q0, q1);
     }
-    if (fused) {  // this warp's z rows -> zT[lane][l]
-      const float* zrow = lat.z + b * L;
-      for (int l = 0; l < LQ; ++l) zT[lane * LQ + l] = l < L ? __ldg(zrow + l) : 0.0f;
-    }
-    __syncwarp();
+    __syncwarp();   // (the warp's z rows have been in zT since the tile's prologue)
 
     const float* recs = wt + SH::BIAS;
     float* const cw = tab.c - lane;                 // element (j, trajectory bb of this warp) at cw[j * stride + bb]
@@ -1417,7 +1440,7 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
 #pragma unroll 1
       for (int j0 = 0; j0 < H; j0 += JC) {
         float ha[JC];
-        lat_chunk<JC>(ls.Wa, ls.ba, SH::HQ, j0, lat.z + b * L, L, ha);
+        lat_chunk<JC>(ls.Wa, ls.ba, SH::HQ, j0, zT + lane * LQ, L, ha);
         // da -> buffer
 #pragma unroll
         for (int jj = 0; jj < JC; ++jj) {
