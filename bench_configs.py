@@ -107,6 +107,31 @@ def cvs_mech(B, T=100):
           flush=True)
 
 
+def heads(B, T=100, S=5, O=3, NQ=3):
+    """Decoder heads (models/decoders.py:45-47): all NQ quantile heads in one pass, forward and backward."""
+    sol = torch.randn(B, T, S, device=dev, requires_grad=True)
+    W = [torch.randn(O, S, device=dev, requires_grad=True) for _ in range(NQ)]
+    G = [torch.randn(B, O, T, device=dev) for _ in range(NQ)]
+
+    def fwd():
+        with torch.no_grad():
+            slode.decoder_heads(sol, W)
+
+    def fwd_bwd():
+        sol.grad = None
+        for w in W:
+            w.grad = None
+        mu = slode.decoder_heads(sol, W)
+        torch.autograd.backward(mu, G)
+
+    ms_f, ms = timed(fwd), timed(fwd_bwd)
+    bytes_f = B * T * 4 * (S + NQ * O)
+    bytes_b = B * T * 4 * (2 * S + NQ * O)
+    print(json.dumps({"case": f"decoder heads, {NQ} heads x obs_dim {O}", "B": B, "T": T, "fwd_ms": round(ms_f, 4),
+                      "fwd_bwd_ms": round(ms, 4), "fwd_GBps": bytes_f / (ms_f * 1e-3) / 1e9,
+                      "bwd_GBps": bytes_b / ((ms - ms_f) * 1e-3) / 1e9}), flush=True)
+
+
 def tensor_core_proxy(B, Hw, S=5, T=100):
     """BASELINE configs[4] asks where the dense head contraction should move from the FMA pipe to tcgen05.  The kernels
     do not run that contraction at all any more (piecewise-linear heads: O(S) per evaluation + O(S) per relu crossing),
@@ -137,6 +162,8 @@ if __name__ == "__main__":
     blackbox("configs[0] CVS default", 128, 86, 15, 25, 5, "midpoint", True)
     blackbox("configs[0] CVS full train set", 810, 86, 15, 25, 5, "midpoint", True)
     cvs_mech(big)
+    heads(big)
+    heads(big, NQ=1)
     for B in (35, 7000, big):
         blackbox("configs[2] challenge dopri5", B, 142, 15, 25, 5, "dopri5", False, rtol=1e-5, atol=1e-6)
     blackbox("configs[2] challenge dopri5 torchdiffeq default tol", 7000, 142, 15, 25, 5, "dopri5", False, rtol=1e-7, atol=1e-9,

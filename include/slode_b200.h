@@ -304,6 +304,14 @@ int slode_heads_bwd(int64_t B, int T, int S, int O, int NQ,
                     float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
                     float* grad_W, void* stream);
 
+/* The same with one (B,O,T) gradient per head (autograd hands the quantile heads' gradients over separately;
+ * NULL = that head did not enter the loss): no stacking copy in front of the kernel. */
+int slode_heads_bwd_split(int64_t B, int T, int S, int O, int NQ,
+                          const float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                          const float* W, const float* grad_mu0, const float* grad_mu1, const float* grad_mu2,
+                          float* grad_sol, int64_t gsol_stride_t, int64_t gsol_stride_b,
+                          float* grad_W, void* stream);
+
 /* element types of the CVS entry points */
 #define SLODE_F32 0
 #define SLODE_F64 1

@@ -47,6 +47,7 @@ SIGNATURES = {
                                      + [ctypes.c_double, ctypes.c_double, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _p]),
     "slode_heads_fwd": (_i, [_i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _p, _p]),
     "slode_heads_bwd": (_i, [_i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p]),
+    "slode_heads_bwd_split": (_i, [_i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _p]),
     "slode_cvs_fixed_fwd": (_i, [_i, _i, _i64, _i, _i] + [_p] * 5 + [_p, _i64, _i64, _p]),
     "slode_cvs_fixed_bwd": (_i, [_i, _i, _i, _i64, _i, _i] + [_p] * 4 + [_p, _i64, _i64, _p, _i64, _i64]
                             + [_p] * 5),

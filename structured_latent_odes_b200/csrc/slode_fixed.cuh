@@ -589,7 +589,8 @@ __device__ __forceinline__ void stage_z_rows(float* __restrict__ zT, int LQ, con
 // acc[j0 .. j0+JC) = bias + sum_l W[l][j] z_l  for one chunk of units; zrow = this thread's staged latent row (16-byte
 // aligned, zero-padded to a multiple of four).  Two units per instruction: the staged weight rows are zero-padded to
 // a multiple of four floats and 16-byte aligned, so a row is read as 16-byte vectors of two weight pairs each.
-template <int JC>
+// ZS = false: zrow is the row in global memory (the widest layer's forward has no shared memory left for the rows).
+template <int JC, bool ZS = true>
 __device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const float* __restrict__ bias, int HQ, int j0,
                                           const float* __restrict__ zrow, int L, float (&acc)[JC]) {
   constexpr int J4 = (JC + 3) / 4;  // 16-byte vectors per row
@@ -603,8 +604,14 @@ __device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const flo
   }
 #pragma unroll 1
   for (int l0 = 0; l0 < L; l0 += 4) {
-    const float4 z4 = *reinterpret_cast<const float4*>(zrow + l0);
-    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    float zz[4];
+    if (ZS) {
+      const float4 z4 = *reinterpret_cast<const float4*>(zrow + l0);
+      zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) zz[k] = l0 + k < L ? __ldg(zrow + l0 + k) : 0.0f;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (l0 + k < L) {
@@ -634,12 +641,17 @@ __host__ __device__ constexpr size_t table_floats() {
   return (size_t)kWarps * H * Shape<H, S>::CS + (size_t)kThreads * Shape<H, S>::HP;
 }
 
+// the forward keeps the warps' latent rows in shared memory unless the staged weights of the widest layer leave no
+// room for them next to a second resident block
+template <int H> __host__ __device__ constexpr bool fwd_stages_z() { return H <= 256; }
+
 template <int H, int S>
 __host__ __device__ constexpr size_t fwd_smem_bytes(int L, bool lat, bool rows_in_time) {
   using SH = Shape<H, S>;
   size_t n = SH::WT;
   if (!SH::BIG) n += table_floats<H, S>();
-  if (lat) n += LatSmem<H, S>::floats(L) + (size_t)kThreads * ((L + 3) / 4 * 4);   // staged nets + the warps' z rows
+  if (lat) n += LatSmem<H, S>::floats(L);                                  // staged nets
+  if (lat && fwd_stages_z<H>()) n += (size_t)kThreads * ((L + 3) / 4 * 4);   // + the warps' z rows
   if (rows_in_time) n += (size_t)kThreads * kStageT * S;
   return n * sizeof(float);
 }
@@ -673,7 +685,7 @@ __device__ __forceinline__ Tab make_tab(float* smem_tables, unsigned char* ws, i
 }
 
 // c_j into the thread's table (from z through the staged W1[:,1:], or from the given (B,H) array); returns x0
-template <int H, int S, bool WANT_X0>
+template <int H, int S, bool WANT_X0, bool ZS = true>
 __device__ __forceinline__ void prologue(const LatSmem<H, S>& ls, const LatentSrc& lat, const float* __restrict__ cin,
                                          const float* __restrict__ zrow, int64_t b, const Tab& tab,
                                          V<(S + 1) / 2>& x0) {
@@ -688,11 +700,11 @@ __device__ __forceinline__ void prologue(const LatSmem<H, S>& ls, const LatentSr
 #pragma unroll 1
     for (int j0 = 0; j0 < H; j0 += JC) {
       float acc[JC];
-      lat_chunk<JC>(ls.Wz, ls.b1, SH::HQ, j0, zrow, lat.L, acc);
+      lat_chunk<JC, ZS>(ls.Wz, ls.b1, SH::HQ, j0, zrow, lat.L, acc);
 #pragma unroll
       for (int j = 0; j < JC; ++j) tab.c[(size_t)(j0 + j) * tab.cs] = acc[j];
       if (WANT_X0) {
-        lat_chunk<JC>(ls.Wa, ls.ba, SH::HQ, j0, zrow, lat.L, acc);
+        lat_chunk<JC, ZS>(ls.Wa, ls.ba, SH::HQ, j0, zrow, lat.L, acc);
 #pragma unroll
         for (int j = 0; j < JC; ++j) {
           const float h = relu_nan(acc[j]);
@@ -734,7 +746,8 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
   if (lat.z) ls.stage(lat_base, lat);
   const int LQ = (lat.L + 3) / 4 * 4;
   float* const zT = lat_base + LatSmem<H, S>::floats(lat.L) + (size_t)warp * 32 * LQ;   // this warp's z rows (lat.z only)
-  float* const ostage = lat_base + (lat.z ? LatSmem<H, S>::floats(lat.L) + (size_t)kThreads * LQ : 0) +
+  constexpr bool kZS = fwd_stages_z<H>();
+  float* const ostage = lat_base + (lat.z ? LatSmem<H, S>::floats(lat.L) + (kZS ? (size_t)kThreads * LQ : 0) : 0) +
                         (size_t)tid * kStageT * S;
   __syncthreads();
   const Tab tab = make_tab<H, S>(tables, ws, warp, lane);
@@ -745,11 +758,12 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     const bool ok = br < B;
     const int64_t b = ok ? br : B - 1;  // tail threads redo trajectory B-1 with their stores masked off
     V<NP> x;
-    if (lat.z) stage_z_rows(zT, LQ, lat.z, lat.L, tile * kThreads + warp * 32, B, lane);
+    if (lat.z && kZS) stage_z_rows(zT, LQ, lat.z, lat.L, tile * kThreads + warp * 32, B, lane);
+    const float* const zrow = kZS ? zT + lane * LQ : lat.z + b * lat.L;
     if (lat.z && lat.Wa) {
-      prologue<H, S, true>(ls, lat, cin, zT + lane * LQ, b, tab, x);
+      prologue<H, S, true, kZS>(ls, lat, cin, zrow, b, tab, x);
     } else {
-      prologue<H, S, false>(ls, lat, cin, zT + lane * LQ, b, tab, x);
+      prologue<H, S, false, kZS>(ls, lat, cin, zrow, b, tab, x);
       x = vload<S>(y0 + b * S);
     }
     float* out = sol + b * sb;
@@ -939,8 +953,20 @@ __host__ __device__ constexpr size_t bwd_smem_bytes(int L, bool lat) {
   return n * sizeof(float);
 }
 
+// resident blocks per SM the reverse sweep is compiled for (each value measured on the B200 at 2^20 x 100): wide
+// layers 2; S > 5 (four register pairs per vector): rk4 2, else 3; S <= 5: rk4 and the DISCRETE midpoint sweep (two
+// evaluations and two cotangent accumulations live at once: 3.67 ms at 128 registers, 2.70 at 168) 3, the rest 4
 template <int H, int S, int METHOD, int MODE>
-__global__ void __launch_bounds__(kThreads, Shape<H, S>::BIG ? 2 : (S > 5 ? (METHOD == SLODE_METHOD_RK4 ? 2 : SLODE_FX_BWD_MINB_WIDE) : (METHOD == SLODE_METHOD_RK4 ? SLODE_FX_BWD_MINB_RK4 : SLODE_FX_BWD_MINB)))
+__host__ __device__ constexpr int bwd_min_blocks() {
+  if (Shape<H, S>::BIG) return 2;
+  if (S > 5) return METHOD == SLODE_METHOD_RK4 ? 2 : SLODE_FX_BWD_MINB_WIDE;
+  if (METHOD == SLODE_METHOD_RK4) return SLODE_FX_BWD_MINB_RK4;
+  if (METHOD == SLODE_METHOD_MIDPOINT && MODE == SLODE_BWD_DISCRETE) return SLODE_FX_BWD_MINB_RK4;
+  return SLODE_FX_BWD_MINB;
+}
+
+template <int H, int S, int METHOD, int MODE>
+__global__ void __launch_bounds__(kThreads, bwd_min_blocks<H, S, METHOD, MODE>())
 fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                  const float* __restrict__ sol, int64_t st, int64_t sb, const float* __restrict__ gsol, int64_t gst,
                  int64_t gsb, float* __restrict__ grad_y0, float* __restrict__ grad_c, float* __restrict__ grad_w,

@@ -39,30 +39,32 @@ class _Heads(torch.autograd.Function):
                                              mu.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "slode_heads_fwd")
         ctx.save_for_backward(sol, Wc)
-        return mu
+        # one output per head (views of one buffer): autograd then hands every head's gradient over on its own, and a
+        # head that does not enter the loss costs nothing -- a single stacked output made it zero-fill and copy
+        # (NQ,B,O,T) once per head
+        return tuple(mu.unbind(0))
 
     @staticmethod
-    def backward(ctx, grad_mu):
+    def backward(ctx, *grads):
         sol, Wc = ctx.saved_tensors
         B, T, S = sol.shape
         NQ, O, _ = Wc.shape
-        grad_mu = grad_mu.to(torch.float32).contiguous()
+        gs = [None if g is None else g.to(torch.float32).contiguous() for g in grads] + [None] * (3 - NQ)
         grad_sol = torch.empty((B, T, S), device=sol.device, dtype=torch.float32)
         grad_W = torch.zeros_like(Wc)
         with torch.cuda.device(sol.device):
-            rc = _cabi.lib().slode_heads_bwd(B, T, S, O, NQ, sol.data_ptr(), sol.stride(1), sol.stride(0), Wc.data_ptr(),
-                                             grad_mu.data_ptr(), grad_sol.data_ptr(), grad_sol.stride(1),
-                                             grad_sol.stride(0), grad_W.data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream)
-        _cabi.check(rc, "slode_heads_bwd")
+            rc = _cabi.lib().slode_heads_bwd_split(
+                B, T, S, O, NQ, sol.data_ptr(), sol.stride(1), sol.stride(0), Wc.data_ptr(),
+                *[g.data_ptr() if g is not None else None for g in gs[:3]], grad_sol.data_ptr(), grad_sol.stride(1),
+                grad_sol.stride(0), grad_W.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "slode_heads_bwd_split")
         return grad_sol, grad_W
 
 
 def decoder_heads(solution, weights):
     """``[Linear_q(solution).permute(0, 2, 1) for q]`` for bias-free ``Linear(S -> O)`` weights, in one kernel."""
     W = torch.stack(list(weights), dim=0)
-    mu = _Heads.apply(solution, W)
-    return [mu[q] for q in range(W.shape[0])]
+    return list(_Heads.apply(solution, W))
 
 
 def _make_ode_model(config, times, latent_dim, device):
