@@ -35,5 +35,8 @@ else:
     y0 = p.initialize_state(z).detach().requires_grad_(True)
     sol = slode.odeint_adjoint(p.gen_dynamics(z), y0, p.times, method="dopri5", rtol=1e-5, atol=1e-6)
     sol.backward(torch.randn_like(sol))
+    from structured_latent_odes_b200 import torchdiffeq_api as api
+    st = api.last_dopri5_adjoint_stats
+    print("adjoint backward: accepted", st.n_accept, "rejected", st.n_reject, "rhs evaluations per trajectory", st.n_rhs)
 torch.cuda.synchronize()
 print("done", what)
