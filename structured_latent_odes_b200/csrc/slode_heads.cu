@@ -128,6 +128,132 @@ heads_bwd_kernel(int64_t B, int T, int O, int NQ, const float* __restrict__ sol,
   for (int i = threadIdx.x; i < nqo * S; i += kBlock) atomicAdd(gW + i, sG[i]);
 }
 
+// Vectorised variants: one thread = FOUR consecutive time points of one trajectory.  With (B,T,S)-contiguous storage
+// and T % 4 == 0 the four state rows are 4*S contiguous floats (S 16-byte loads), every head output / head gradient row
+// contributes one 16-byte access, and a thread has 14 (NQ*O = 9, S = 5) 16-byte loads in flight instead of 14 4-byte
+// ones: the scalar kernels are bound by memory-level parallelism (1.75 TB/s backward), not by bytes.
+template <int S, int QM>
+__global__ void __launch_bounds__(kBlock)
+heads_fwd_vec_kernel(int64_t B, int T, int O, int NQ, const float* __restrict__ sol, int64_t sb,
+                     const float* __restrict__ W, float* __restrict__ mu) {
+  __shared__ float sW[QM * S];
+  __shared__ int64_t sOff[QM];
+  const int nqo = NQ * O;
+  for (int i = threadIdx.x; i < QM * S; i += kBlock) sW[i] = i < nqo * S ? W[i] : 0.0f;
+  for (int i = threadIdx.x; i < QM; i += kBlock) {
+    const int q = i / O, o = i - q * O;
+    sOff[i] = ((int64_t)q * B * O + o) * T;
+  }
+  __syncthreads();
+  const int T4 = T / 4;
+  const int64_t n = B * (int64_t)T4, OT = (int64_t)O * T;
+  for (int64_t idx = (int64_t)blockIdx.x * kBlock + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * kBlock) {
+    const int64_t b = idx / T4;
+    const int t = 4 * (int)(idx - b * T4);
+    const float4* x4 = reinterpret_cast<const float4*>(sol + b * sb + (int64_t)t * S);
+    float x[4 * S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const float4 v = __ldg(x4 + k);
+      x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+    }
+    float* out = mu + b * OT + t;
+#pragma unroll
+    for (int qo = 0; qo < QM; ++qo) {
+      if (qo < nqo) {
+        float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float w = sW[qo * S + s];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) a[tt] = fmaf(w, x[tt * S + s], a[tt]);
+        }
+        *reinterpret_cast<float4*>(out + sOff[qo]) = make_float4(a[0], a[1], a[2], a[3]);
+      }
+    }
+  }
+}
+
+template <int S, int QM>
+__global__ void __launch_bounds__(kBlock)
+heads_bwd_vec_kernel(int64_t B, int T, int O, int NQ, const float* __restrict__ sol, int64_t sb,
+                     const float* __restrict__ W, const float* __restrict__ g0, const float* __restrict__ g1,
+                     const float* __restrict__ g2, float* __restrict__ gsol, int64_t gsb, float* __restrict__ gW) {
+  __shared__ float sW[QM * S];
+  __shared__ float sG[QM * S];
+  __shared__ const float* sPtr[QM];
+  const int nqo = NQ * O;
+  for (int i = threadIdx.x; i < QM * S; i += kBlock) {
+    sW[i] = i < nqo * S ? W[i] : 0.0f;
+    sG[i] = 0.0f;
+  }
+  for (int i = threadIdx.x; i < QM; i += kBlock) {
+    const int q = i / O, o = i - q * O;
+    const float* base = q == 0 ? g0 : (q == 1 ? g1 : g2);
+    sPtr[i] = (i < nqo && base) ? base + (int64_t)o * T : nullptr;
+  }
+  __syncthreads();
+  float acc[QM][S];
+#pragma unroll
+  for (int qo = 0; qo < QM; ++qo) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[qo][s] = 0.0f;
+  }
+  const int T4 = T / 4;
+  const int64_t n = B * (int64_t)T4, OT = (int64_t)O * T;
+  for (int64_t idx = (int64_t)blockIdx.x * kBlock + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * kBlock) {
+    const int64_t b = idx / T4;
+    const int t = 4 * (int)(idx - b * T4);
+    const float4* x4 = reinterpret_cast<const float4*>(sol + b * sb + (int64_t)t * S);
+    float x[4 * S], gs[4 * S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const float4 v = __ldg(x4 + k);
+      x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4 * S; ++k) gs[k] = 0.0f;
+    const int64_t off = b * OT + t;
+#pragma unroll
+    for (int qo = 0; qo < QM; ++qo) {
+      if (qo < nqo) {
+        const float* gp = sPtr[qo];
+        const float4 g4 = gp ? __ldg(reinterpret_cast<const float4*>(gp + off)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float w = sW[qo * S + s];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            gs[tt * S + s] = fmaf(g[tt], w, gs[tt * S + s]);
+            acc[qo][s] = fmaf(g[tt], x[tt * S + s], acc[qo][s]);
+          }
+        }
+      }
+    }
+    float4* o4 = reinterpret_cast<float4*>(gsol + b * gsb + (int64_t)t * S);
+#pragma unroll
+    for (int k = 0; k < S; ++k) o4[k] = make_float4(gs[4 * k], gs[4 * k + 1], gs[4 * k + 2], gs[4 * k + 3]);
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int qo = 0; qo < QM; ++qo) {
+    if (qo < nqo) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float v = acc[qo][s];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) atomicAdd(&sG[qo * S + s], v);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nqo * S; i += kBlock) atomicAdd(gW + i, sG[i]);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // resident blocks per SM of a kernel (cached per kernel)
 template <class K>
 static int blocks_per_sm(K kern) {
@@ -173,11 +299,31 @@ extern "C" int slode_heads_fwd(int64_t B, int T, int S, int O, int NQ, const flo
   }
   if (B == 0) return SLODE_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int64_t blocks = (B * (int64_t)T + heads::kBlock - 1) / heads::kBlock;
-  const int grid = (int)std::min<int64_t>(blocks, (int64_t)heads::device_sms() * 32);
+  const int nqo = NQ * O;
+  if (T % 4 == 0 && sol_stride_t == S && (sol_stride_b % 4) == 0 && nqo <= 12 && heads::aligned16(sol) &&
+      heads::aligned16(mu)) {
+    const int64_t blocks = (B * (int64_t)(T / 4) + heads::kBlock - 1) / heads::kBlock;
+    const int sms = heads::device_sms();
+#define GOV(SS, QM)                                                                                                \
+  do {                                                                                                             \
+    auto kern = heads::heads_fwd_vec_kernel<SS, QM>;                                                               \
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * heads::blocks_per_sm(kern));                    \
+    kern<<<grid, heads::kBlock, 0, stream>>>(B, T, O, NQ, sol, sol_stride_b, W, mu);                               \
+  } while (0)
+#define GOVQ(SS)                                                                                                   \
+  do {                                                                                                             \
+    if (nqo <= 3) GOV(SS, 3); else if (nqo <= 9) GOV(SS, 9); else GOV(SS, 12);                                     \
+  } while (0)
+    if (S == 4) GOVQ(4); else if (S == 5) GOVQ(5); else GOVQ(8);
+#undef GOVQ
+#undef GOV
+  } else {
+    const int64_t blocks = (B * (int64_t)T + heads::kBlock - 1) / heads::kBlock;
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)heads::device_sms() * 32);
 #define GO(SS) heads::heads_fwd_kernel<SS><<<grid, heads::kBlock, 0, stream>>>(B, T, O, NQ, sol, sol_stride_t, sol_stride_b, W, mu)
-  if (S == 4) GO(4); else if (S == 5) GO(5); else GO(8);
+    if (S == 4) GO(4); else if (S == 5) GO(5); else GO(8);
 #undef GO
+  }
   SLODE_CUDA_TRY(cudaGetLastError());
   g_fwd_launches = 1;
   return SLODE_OK;
@@ -210,22 +356,43 @@ extern "C" int slode_heads_bwd_split(int64_t B, int T, int S, int O, int NQ, con
   if (NQ < 3) g2 = nullptr;
   if (B == 0) return SLODE_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int64_t blocks = (B * (int64_t)T + heads::kBlock - 1) / heads::kBlock;
   const int sms = heads::device_sms(), nqo = NQ * O;
-#define GO(SS, QM)                                                                                                 \
+  if (T % 4 == 0 && sol_stride_t == S && gsol_stride_t == S && (sol_stride_b % 4) == 0 && (gsol_stride_b % 4) == 0 &&
+      nqo <= 12 && heads::aligned16(sol) && heads::aligned16(grad_sol) && heads::aligned16(g0) && heads::aligned16(g1) &&
+      heads::aligned16(g2)) {
+    const int64_t blocks = (B * (int64_t)(T / 4) + heads::kBlock - 1) / heads::kBlock;
+#define GOV(SS, QM)                                                                                                \
   do {                                                                                                             \
-    auto kern = heads::heads_bwd_kernel<SS, QM>;                                                                   \
+    auto kern = heads::heads_bwd_vec_kernel<SS, QM>;                                                               \
     const int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * heads::blocks_per_sm(kern));                    \
-    kern<<<grid, heads::kBlock, 0, stream>>>(B, T, O, NQ, sol, sol_stride_t, sol_stride_b, W, g0, g1, g2, grad_sol, \
-                                             gsol_stride_t, gsol_stride_b, grad_W);                                \
+    kern<<<grid, heads::kBlock, 0, stream>>>(B, T, O, NQ, sol, sol_stride_b, W, g0, g1, g2, grad_sol,              \
+                                             gsol_stride_b, grad_W);                                               \
   } while (0)
-#define GOQ(SS)                                                                                                    \
+#define GOVQ(SS)                                                                                                   \
   do {                                                                                                             \
-    if (nqo <= 3) GO(SS, 3); else if (nqo <= 9) GO(SS, 9); else GO(SS, 24);                                        \
+    if (nqo <= 3) GOV(SS, 3); else if (nqo <= 9) GOV(SS, 9); else GOV(SS, 12);                                     \
   } while (0)
-  if (S == 4) GOQ(4); else if (S == 5) GOQ(5); else GOQ(8);
-#undef GOQ
-#undef GO
+    if (S == 4) GOVQ(4); else if (S == 5) GOVQ(5); else GOVQ(8);
+#undef GOVQ
+#undef GOV
+  } else {
+  const int64_t blocks = (B * (int64_t)T + heads::kBlock - 1) / heads::kBlock;
+    const int sms = heads::device_sms(), nqo = NQ * O;
+  #define GO(SS, QM)                                                                                                 \
+    do {                                                                                                             \
+      auto kern = heads::heads_bwd_kernel<SS, QM>;                                                                   \
+      const int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * heads::blocks_per_sm(kern));                    \
+      kern<<<grid, heads::kBlock, 0, stream>>>(B, T, O, NQ, sol, sol_stride_t, sol_stride_b, W, g0, g1, g2, grad_sol, \
+                                               gsol_stride_t, gsol_stride_b, grad_W);                                \
+    } while (0)
+  #define GOQ(SS)                                                                                                    \
+    do {                                                                                                             \
+      if (nqo <= 3) GO(SS, 3); else if (nqo <= 9) GO(SS, 9); else GO(SS, 24);                                        \
+    } while (0)
+    if (S == 4) GOQ(4); else if (S == 5) GOQ(5); else GOQ(8);
+  #undef GOQ
+  #undef GO
+  }
   SLODE_CUDA_TRY(cudaGetLastError());
   g_bwd_launches = 1;
   return SLODE_OK;

@@ -106,3 +106,24 @@ def test_multiple_samples_equals_the_reference_style_loop():
             _, q75, q50, q25, _ = dec(res["z"][k])
             assert torch.equal(res["mu_50"][..., k], q50) and torch.equal(res["mu_75"][..., k], q75)
             assert torch.equal(res["mu_25"][..., k], q25)
+
+
+@pytest.mark.parametrize("S,O,NQ,T,B", [(5, 3, 3, 100, 130), (8, 4, 3, 100, 37), (4, 2, 1, 16, 300), (5, 3, 2, 86, 65),
+                                        (5, 8, 3, 40, 50)])
+def test_heads_vector_and_scalar_paths_against_torch(S, O, NQ, T, B):
+    """The heads kernels take four time points per thread when T % 4 == 0 on (B,T,S)-contiguous rows (16-byte loads)
+    and one otherwise; NQ*O up to 12 is unrolled, above that rolled.  Both against plain torch, including a batch
+    slice that starts in the middle of the buffer and a head whose output does not enter the loss."""
+    import structured_latent_odes_b200 as slode
+    g = torch.Generator(device="cuda").manual_seed(S * 100 + T)
+    full = torch.randn(B + 5, T, S, device="cuda", generator=g)
+    x = full[3:3 + B].detach().requires_grad_(True)          # view with an offset: rows stay contiguous
+    W = [torch.randn(O, S, device="cuda", generator=g).requires_grad_(True) for _ in range(NQ)]
+    mus = slode.decoder_heads(x, W)
+    ref = [(x @ w.t()).permute(0, 2, 1) for w in W]
+    used = list(range(NQ)) if NQ < 3 else [0, 2]             # with three heads, leave the middle one out of the loss
+    G = {q: torch.randn(B, O, T, device="cuda", generator=g) for q in used}
+    outs = torch.autograd.grad(sum((mus[q] * G[q]).sum() for q in used), [x] + [W[q] for q in used])
+    refs = torch.autograd.grad(sum((ref[q] * G[q]).sum() for q in used), [x] + [W[q] for q in used])
+    for a, b in zip(list(mus) + list(outs), list(ref) + list(refs)):
+        assert U.rel_err(a, b) < 1e-5
