@@ -221,8 +221,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, B_per_gpu=B, n=1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        # the b200 arm's config (the workload both arms are quoted on); what this arm actually ran per step is the
+        # bounded sample described in cpu_baseline.sample
+        "config": workload_config(args, B_per_gpu=args.batch, n=args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "sample_trajectories_per_step": B},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -234,11 +237,15 @@ def workload_config(args, B_per_gpu, n):
             "trajectories_per_gpu": B_per_gpu, "trajectories_total": B_per_gpu * n, "obs_times": T, "latent_dim": L,
             "sol_layout": getattr(args, "layout", "tbs"), "ode_hidden_dim": H, "ode_state_dim": S, "solver": args.method,
             "gradient": "odeint_adjoint emulation" if args.adjoint else "discrete adjoint (odeint + autograd parity)",
-            "mlp_evaluation": "piecewise-linear heads (alpha t + beta per trajectory, updated at relu crossings)",
-            "reverse_sweep": "re-evaluates the heads from the stored grid states (nothing else is checkpointed)",
-            "thread_mapping": "one trajectory per thread, fp32x2 over state pairs",
             "parallelism": f"trajectory-sharded x{n}, one flat all-reduce of parameter gradients",
             "l2": "inputs larger than L2 (sol / grad_sol are 2.1 GB each per GPU vs 126 MB L2)"}
+
+
+IMPLEMENTATION = {   # how the b200 arm computes the workload above (not part of the workload: the reference arm differs)
+    "mlp_evaluation": "piecewise-linear heads (alpha t + beta per trajectory, updated at relu crossings)",
+    "reverse_sweep": "re-evaluates the heads from the stored grid states (nothing else is checkpointed)",
+    "thread_mapping": "one trajectory per thread, fp32x2 over state pairs",
+}
 
 
 def pin_to_gpu_numa_node(index):
@@ -544,6 +551,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, B, world),
+            "implementation": IMPLEMENTATION,
             "clocks": dict(clocks.summary(), e2e_region=clocks_e2e.summary()),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "copy_bound_ms": copy_ms, "frac_of_copy_bound": copy_ms / e2e_ms,
