@@ -19,6 +19,14 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
+# Code-generation guard (tests/test_gpu_codegen_guard.py): the translation unit with the largest register-resident
+# sorting network -- (64,5): 64 keys, spills at 96 / 168 registers -- is ALSO built at ptxas -O1 and linked into a second
+# library; on the GPU both builds must give the same trajectories and gradients.  (Round 1 hit a ptxas -O3
+# miscompile in exactly such an instantiation; its kernels are gone, the guard stays.)
+GUARD_SRC = "slode_fixed_64_5.cu"
+GUARD_LIB = os.path.join(CSRC, "libslode_b200_guard_O1.so")
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isfile(cand) or cand == "nvcc"):
@@ -79,6 +87,13 @@ def build(force=False, verbose=False):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     with open(stamp, "w") as f:
         f.write(str(digest))
+    go = os.path.join(OBJ, GUARD_SRC.replace(".cu", "_O1.o"))
+    gs = os.path.join(CSRC, GUARD_SRC)
+    if force or _stale(go, [gs] + headers):
+        run([nvcc] + NVCC_FLAGS + ["-Xptxas", "-O1", "-c", gs, "-o", go])
+    if force or jobs or _stale(GUARD_LIB, objs + [go]):
+        others = [o for o in objs if not o.endswith(GUARD_SRC.replace(".cu", ".o"))]
+        run([nvcc, "-shared", "-o", GUARD_LIB] + others + [go, "-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 
 
