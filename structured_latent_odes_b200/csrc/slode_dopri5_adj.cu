@@ -31,7 +31,11 @@ namespace slode {
 namespace adj {
 
 constexpr int kT = 128;      // threads per block
-constexpr int kCT = kT + 1;  // row stride of the per-trajectory c table (conflict-free for lanes over trajectories)
+// TILE = trajectories per block and pass: 128 (one per thread) for batches that fill the device, 32 for small ones.
+// A pass is as long as ONE warp's instruction stream (one warp per scheduler, every pass ends in a grid barrier), and
+// 70 % of that stream is the "lane = hidden unit" walk over the warp's trajectories: with TILE = 32 the four warps
+// of a block share one warp's 32 trajectories, eight each, instead of walking 32 each (the state part then runs on
+// warp 0 alone).  Row stride of the per-trajectory c table: TILE + 1 (conflict-free for lanes over trajectories).
 constexpr int kNT = 8;       // tensors of the mixed norm: y, a, W1, b1, Wg, bg, Wd, bd
 
 // Dormand-Prince tableau (torchdiffeq _DORMAND_PRINCE_SHAMPINE_TABLEAU)
@@ -99,9 +103,9 @@ struct Layout {
 
 struct Smem {
   float *wgd, *w1t, *bgd;  // [H][2S] head weights (growth 0..S-1, degradation S..2S-1), [H], [2S]
-  float* ct;               // [H][kCT]   c_j of the block's trajectories
-  float* dl;               // [6][2S][kT] head cotangents of the pass's stages
-  float* zt;               // [kT][LZ]   latent rows
+  float* ct;               // [H][TILE+1] c_j of the block's trajectories
+  float* dl;               // [6][2S][TILE] head cotangents of the pass's stages
+  float* zt;               // [TILE][LZ]  latent rows
   float* bacc;             // [4][P]     block sums of the four combinations
   float* coef;             // [4][6]     combination coefficient of every stage slot
   float* ts;               // [6]        evaluation time (t, not s) of every stage slot
@@ -110,12 +114,12 @@ struct Smem {
 };
 
 __host__ __device__ inline int lz_of(int L) { return L | 1; }
-__host__ __device__ inline size_t smem_floats(int L, int H, int S) {
-  return (size_t)H * 2 * S + H + 2 * S + (size_t)H * kCT + (size_t)6 * 2 * S * kT + (size_t)kT * lz_of(L) +
+__host__ __device__ inline size_t smem_floats(int L, int H, int S, int TILE) {
+  return (size_t)H * 2 * S + H + 2 * S + (size_t)H * (TILE + 1) + (size_t)6 * 2 * S * TILE + (size_t)TILE * lz_of(L) +
          (size_t)4 * n_params(L, H, S) + 24 + 8;
 }
-__host__ __device__ inline size_t smem_bytes(int L, int H, int S) {
-  return (smem_floats(L, H, S) * 4 + 15) / 16 * 16 + 64 * sizeof(double);
+__host__ __device__ inline size_t smem_bytes(int L, int H, int S, int TILE) {
+  return (smem_floats(L, H, S, TILE) * 4 + 15) / 16 * 16 + 64 * sizeof(double);
 }
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter) {
@@ -176,18 +180,18 @@ __device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, 1.0
 
 // one evaluation of the augmented right-hand side (reversed time) for this thread's trajectory at time te;
 // the head cotangents go to the stage slot's rows of sm.dl
-template <int S>
-__device__ __forceinline__ void eval_stage(const Smem& sm, int H, float te, const float (&y)[S], const float (&a)[S],
-                                           float (&ky)[S], float (&ka)[S], int slot) {
+template <int S, int TILE>
+__device__ __forceinline__ void eval_stage(const Smem& sm, int H, int ti, float te, const float (&y)[S],
+                                           const float (&a)[S], float (&ky)[S], float (&ka)[S], int slot) {
   float pg[S], pd[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     pg[s] = sm.bgd[s];
     pd[s] = sm.bgd[S + s];
   }
-  const float* crow = sm.ct + threadIdx.x;
+  const float* crow = sm.ct + ti;
   for (int j = 0; j < H; ++j) {
-    const float h = fmaxf(fmaf(sm.w1t[j], te, crow[j * kCT]), 0.0f);
+    const float h = fmaxf(fmaf(sm.w1t[j], te, crow[j * (TILE + 1)]), 0.0f);
     const float* w = sm.wgd + j * 2 * S;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -195,21 +199,24 @@ __device__ __forceinline__ void eval_stage(const Smem& sm, int H, float te, cons
       pd[s] = fmaf(w[S + s], h, pd[s]);
     }
   }
-  float* d = sm.dl + (size_t)slot * 2 * S * kT + threadIdx.x;
+  float* d = sm.dl + (size_t)slot * 2 * S * TILE + ti;
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     const float G = sigmoidf_(pg[s]), D = sigmoidf_(pd[s]);
     ky[s] = D * y[s] - G;          // -f
     ka[s] = -a[s] * D;             // a * df/dy
-    d[s * kT] = a[s] * (G - G * G);                // a * df/d(pre_G)
-    d[(S + s) * kT] = -a[s] * y[s] * (D - D * D);  // a * df/d(pre_D)
+    d[s * TILE] = a[s] * (G - G * G);                // a * df/d(pre_G)
+    d[(S + s) * TILE] = -a[s] * y[s] * (D - D * D);  // a * df/d(pre_D)
   }
 }
 
-template <int S>
+template <int S, int TILE>
 __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
   extern __shared__ __align__(16) unsigned char adj_smem[];
   const int H = p.H, L = p.L, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kCT = TILE + 1;
+  const int ti = TILE == kT ? tid : lane;          // this thread's trajectory slot in the tile (state part)
+  const bool worker = TILE == kT || warp == 0;     // ... which only the first TILE threads work on
   const Layout lay(L, H, S);
   const int P = lay.P;
   Smem sm;
@@ -219,13 +226,13 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
     sm.w1t = f; f += H;
     sm.bgd = f; f += 2 * S;
     sm.ct = f; f += (size_t)H * kCT;
-    sm.dl = f; f += (size_t)6 * 2 * S * kT;
+    sm.dl = f; f += (size_t)6 * 2 * S * TILE;
     sm.LZ = lz_of(L);
-    sm.zt = f; f += (size_t)kT * sm.LZ;
+    sm.zt = f; f += (size_t)TILE * sm.LZ;
     sm.bacc = f; f += (size_t)4 * P;
     sm.coef = f; f += 24;
     sm.ts = f; f += 8;
-    sm.red = reinterpret_cast<double*>(adj_smem + (smem_floats(L, H, S) * 4 + 15) / 16 * 16);
+    sm.red = reinterpret_cast<double*>(adj_smem + (smem_floats(L, H, S, TILE) * 4 + 15) / 16 * 16);
   }
   for (int i = tid; i < H * 2 * S; i += kT) {
     const int j = i / (2 * S), o = i % (2 * S);
@@ -235,16 +242,21 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
   for (int i = tid; i < 2 * S; i += kT) sm.bgd[i] = i < S ? p.bg[i] : p.bd[i - S];
   __syncthreads();
 
-  const int64_t ntiles = (p.B + kT - 1) / kT;
+  const int64_t ntiles = (p.B + TILE - 1) / TILE;
   const bool resident = ntiles <= (int64_t)gridDim.x;  // every block owns at most one tile: its tables stay loaded
   const size_t nthreads = (size_t)gridDim.x * kT, gthread = (size_t)blockIdx.x * kT + tid;
   const double n_of[kNT] = {(double)p.B * S, (double)p.B * S, (double)H * (L + 1), (double)H,
                             (double)S * H,   (double)S,       (double)S * H,       (double)S};
 
-  auto load_tables = [&](int64_t tile) {
-    const int64_t b = min(tile * kT + tid, p.B - 1);
-    for (int j = 0; j < H; ++j) sm.ct[j * kCT + tid] = __ldg(p.c + b * H + j);
-    for (int l = 0; l < L; ++l) sm.zt[tid * sm.LZ + l] = __ldg(p.z + b * L + l);
+  auto load_tables = [&](int64_t tile) {   // all threads: consecutive threads read consecutive floats of the tile's rows
+    for (int i = tid; i < TILE * H; i += kT) {
+      const int r = i / H, j = i - r * H;
+      sm.ct[j * kCT + r] = __ldg(p.c + min(tile * TILE + r, p.B - 1) * H + j);
+    }
+    for (int i = tid; i < TILE * L; i += kT) {
+      const int r = i / L, l = i - r * L;
+      sm.zt[r * sm.LZ + l] = __ldg(p.z + min(tile * TILE + r, p.B - 1) * L + l);
+    }
   };
   if (resident && blockIdx.x < ntiles) load_tables(blockIdx.x);
   for (int e = (int)gthread; e < P; e += (int)nthreads) p.g[e] = 0.0f;
@@ -254,7 +266,9 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
   // combinations of every parameter element of the lane's units, added to the block sums in warp order -------
   auto unit_pass = [&](int nst) {
     constexpr int LC = S <= 5 ? 16 : 8;  // latent columns per trip (registers)
-    const int tb = warp * 32;
+    // the trajectories this warp walks: its own 32 (TILE = 128) or its quarter of the tile's 32 (TILE = 32)
+    const int tb = TILE == kT ? warp * 32 : 0;
+    const int bb0 = TILE == kT ? 0 : warp * (32 / (kT / 32)), bb1 = TILE == kT ? 32 : bb0 + 32 / (kT / 32);
     for (int j0 = 0; j0 < H; j0 += 32) {
       const int j = j0 + lane;
       const bool act = j < H;
@@ -273,20 +287,20 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
 #pragma unroll
           for (int l = 0; l < LC; ++l) aZ[k][l] = 0.0f;
         }
-        for (int bb = 0; bb < 32; ++bb) {
+        for (int bb = bb0; bb < bb1; ++bb) {
           const float cj = act ? sm.ct[j * kCT + tb + bb] : 0.0f;
           float dc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dct[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           for (int i = 0; i < nst; ++i) {
             const float te = sm.ts[i];
             const float pre = fmaf(w1, te, cj);
             const float h = fmaxf(pre, 0.0f);
-            const float* d = sm.dl + (size_t)i * 2 * S * kT + tb + bb;
+            const float* d = sm.dl + (size_t)i * 2 * S * TILE + tb + bb;
             float v = 0.0f;
             const float c0 = sm.coef[kS * 6 + i], c1 = sm.coef[kE * 6 + i], c2 = sm.coef[kM * 6 + i],
                         c3 = sm.coef[kK * 6 + i];
 #pragma unroll
             for (int o = 0; o < 2 * S; ++o) {
-              const float dd = d[o * kT];
+              const float dd = d[o * TILE];
               v = fmaf(w[o], dd, v);
               if (head) {
                 const float u = dd * h;
@@ -353,9 +367,9 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
       float ab[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       if (lane < 2 * S) {
         for (int i = 0; i < nst; ++i) {
-          const float* d = sm.dl + ((size_t)i * 2 * S + lane) * kT + tb;
+          const float* d = sm.dl + ((size_t)i * 2 * S + lane) * TILE + tb;
           float s = 0.0f;
-          for (int bb = 0; bb < 32; ++bb) s += d[bb];
+          for (int bb = bb0; bb < bb1; ++bb) s += d[bb];
 #pragma unroll
           for (int k = 0; k < 4; ++k) ab[k] = fmaf(sm.coef[k * 6 + i], s, ab[k]);
         }
@@ -408,11 +422,13 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
         load_tables(tile);
         __syncthreads();
       }
-      const int64_t br = tile * kT + tid;
-      const bool ok = br < p.B;
-      const int64_t b = ok ? br : p.B - 1;
+      const int64_t br = tile * TILE + ti;
+      const bool ok = worker && br < p.B;
+      const int64_t b = br < p.B ? br : p.B - 1;
       float y0[S], a0[S];
-      if (kind == kPassF0) {
+      if (!worker) {
+        // (TILE = 32: warps 1..3 only take part in the unit pass below)
+      } else if (kind == kPassF0) {
         // interval start: y <- the stored forward value, a <- the carried adjoint + the output cotangent
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -421,7 +437,7 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
           a0[s] = ok ? (iv == p.T - 1 ? gi : p.a[b * S + s] + gi) : 0.0f;
         }
         float ky[S], ka[S];
-        eval_stage<S>(sm, H, sm.ts[0], y0, a0, ky, ka, 0);
+        eval_stage<S, TILE>(sm, H, ti, sm.ts[0], y0, a0, ky, ka, 0);
         if (ok) {
 #pragma unroll
           for (int s = 0; s < S; ++s) {
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
           y1[s] = fmaf(dsf, f0y[s], y0[s]);
           a1[s] = fmaf(dsf, f0a[s], a0[s]);
         }
-        eval_stage<S>(sm, H, sm.ts[0], y1, a1, ky, ka, 0);
+        eval_stage<S, TILE>(sm, H, ti, sm.ts[0], y1, a1, ky, ka, 0);
         if (ok) {
 #pragma unroll
           for (int s = 0; s < S; ++s) {
@@ -484,7 +500,7 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
             yi[s] = y0[s] + sy;
             ai[s] = a0[s] + sa;
           }
-          eval_stage<S>(sm, H, sm.ts[i - 1], yi, ai, ky[i], ka[i], i - 1);
+          eval_stage<S, TILE>(sm, H, ti, sm.ts[i - 1], yi, ai, ky[i], ka[i], i - 1);
         }
         if (ok) {
 #pragma unroll
@@ -624,8 +640,8 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
         const float x = __fdiv_rn(__fsub_rn((float)s_end, s0f), __fsub_rn(s1f, s0f));
         // commit: every trajectory / parameter element by its owner thread
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          const int64_t b = tile * kT + tid;
-          if (b < p.B) {
+          const int64_t b = tile * TILE + ti;
+          if (worker && b < p.B) {
 #pragma unroll
             for (int s = 0; s < S; ++s) {
               const int64_t o = b * S + s;
@@ -664,8 +680,8 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
   }
   // ---- outputs: dL/dy0 = a + grad_sol[0], dL/dtheta = a_theta -------------------------------------------------
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t b = tile * kT + tid;
-    if (b < p.B) {
+    const int64_t b = tile * TILE + ti;
+    if (worker && b < p.B) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         const float gi = __ldg(p.gsol + b * p.gsb + s);
@@ -682,10 +698,10 @@ __global__ void __launch_bounds__(kT, 1) dopri5_adjoint_kernel(Args p) {
   }
 }
 
-template <int S>
+template <int S, int TILE>
 static int plan(int L, int H, int sms, int64_t B, int* grid, size_t* smem) {
-  *smem = smem_bytes(L, H, S);
-  auto kern = dopri5_adjoint_kernel<S>;
+  *smem = smem_bytes(L, H, S, TILE);
+  auto kern = dopri5_adjoint_kernel<S, TILE>;
   int dev = 0, max_optin = 0;
   SLODE_CUDA_TRY(cudaGetDevice(&dev));
   SLODE_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -701,7 +717,7 @@ static int plan(int L, int H, int sms, int64_t B, int* grid, size_t* smem) {
     set_error("dopri5 adjoint: kernel does not fit an SM");
     return SLODE_ECUDA;
   }
-  const int64_t tiles = (B + kT - 1) / kT;
+  const int64_t tiles = (B + TILE - 1) / TILE;
   *grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sms * per_sm));
   return SLODE_OK;
 }
@@ -714,11 +730,11 @@ static size_t workspace_bytes(int64_t B, int L, int H, int S, int grid) {
          align256(sizeof(float) * 4 * P * (size_t)grid) + align256(sizeof(double) * 2 * 2 * kNT * (size_t)grid) + 256;
 }
 
-template <int S>
-static int launch(Args a, int sms, void* ws, size_t ws_bytes, bool plan_only, size_t* need, cudaStream_t stream) {
+template <int S, int TILE>
+static int launch_tile(Args a, int sms, void* ws, size_t ws_bytes, bool plan_only, size_t* need, cudaStream_t stream) {
   int grid = 0;
   size_t smem = 0;
-  const int rc = plan<S>(a.L, a.H, sms, a.B, &grid, &smem);
+  const int rc = plan<S, TILE>(a.L, a.H, sms, a.B, &grid, &smem);
   if (rc) return rc;
   *need = workspace_bytes(a.B, a.L, a.H, S, grid);
   if (plan_only) return SLODE_OK;
@@ -743,9 +759,17 @@ static int launch(Args a, int sms, void* ws, size_t ws_bytes, bool plan_only, si
   a.barrier = reinterpret_cast<unsigned long long*>(w);
   SLODE_CUDA_TRY(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned long long), stream));
   void* args[] = {&a};
-  SLODE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)dopri5_adjoint_kernel<S>, dim3(grid), dim3(kT), args, smem,
-                                             stream));
+  SLODE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)dopri5_adjoint_kernel<S, TILE>, dim3(grid), dim3(kT), args,
+                                             smem, stream));
   return SLODE_OK;
+}
+
+template <int S>
+static int launch(const Args& a, int sms, void* ws, size_t ws_bytes, bool plan_only, size_t* need, cudaStream_t stream) {
+  // small batches: 32 trajectories per block (four warps share them); batches that give every SM a 128-trajectory
+  // block keep one trajectory per thread
+  if ((a.B + kT - 1) / kT < sms) return launch_tile<S, 32>(a, sms, ws, ws_bytes, plan_only, need, stream);
+  return launch_tile<S, kT>(a, sms, ws, ws_bytes, plan_only, need, stream);
 }
 
 static int dispatch(const Args& a, int S, int sms, void* ws, size_t ws_bytes, bool plan_only, size_t* need,
