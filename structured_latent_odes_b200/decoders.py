@@ -19,7 +19,7 @@ from torch import nn
 from . import _cabi
 from .blackbox_ode import OdeModel
 
-__all__ = ["Decoder", "GaussianDecoder", "decoder_heads", "multiple_samples"]
+__all__ = ["Decoder", "GaussianDecoder", "VarianceGaussianDecoder", "decoder_heads", "multiple_samples"]
 
 
 class _Heads(torch.autograd.Function):
@@ -115,6 +115,32 @@ class GaussianDecoder(nn.Module):
         solution = self.ode_model.solve_ODE(z=z)
         (mean,) = decoder_heads(solution, (self.output_mean[0].weight,))
         std = torch.ones_like(mean) * nn.functional.softplus(self.constant_std)
+        return solution, mean, std
+
+
+class VarianceGaussianDecoder(nn.Module):
+    """``models/decoders.py:94-141``: a second latent ODE (``std_ode_model``) whose head gives the observation scale
+    (no model of the reference uses it; mirrored for the module's completeness).  Two fused solves, two head passes."""
+
+    def __init__(self, config, times, latent_dim, device):
+        super().__init__()
+        self.times = times
+        self.ode_state_dim = config.ode_state_dim
+        self.obs_dim = config.obs_dim
+        self.latent_dim = latent_dim
+        self.ode_hidden_dim = config.ode_hidden_dim
+        self.ode_model = _make_ode_model(config, times, latent_dim, device)
+        self.std_ode_model = _make_ode_model(config, times, latent_dim, device)
+        self.output_mean = nn.Sequential(nn.Linear(self.ode_state_dim, self.obs_dim, bias=False))
+        self.output_std = nn.Sequential(nn.Linear(self.ode_state_dim, self.obs_dim, bias=False))
+        self.constant_std = nn.Parameter(torch.ones(self.obs_dim, len(self.times)) * config.constant_std,
+                                         requires_grad=True)
+
+    def forward(self, z):
+        solution = self.ode_model.solve_ODE(z=z)
+        (mean,) = decoder_heads(solution, (self.output_mean[0].weight,))
+        solution_std = self.std_ode_model.solve_ODE(z=z)
+        (std,) = decoder_heads(solution_std, (self.output_std[0].weight,))
         return solution, mean, std
 
 

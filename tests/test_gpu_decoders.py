@@ -90,6 +90,19 @@ def test_state_dict_keys_equal_reference_decoder():
         gref = dec_ref.GaussianDecoder(config=cfg, latent_dim=L, times=times, device="cpu")
     assert sorted(ref.state_dict()) == sorted(slode.Decoder(cfg, times, L, "cpu").state_dict())
     assert sorted(gref.state_dict()) == sorted(slode.GaussianDecoder(cfg, times, L, "cpu").state_dict())
+    with contextlib.redirect_stdout(io.StringIO()):
+        vref = dec_ref.VarianceGaussianDecoder(config=cfg, latent_dim=L, times=times, device="cpu")
+    ours = slode.VarianceGaussianDecoder(cfg, times.cuda(), L, "cuda")
+    assert sorted(vref.state_dict()) == sorted(ours.state_dict())
+    # same weights -> same outputs as the reference's real class over the oracle solver (it runs on the CPU)
+    ours.load_state_dict(vref.state_dict())
+    ours = ours.cuda()
+    z = torch.randn(9, L)
+    with torch.no_grad():
+        sol_r, mean_r, std_r = vref(z)
+        sol_o, mean_o, std_o = ours(z.cuda())
+    for a, b in ((sol_o, sol_r), (mean_o, mean_r), (std_o, std_r)):
+        assert U.rel_err(a, b) < 1e-5
 
 
 def test_multiple_samples_equals_the_reference_style_loop():
