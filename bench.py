@@ -563,6 +563,8 @@ def main():
                             f"loss + {reducer.numel} parameter gradients on the host; {nchunk} double-buffered chunks; "
                             "copy_bound_ms = the same pinned->device copies alone, all ranks at once"},
             "gpu_launches": n_launches,
+            "kernel_ms_series": {k: {"first": [round(x, 3) for x in v[:4]], "last": [round(x, 3) for x in v[-4:]]}
+                                 for k, v in ktimes.items()},
             "step_frac_of_xu_bound": xu_step_ms / (ms_total / args.steps),
         }
         dominant_is_bwd = bwd_ms >= fwd_ms
