@@ -75,6 +75,7 @@ def blackbox():
                 z = z0.clone().requires_grad_(True)
                 if method == "dopri5":
                     x0 = m.initialize_state(z)
+                    x0.retain_grad()
                     f = m.gen_dynamics(z)
                     solve = tde.odeint_adjoint if adj else tde.odeint
                     sol = solve(f, x0, times, method="dopri5", rtol=1e-5, atol=1e-6).permute(1, 0, 2)
@@ -84,6 +85,13 @@ def blackbox():
                     sol = m.solve_ODE(z)
                 (sol * G).sum().backward()
                 key = f"{name}/{method}/{int(adj)}"
+                if method == "dopri5" and adj:
+                    # the backward pass of odeint_adjoint: one adaptive solve per output interval; its step log in the
+                    # device's format (interval index, -, step size, accepted) so that the sequence can be replayed
+                    rows = [(float(i), 0.0, d, 1.0 if a else 0.0) for i, acc, dts in tde.last_adjoint_intervals
+                            for a, d in zip(acc, dts)]
+                    out[f"{key}/backward_steps"] = np.array(rows, dtype=np.float64)
+                    out[f"{key}/grad_y0"] = x0.grad.numpy() if x0.grad is not None else None
                 out[f"{key}/sol"] = sol.detach().numpy()
                 out[f"{key}/grad_z"] = z.grad.numpy()
                 for k, p in m.named_parameters():

@@ -205,3 +205,37 @@ def test_raw_c_abi_and_errors():
     one = slode.odeint_adjoint(p.gen_dynamics(z), y1, p.times[:1], method="dopri5")
     one.sum().backward()
     assert torch.equal(y1.grad, torch.ones_like(y1))
+
+
+def test_golden_fixture_from_reference_classes(golden_dir):
+    """tests/golden/blackbox_golden.npz case ``chal/dopri5/1``: ``odeint_adjoint(..., method="dopri5")`` under the
+    reference's REAL OdeModel / OdeFunc / Dynamics classes (tests/golden/make_golden.py), with the step logs of its
+    forward and of its backward solves.  Both sequences replayed on the device: trajectories, dL/dx0 and the six
+    parameter gradients of func.parameters() equal the fixture's."""
+    import os
+    import structured_latent_odes_b200 as slode
+    g = np.load(os.path.join(golden_dir, "blackbox_golden.npz"))
+    times = torch.from_numpy(g["chal/times"]).cuda()
+    W = {k[len("chal/w/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("chal/w/")}
+    m = slode.OdeModel()
+    m.init_with_params(times, 5, 15, 25, True, "dopri5", "cuda")
+    m.load_state_dict(W, strict=False)
+    m = m.cuda()
+    z = torch.from_numpy(g["chal/z"]).cuda()
+    G = torch.from_numpy(g["chal/G"]).cuda()
+    rows, t = [], float(times[0])
+    for a, d in zip(g["chal/dopri5/1/accepted"], g["chal/dopri5/1/dts"]):
+        rows.append((t, float(d), 1.0 if a else 0.0))
+        t = t + float(d) if a else t
+    y0 = m.initialize_state(z).detach().requires_grad_(True)
+    sol = slode.odeint_adjoint(m.gen_dynamics(z), y0, times, method="dopri5", rtol=1e-5, atol=1e-6,
+                               options={"replay_steps": torch.tensor(rows, dtype=torch.float64),
+                                        "adjoint_replay_steps": torch.from_numpy(g["chal/dopri5/1/backward_steps"])})
+    (sol.permute(1, 0, 2) * G).sum().backward()
+    assert U.rel_err(sol.permute(1, 0, 2), torch.from_numpy(g["chal/dopri5/1/sol"])) < 1e-5
+    assert U.rel_err(y0.grad, torch.from_numpy(g["chal/dopri5/1/grad_y0"])) < 5e-5
+    for k, p_ in m.dynamics.named_parameters():
+        if ".prod." in k or ".degr." in k:
+            continue
+        want = torch.from_numpy(g[f"chal/dopri5/1/g/dynamics.{k}"])
+        assert U.rel_err(p_.grad, want) < 5e-5, (k, U.rel_err(p_.grad, want))
