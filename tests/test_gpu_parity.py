@@ -308,3 +308,26 @@ def test_full_size_exact_bench_step_oracle_spot_check():
     assert set(gro) == set(grp)
     for k in gro:
         assert U.rel_err(grp[k], gro[k]) < TOL, (k, U.rel_err(grp[k], gro[k]))
+
+
+@pytest.mark.parametrize("method,adjoint", [("rk4", False), ("midpoint", True)])
+def test_non_finite_latents_propagate_like_torch(method, adjoint):
+    """A NaN / inf latent row (an encoder whose exp-scale overflowed) must surface as non-finite trajectories of THAT
+    row, as torch's relu / sigmoid give in the reference -- not be laundered into finite numbers by fmin / fmax
+    clamps -- and must leave every other row untouched."""
+    o = U.make_oracle("cvs", method, adjoint)
+    p = U.make_product(o)
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(70, 15, generator=g)
+    clean = p.solve_ODE(z.cuda()).detach()
+    z_bad = z.clone()
+    z_bad[5, 3] = float("nan")
+    z_bad[40, 0] = float("inf")
+    with torch.no_grad():
+        want = o.solve_ODE(z_bad)
+        got = p.solve_ODE(z_bad.cuda()).cpu()
+    for row in (5, 40):
+        assert not torch.isfinite(want[row]).all()          # the reference's arithmetic does not hide it ...
+        assert not torch.isfinite(got[row]).all()           # ... and neither do the kernels
+    keep = [i for i in range(70) if i not in (5, 40)]
+    assert torch.equal(got[keep], clean.cpu()[keep])
