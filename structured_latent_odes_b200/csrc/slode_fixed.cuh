@@ -424,7 +424,16 @@ struct Pl {
   // move (alpha, beta) to evaluation time te: every pending crossing whose key is due is confirmed with the exact
   // gate test of the dense evaluation and applied as one rank-one update.  Divergent but short: a unit flips at
   // most once per trajectory and sweep.
+  // on_flip(j) is called for every confirmed flip, inside the same divergent trip (reverse sweep: the flip record, where
+  // the prefix sums do not change between this seek and the evaluation's accumulation).
+  struct NoFlipAction {
+    __device__ __forceinline__ void operator()(int) const {}
+  };
   __device__ __forceinline__ void seek(const float* __restrict__ wt, const Tab& tab, float te) {
+    seek(wt, tab, te, NoFlipAction());
+  }
+  template <class OnFlip>
+  __device__ __forceinline__ void seek(const float* __restrict__ wt, const Tab& tab, float te, OnFlip on_flip) {
     const float uq = dirsign * (te - t_start);
     while (uq >= nk) {
       const int j = (int)(__float_as_uint(nk) & SH::IMASK);
@@ -442,6 +451,7 @@ struct Pl {
         al[q] = fma2(w, uu, al[q]);
         be[q] = fma2(w, vv, be[q]);
       }
+      on_flip(j);
       ++pos;
       nk = __uint_as_float(tab.k[(size_t)pos * tab.ks]);
     }
@@ -901,23 +911,25 @@ struct Sweep {
   // the units whose keys sit at positions [p0, p1) of the sorted table flipped between the previous contributing
   // evaluation and the next one: snapshot the prefix sums as they stand into each unit's record
   __device__ __forceinline__ void events(f2* __restrict__ rec, const Tab& tab, int p0, int p1) {
-    for (int p = p0; p < p1; ++p) {
-      const int j = (int)(tab.k[(size_t)p * tab.ks] & SH::IMASK);
-      // record: [q] -> (P[q], Q[q]).  Two 8-byte stores per q: one 16-byte store would tie P[q] and Q[q] to an aligned
-      // register quad for the whole sweep and the time loop would end in ~24 register copies per interval
-      f2* dst = rec + j * (2 * NQ);
+    for (int p = p0; p < p1; ++p) record(rec, tab, (int)(tab.k[(size_t)p * tab.ks] & SH::IMASK));
+  }
+
+  // snapshot of the prefix sums as they stand into unit j's record
+  __device__ __forceinline__ void record(f2* __restrict__ rec, const Tab& tab, int j) {
+    // record: [q] -> (P[q], Q[q]).  Two 8-byte stores per q: one 16-byte store would tie P[q] and Q[q] to an aligned
+    // register quad for the whole sweep and the time loop would end in ~24 register copies per interval
+    f2* dst = rec + j * (2 * NQ);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        dst[2 * q] = P[q];
-        dst[2 * q + 1] = Q[q];
-      }
-      if constexpr (SH::BIG) {
-        tab.fs[(size_t)j * tab.ks] |= 2;
-      } else {
+    for (int q = 0; q < NQ; ++q) {
+      dst[2 * q] = P[q];
+      dst[2 * q + 1] = Q[q];
+    }
+    if constexpr (SH::BIG) {
+      tab.fs[(size_t)j * tab.ks] |= 2;
+    } else {
 #pragma unroll
-        for (int w = 0; w < SH::NWR; ++w) {
-          if (w == (j >> 5)) flipped[w] |= 1u << (j & 31);
-        }
+      for (int w = 0; w < SH::NWR; ++w) {
+        if (w == (j >> 5)) flipped[w] |= 1u << (j & 31);
       }
     }
   }
@@ -1073,6 +1085,11 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     for (int i = T - 2; i >= 0; --i) {
       const float t0 = t_ahead;
       if (i > 0) t_ahead = ld_early(tgrid + i - 1);
+      // euler (both modes) and the midpoint odeint_adjoint step accumulate ONE evaluation per interval, after all of the
+      // interval's seeks: the prefix sums do not move between a seek and that accumulation, so the flip records are
+      // written inside the seek trips themselves and the separate pass over the flipped keys (another divergent trip
+      // per flip) is not needed there
+      auto rec_now = [&](int j) { sw.record(rec, tab, j); };
       auto state_row = [&]() {  // the interval's state row; its slot is refilled for the next interval at once
         cp_wait<1>();
         const V<NP> r = row_read<S>(rowx);
@@ -1085,13 +1102,11 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
         const float dt = t1 - t0;
         if (METHOD == SLODE_METHOD_EULER) {
           V<NP> G, D;
-          pl.seek(wt, tab, t0);
+          pl.seek(wt, tab, t0, rec_now);
           pl.template eval<false>(t0, G, D);
           const V<NP> x = state_row();
           const V<NP> gk = vscale<NP>(lam, dt);
           const V<NP> gy = vmul<NP>(gk, D);   // D holds -sigmoid
-          sw.events(rec, tab, pdone, pl.pos);
-          pdone = pl.pos;
           sw.add(t0, gk, gy, x, G, D);
           lam = vadd<NP>(lam, gy);
         } else if (METHOD == SLODE_METHOD_MIDPOINT) {
@@ -1175,28 +1190,24 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
         const V<NP> y = state_row();
         if (METHOD == SLODE_METHOD_EULER) {
           V<NP> G, D;
-          pl.seek(wt, tab, t1);
+          pl.seek(wt, tab, t1, rec_now);
           pl.template eval<false>(t1, G, D);
           const V<NP> v = vscale<NP>(lam, ds);
           const V<NP> gy = vmul<NP>(v, D);
-          sw.events(rec, tab, pdone, pl.pos);
-          pdone = pl.pos;
           sw.add(t1, v, gy, y, G, D);
           lam = vadd<NP>(lam, gy);
         } else if (METHOD == SLODE_METHOD_MIDPOINT) {
           const float half = 0.5f * ds;
           const float tm = t1 - half;
           V<NP> Ga, Da, Gm, Dm;
-          pl.seek(wt, tab, t1);   // the stage at t1 has weight 0 in a_theta: its flips are recorded with the next
-          pl.template eval<false>(t1, Ga, Da);
-          pl.seek(wt, tab, tm);
+          pl.seek(wt, tab, t1, rec_now);   // (the stage at t1 has weight 0 in a_theta: nothing is accumulated between
+          pl.template eval<false>(t1, Ga, Da);   //  its flips and those found on the way to tm)
+          pl.seek(wt, tab, tm, rec_now);
           pl.template eval<false>(tm, Gm, Dm);
           const V<NP> ym = vaxpy<NP>(-half, rhs<NP>(Ga, Da, y), y);  // y + half*(D1*y - A1)
           const V<NP> am = vaxpy<NP>(half, vmul<NP>(lam, Da), lam);  // a + half*(-a*D1), D holds -sigmoid
           const V<NP> v = vscale<NP>(am, ds);
           const V<NP> gy = vmul<NP>(v, Dm);
-          sw.events(rec, tab, pdone, pl.pos);
-          pdone = pl.pos;
           sw.add(tm, v, gy, ym, Gm, Dm);
           lam = vadd<NP>(lam, gy);
         } else {  // rk4 3/8 on the augmented system; Ky = -f, Ka = -a*D; new evaluations at ta, tb, t0
