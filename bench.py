@@ -572,6 +572,8 @@ def main():
         line["roofline_other"] = rl_f if dominant_is_bwd else rl_b
         if epoch is not None:
             line["epoch"] = epoch
+        if not args.no_epoch:
+            line["cvs_mechanistic"] = time_cvs_mechanistic(dev, B, hbm_peak)
         if not args.no_cpu_baseline and world == 1:
             reps = 3
             times, cores = time_cpu_reference(args.method, args.adjoint, args.ref_batch, reps)
@@ -587,6 +589,38 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_cvs_mechanistic(dev, B, hbm_peak):
+    """The other right-hand side BASELINE configs[1] names: the CVS mechanistic dynamics (data/cvs/cvs_data.py:52-91) as
+    a forward(t, state) module through the same odeint call, same trajectory count and grid, rk4, fp32 (rank 0's GPU)."""
+    import structured_latent_odes_b200 as slode
+    g = torch.Generator(device=dev).manual_seed(12)
+    ie = torch.where(torch.rand(B, device=dev, generator=g) < 0.5, -2.0, 0.0)
+    rm = torch.where(torch.rand(B, device=dev, generator=g) < 0.5, 0.5, 0.0)
+    f = slode.CvsMechanistic(ie, rm, learn_constants=True)
+    t = torch.arange(0.0, T, 1.0, device=dev)
+    y0 = torch.ones(B, 4, device=dev, requires_grad=True)
+    G = torch.randn(T, B, 4, device=dev, generator=g)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    best = [1e30, 1e30]
+    for r in range(6):
+        f.zero_grad(set_to_none=True)
+        y0.grad = None
+        torch.cuda.synchronize()
+        ev[0].record()
+        sol = slode.odeint(f, y0, t, method="rk4")
+        ev[1].record()
+        sol.backward(G)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            best = [min(best[0], ev[0].elapsed_time(ev[1])), min(best[1], ev[1].elapsed_time(ev[2]))]
+    bytes_f, bytes_b = B * 4 * (T * 4 + 6), B * 4 * (2 * T * 4 + 8)
+    return {"fwd_ms": best[0], "bwd_ms": best[1], "value": B * (T - 1) / ((best[0] + best[1]) * 1e-3), "unit": UNIT,
+            "fwd_hbm_frac": bytes_f / (best[0] * 1e-3) / 1e9 / hbm_peak, "bwd_hbm_frac": bytes_b / (best[1] * 1e-3) / 1e9 / hbm_peak,
+            "what": f"CvsMechanistic RHS, {B} trajectories x {T} times, rk4, fp32, forward + discrete-adjoint backward "
+                    "(gradients to y0, the treatments and the ten shared constants)"}
 
 
 def time_cvs_epoch(dev, rank, world, sync_all):
