@@ -132,6 +132,42 @@ def heads(B, T=100, S=5, O=3, NQ=3):
                       "bwd_GBps": bytes_b / ((ms - ms_f) * 1e-3) / 1e9}), flush=True)
 
 
+def predict(B, T=100, L=15, H=25, S=5, O=3, method="rk4", gaussian=False, times=None, layout="bts"):
+    """Reconstruction / posterior sampling (SURVEY f2 + f3): Decoder.forward under no_grad (solver kernel + heads
+    kernel, the trajectories written and read back) against Decoder.predict (heads in the solver's epilogue, the
+    trajectories never in HBM)."""
+    import types
+    cfg = types.SimpleNamespace(obs_dim=O, ode_state_dim=S, ode_hidden_dim=H, adjoint_solver=False, solver=method,
+                                constant_std=1e-2)
+    t = (torch.arange(T, dtype=torch.float32) if times is None else times).to(dev)
+    torch.manual_seed(12)
+    dec = (slode.GaussianDecoder if gaussian else slode.Decoder)(cfg, t, L, dev).to(dev)
+    dec.ode_model.layout = layout
+    z = torch.randn(B, L, device=dev, generator=torch.Generator(device=dev).manual_seed(12))
+
+    def two():
+        with torch.no_grad():
+            dec(z)
+
+    ms2 = timed(two)
+    ms1 = timed(lambda: dec.predict(z))
+    ms1s = timed(lambda: dec.predict(z, want_solution=True))
+    heads_w = ((dec.output_mean[0].weight,) if gaussian else
+               (dec.output_q50[0].weight, dec.output_q75[0].weight, dec.output_q25[0].weight))
+    ms_k = timed(lambda: dec.ode_model.solve_ODE_heads(z, heads_w))                       # the fused call alone
+    ms_kc = timed(lambda: dec.ode_model.solve_ODE_heads(z, heads_w, contiguous=True))     # unpadded (B,O,T) rows
+    with torch.no_grad():
+        ms_s = timed(lambda: dec.ode_model.solve_ODE(z))                                  # the solve alone
+    nq = 1 if gaussian else 3
+    print(json.dumps({"case": f"predict (no_grad decoder), {nq} heads x obs_dim {O}, (L,H,S)=({L},{H},{S}), {method}, "
+                              f"sol layout {layout}", "B": B, "T": T,
+                      "two_kernels_ms": round(ms2, 4), "fused_ms": round(ms1, 4), "fused_with_sol_ms": round(ms1s, 4),
+                      "solve_heads_call_ms": round(ms_k, 4), "solve_heads_call_contiguous_rows_ms": round(ms_kc, 4),
+                      "solve_only_call_ms": round(ms_s, 4),
+                      "fused_out_GBps": B * T * 4 * nq * O / (ms1 * 1e-3) / 1e9,
+                      "trajectory_steps_per_s_fused": B * (T - 1) / (ms1 * 1e-3)}), flush=True)
+
+
 def tensor_core_proxy(B, Hw, S=5, T=100):
     """BASELINE configs[4] asks where the dense head contraction should move from the FMA pipe to tcgen05.  The kernels
     do not run that contraction at all any more (piecewise-linear heads: O(S) per evaluation + O(S) per relu crossing),
@@ -157,13 +193,28 @@ def tensor_core_proxy(B, Hw, S=5, T=100):
     print(json.dumps(out), flush=True)
 
 
+def predict_cases(big):
+    predict(big)
+    predict(big, layout="tbs")
+    predict(big, gaussian=True)
+    predict(big, method="midpoint")
+    predict(35 * 200, T=142, O=4, method="midpoint")                    # challenge: 35 series x 200 posterior samples
+    tt = torch.cat([torch.zeros(1), torch.cumsum(0.193 + 0.003 * torch.rand(99, generator=torch.Generator().manual_seed(7)), 0)])
+    predict(312 * 200, L=50, S=8, O=4, method="midpoint", times=tt)     # proc: 312 wells x 200 samples
+    predict(312 * 4096, L=50, S=8, O=4, method="midpoint", times=tt)
+
+
 if __name__ == "__main__":
     big = 1 << 20
+    if "predict" in sys.argv[1:]:
+        predict_cases(big)
+        sys.exit(0)
     blackbox("configs[0] CVS default", 128, 86, 15, 25, 5, "midpoint", True)
     blackbox("configs[0] CVS full train set", 810, 86, 15, 25, 5, "midpoint", True)
     cvs_mech(big)
     heads(big)
     heads(big, NQ=1)
+    predict_cases(big)
     for B in (35, 7000, big):
         blackbox("configs[2] challenge dopri5", B, 142, 15, 25, 5, "dopri5", False, rtol=1e-5, atol=1e-6)
     blackbox("configs[2] challenge dopri5 torchdiffeq default tol", 7000, 142, 15, 25, 5, "dopri5", False, rtol=1e-7, atol=1e-9,

@@ -160,6 +160,36 @@ int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H, int S,
                            float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * The forward solve with the decoder heads fused into its epilogue; replaces, in ONE kernel,
+ *     solution = OdeModel.solve_ODE(z)                       models/blackbox_ode.py:36-47
+ *     mu_q     = Linear_q(solution).permute(0, 2, 1)         models/decoders.py:45-47 (Decoder), :86 (GaussianDecoder)
+ * for callers that use the head outputs only (reconstruction / posterior sampling under no_grad,
+ * training_challenge.py:174-195, training_proc.py:205-223): the heads are applied to the states while the solver
+ * thread still holds them, mu is written in the reference's (B, obs_dim, T) layout, and the trajectories themselves
+ * reach HBM only if the caller asks for them.
+ *   head_W  (NQ, O, S) contiguous, as in slode_heads_fwd
+ *   mu      out: element (q, b, o, t) at mu[((q*B + b)*O + o)*mu_row_pitch + t], mu_row_pitch >= T floats.
+ *           mu_row_pitch = T is the reference's contiguous (B, obs_dim, T) per head.  The kernel writes whole 32-byte
+ *           sectors of a row (eight consecutive times) per store; with a pitch that is a multiple of 8 floats (T
+ *           rounded up; the caller hands out mu[..., :T] views) every row has the same sector phase and all
+ *           trajectories of a warp store at the same steps -- about a fifth faster than an unaligned pitch.
+ *   sol     NULL (not written) or as in slode_latent_fixed_fwd with its strides
+ *   every other argument as in slode_latent_fixed_fwd; workspace: slode_fixed_workspace_bytes of the forward with
+ *   the same sizes (rows_in_time = 0) is sufficient.  Results are bit-equal to slode_latent_fixed_fwd followed by
+ *   slode_heads_fwd.  Forward only: a training step needs sol as the reverse sweep's checkpoint and uses the two
+ *   separate entry points.
+ */
+int slode_latent_fixed_heads_fwd(int method, int64_t B, int T, int L, int H, int S,
+                                 const float* t, const float* z,
+                                 const float* W1, const float* b1, const float* Wg, const float* bg,
+                                 const float* Wd, const float* bd,
+                                 const float* Wa, const float* ba, const float* Wb, const float* bb,
+                                 const float* y0,
+                                 int O, int NQ, const float* head_W, float* mu, int64_t mu_row_pitch,
+                                 float* sol, int64_t sol_stride_t, int64_t sol_stride_b,
+                                 void* workspace, int64_t workspace_bytes, void* stream);
+
 int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H, int S,
                            const float* t, const float* z,
                            const float* W1, const float* b1, const float* Wg, const float* bg,

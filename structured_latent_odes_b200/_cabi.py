@@ -34,6 +34,8 @@ SIGNATURES = {
     "slode_mlp_fixed_bwd": (_i, [_i, _i, _i64, _i, _i, _i] + [_p] * 7 + [_p, _i64, _i64, _p, _i64, _i64]
                             + [_p, _p, _p, _p, _i64, _p]),
     "slode_latent_fixed_fwd": (_i, [_i, _i64, _i, _i, _i, _i] + [_p] * 13 + [_p, _i64, _i64, _p, _i64, _p]),
+    "slode_latent_fixed_heads_fwd": (_i, [_i, _i64, _i, _i, _i, _i] + [_p] * 13 + [_i, _i, _p, _p, _i64]
+                                     + [_p, _i64, _i64, _p, _i64, _p]),
     "slode_latent_fixed_bwd": (_i, [_i, _i, _i64, _i, _i, _i, _i] + [_p] * 12 + [_p, _i64, _i64, _p, _i64, _i64]
                                + [_p, _p, _p, _p, _i64, _p]),
     "slode_mlp_dopri5_fwd": (_i, [_i64, _i, _i, _i] + [_p] * 8 + [ctypes.c_double] * 3 + [_i64, _p, _i64]

@@ -102,6 +102,17 @@ class OdeModel(nn.Module):
         sol = solve(func=func, y0=init_state, t=self.times, method=self.solver, layout=self.layout)
         return sol.permute(1, 0, 2)
 
+    def solve_ODE_heads(self, z, head_weights, want_solution=False, contiguous=False):
+        """``solve_ODE`` with the decoder heads fused into the solver's epilogue, under ``no_grad``:
+        returns ``(mu (NQ,B,O,T), solution (B,T,S) or None)``; without ``want_solution`` the trajectories never reach
+        HBM.  Falls back to NOTHING: solvers / state nets the fused kernel does not cover raise."""
+        if not (self.solver in _api.FIXED_METHODS and self._x0_net_is_reference_shaped()):
+            raise NotImplementedError("fused decoder heads need a fixed-grid solver and the reference's latent_to_ode_net")
+        mu, sol = _api.solve_latent_heads(z, self.dynamics, self.latent_to_ode_net, self.times, self.solver,
+                                          head_weights, want_solution=want_solution, layout=self.layout,
+                                          contiguous=contiguous)
+        return mu, (None if sol is None else sol.permute(1, 0, 2))
+
     def _x0_net_is_reference_shaped(self):
         n = self.latent_to_ode_net
         return (isinstance(n, nn.Sequential) and len(n) == 4 and isinstance(n[0], nn.Linear) and isinstance(n[1], nn.ReLU)

@@ -644,6 +644,16 @@ __device__ __forceinline__ void lat_chunk(const float* __restrict__ W, const flo
 // forward
 // ---------------------------------------------------------------------------------------------
 constexpr int kStageT = 4;  // output times staged per trajectory for (B,T,S)-contiguous storage
+constexpr int kHeadRing = 8;  // fused decoder heads: states kept per trajectory = floats of one 32-byte sector of a mu row
+constexpr int kHeadRows = 24; // at most NQ * O = 3 * 8 (head, output) rows
+constexpr int kHeadTab = 2 * kHeadRows + 8;  // floats: row offsets (int64 each) + due masks by sector phase
+
+// one 32-byte store (STG.256): a whole, aligned sector of a head-output row in ONE request
+__device__ __forceinline__ void st_sector(float* dst, const float (&a)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(a[0]), "f"(a[1]), "f"(a[2]),
+               "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7])
+               : "memory");
+}
 
 // shared-memory floats of the per-trajectory tables of a block (narrow layers): c [warp][H][CS], keys [warp][HP][32]
 template <int H, int S>
@@ -655,14 +665,27 @@ __host__ __device__ constexpr size_t table_floats() {
 // room for them next to a second resident block
 template <int H> __host__ __device__ constexpr bool fwd_stages_z() { return H <= 256; }
 
+// fused decoder heads: floats per thread of the state ring's region (also holds the thread's staged z row before the
+// time loop starts), and the floats of the time grid staged per block (grids above kHeadGridMax stay in global memory)
+constexpr int kHeadGridMax = 1024;
+template <int H, int S> __host__ __device__ constexpr int head_ring_floats(int L, bool lat) {
+  const int LQ = (L + 3) / 4 * 4;
+  return (lat && fwd_stages_z<H>() && LQ > kHeadRing * S) ? LQ : kHeadRing * S;
+}
+__host__ __device__ constexpr int head_grid_floats(int T) { return T <= kHeadGridMax ? (T + 3) / 4 * 4 : 0; }
+
 template <int H, int S>
-__host__ __device__ constexpr size_t fwd_smem_bytes(int L, bool lat, bool rows_in_time) {
+__host__ __device__ constexpr size_t fwd_smem_bytes(int L, bool lat, bool rows_in_time, bool heads = false, int T = 0) {
   using SH = Shape<H, S>;
   size_t n = SH::WT;
   if (!SH::BIG) n += table_floats<H, S>();
   if (lat) n += LatSmem<H, S>::floats(L);                                  // staged nets
-  if (lat && fwd_stages_z<H>()) n += (size_t)kThreads * ((L + 3) / 4 * 4);   // + the warps' z rows
-  if (rows_in_time) n += (size_t)kThreads * kStageT * S;
+  if (lat && fwd_stages_z<H>() && !heads) n += (size_t)kThreads * ((L + 3) / 4 * 4);   // + the warps' z rows
+  if (rows_in_time && !heads) n += (size_t)kThreads * kStageT * S;                    // staged output rows
+  if (heads) {
+    // state ring (its region doubles as the warp's z rows during the prologue) + head weights + row tables + time grid
+    n += (size_t)kThreads * head_ring_floats<H, S>(L, lat) + kMaxHeadW + kHeadTab + head_grid_floats(T);
+  }
   return n * sizeof(float);
 }
 
@@ -738,27 +761,70 @@ __device__ __forceinline__ void prologue(const LatSmem<H, S>& ls, const LatentSr
   }
 }
 
-template <int H, int S, int METHOD>
-__global__ void __launch_bounds__(kThreads, (Shape<H, S>::BIG || S > 5) ? 3 : SLODE_FX_FWD_MINB)
+// HEADS: the decoder heads are applied to the states while the thread still holds them and written in the reference's
+// (B, obs_dim, T) layout (hd.mu, (NQ,B,O,T)); sol is then optional (null: never written).  A mu row runs along TIME, a
+// thread produces one time point per step, and a row's pitch (T floats) puts its 32-byte sectors at a phase that
+// depends on (trajectory, head, output).  Writing less than a whole sector per request is what must not happen: the
+// first version stored 16 bytes per row every four steps and the L2 filled every sector from DRAM for the partial
+// write and wrote most of them back twice (ncu: 3.5 GB read + 6.7 GB written for 3.8 GB of output, 6.5 ms).  So the
+// thread keeps its last kHeadRing = 8 states in a shared-memory ring (warp-major, conflict-free) and, at the step
+// where a row's current sector becomes complete, computes the sector's eight outputs and stores them with ONE 32-byte
+// store; only a row's first and last sectors can be partial.  The dot products run in the order of heads_fwd_kernel
+// (slode_heads.cu), so fused and two-kernel results are bit-equal.
+template <int H, int S, int METHOD, bool HEADS = false>
+__global__ void __launch_bounds__(kThreads, (Shape<H, S>::BIG || S > 5) ? 3 : (HEADS ? 4 : SLODE_FX_FWD_MINB))
 fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float* __restrict__ cin,
                  const float* __restrict__ y0, float* __restrict__ sol, int64_t st, int64_t sb, PackSrc w,
-                 int w1t_stride, LatentSrc lat, unsigned char* __restrict__ ws) {
+                 int w1t_stride, LatentSrc lat, unsigned char* __restrict__ ws, HeadsSrc hd) {
   using SH = Shape<H, S>;
   constexpr int NP = SH::NP;
   extern __shared__ __align__(16) float fx_smem[];
   float* const wt = fx_smem;
   float* const tables = wt + SH::WT;
   float* lat_base = tables + (SH::BIG ? 0 : table_floats<H, S>());
-  const bool rows_in_time = (st == S);
+  const bool rows_in_time = !HEADS && (st == S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   LatSmem<H, S> ls{};
   stage_weights<H, S>(wt, w.w1t, w1t_stride, w.Wg, w.bg, w.Wd, w.bd);
   if (lat.z) ls.stage(lat_base, lat);
   const int LQ = (lat.L + 3) / 4 * 4;
-  float* const zT = lat_base + LatSmem<H, S>::floats(lat.L) + (size_t)warp * 32 * LQ;   // this warp's z rows (lat.z only)
+  // this warp's z rows (lat.z only); HEADS: inside the warp's state-ring region, which is idle until the first output
+  const int ring_w = 32 * head_ring_floats<H, S>(lat.L, lat.z != nullptr);   // floats of a warp's ring region
+  float* const zT = lat_base + LatSmem<H, S>::floats(lat.L) + (size_t)warp * (HEADS ? ring_w : 32 * LQ);
   constexpr bool kZS = fwd_stages_z<H>();
-  float* const ostage = lat_base + (lat.z ? LatSmem<H, S>::floats(lat.L) + (kZS ? (size_t)kThreads * LQ : 0) : 0) +
-                        (size_t)tid * kStageT * S;
+  float* const ostage0 =
+      lat_base + (lat.z ? LatSmem<H, S>::floats(lat.L) + ((kZS && !HEADS) ? (size_t)kThreads * LQ : 0) : 0);
+  float* const ostage = ostage0 + (size_t)tid * kStageT * S;
+  // HEADS: ring[(slot * S + s) * 32] of this lane, then the stacked head weights (NQ,O,S), then two small tables:
+  //   roff[r]  float offset of row r = (q,o) from row (0,0) of the same trajectory: (q B O + o) P, P = hd.pitch >= T the
+  //            row pitch (with P % 8 == 0 every row of the launch has the same sector phase: all lanes flush all
+  //            their rows at the same steps, k % 8 == 7, and nothing diverges)
+  //   due[c]   bit r set: row r completes a 32-byte sector at a step with ((e_b + k) & 7) == c
+  float* const ring = ostage0 + (size_t)warp * ring_w + lane;
+  float* const hw = ostage0 + (size_t)kWarps * ring_w;
+  int64_t* const roff = reinterpret_cast<int64_t*>(hw + kMaxHeadW);   // 8-byte aligned: every region is a multiple of 4 floats
+  uint32_t* const due = reinterpret_cast<uint32_t*>(roff + kHeadRows);
+  // the time grid: the scattered sector stores queue in front of every global load (a grid element fetched one step
+  // ahead cost 10 % of the fused kernel's stall samples), so the loop reads it from shared memory
+  float* const sgrid = reinterpret_cast<float*>(due + 8);
+  const float* const tg = (HEADS && T <= kHeadGridMax) ? sgrid : tgrid;
+  if (HEADS && T <= kHeadGridMax) {
+    for (int i = tid; i < T; i += kThreads) sgrid[i] = __ldg(tgrid + i);
+  }
+  const int nqo = HEADS ? hd.NQ * hd.O : 0;
+  if (HEADS) {
+    for (int i = tid; i < nqo * S; i += kThreads) hw[i] = hd.W[i];
+    if (tid < nqo) roff[tid] = ((int64_t)(tid / hd.O) * B * hd.O + (tid % hd.O)) * hd.pitch;
+    if (tid >= 32 && tid < 40) {
+      const int c = tid - 32;
+      uint32_t m = 0;
+      for (int r = 0; r < nqo; ++r) {
+        const int64_t e = ((int64_t)(r / hd.O) * B * hd.O + (r % hd.O)) * hd.pitch;
+        if (((c + (int)(e & 7)) & 7) == 7) m |= 1u << r;
+      }
+      due[c] = m;
+    }
+  }
   __syncthreads();
   const Tab tab = make_tab<H, S>(tables, ws, warp, lane);
   const float dir = (T < 2 || __ldg(tgrid + T - 1) >= __ldg(tgrid)) ? 1.0f : -1.0f;
@@ -778,8 +844,67 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     }
     float* out = sol + b * sb;
     float* const row = out;
+    int hd_eb = 0;
+    if (HEADS)
+      hd_eb = (int)((((b & 7) * (hd.O & 7) * (hd.pitch & 7)) + ((reinterpret_cast<uintptr_t>(hd.mu) >> 2) & 7)) & 7);
 
     auto put = [&](int k, const V<NP>& xv) {
+      if (HEADS) {
+        if (sol) vstore<S>(out, ok, xv);
+        const int slot = k & (kHeadRing - 1);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          float lo, hi;
+          unpk(xv.v[p], lo, hi);
+          ring[(slot * S + 2 * p) * 32] = lo;
+          if (2 * p + 1 < S) ring[(slot * S + 2 * p + 1) * 32] = hi;
+        }
+        const bool last = (k == T - 1);
+        const int base = hd_eb + k;   // sector phase of time k in row (0,0) of this trajectory
+        uint32_t todo = last ? (nqo >= 32 ? 0xffffffffu : (1u << nqo) - 1u) : due[base & 7];
+        if (!ok) todo = 0;
+        if (todo) {
+          // the last eight states, oldest first, as four pairs of consecutive times: state at time k - 7 + j is
+          // half j & 1 of xs[j >> 1] (garbage before time 0: never stored)
+          V<S> xs[kHeadRing / 2];   // V<S>: S register pairs
+#pragma unroll
+          for (int m = 0; m < kHeadRing / 2; ++m) {
+            const int sa = (k + 1 + 2 * m) & (kHeadRing - 1), sb2 = (k + 2 + 2 * m) & (kHeadRing - 1);
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) xs[m].v[s2] = pk(ring[(sa * S + s2) * 32], ring[(sb2 * S + s2) * 32]);
+          }
+          float* const mrow = hd.mu + b * (hd.O * hd.pitch) + k;   // time k of row (0,0)
+          do {   // this lane's due rows; lanes with fewer of them idle in the last trips
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t ro = roff[r];
+            const int ph = (base + (int)(ro & 7)) & 7;   // position of time k inside its sector
+            const float* wr = hw + r * S;
+            f2 acc[kHeadRing / 2];
+#pragma unroll
+            for (int m = 0; m < kHeadRing / 2; ++m) acc[m] = bc(0.0f);
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) {   // same order as heads_fwd_kernel: acc = fma(w_s, x_s, acc), s ascending
+              const f2 wv = bc(wr[s2]);
+#pragma unroll
+              for (int m = 0; m < kHeadRing / 2; ++m) acc[m] = fma2(wv, xs[m].v[s2], acc[m]);
+            }
+            float a[kHeadRing];
+#pragma unroll
+            for (int m = 0; m < kHeadRing / 2; ++m) unpk(acc[m], a[2 * m], a[2 * m + 1]);
+            float* const dk = mrow + ro;   // &mu[q][b][o][k]
+            if (ph == 7 && k >= 7) {
+              st_sector(dk - 7, a);
+            } else {
+              const int n = min(ph, k) + 1;   // times k - n + 1 .. k are pending
+#pragma unroll
+              for (int j = 0; j < kHeadRing; ++j)
+                if (j >= kHeadRing - n) dk[j - (kHeadRing - 1)] = a[j];
+            }
+          } while (todo);
+        }
+        return;
+      }
       if (!rows_in_time) {
         vstore<S>(out, ok, xv);
         return;
@@ -807,8 +932,9 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
       }
     };
 
+    if (HEADS) __syncwarp();   // every lane of the warp has read its z row: the region becomes the state ring
     put(0, x);
-    float t0 = __ldg(tgrid);
+    float t0 = HEADS ? tg[0] : __ldg(tgrid);
     Pl<H, S> pl;
     uint32_t first[SH::NWR];
     if (T > 1) pl.init(wt, tab, t0, dir, first);
@@ -818,11 +944,11 @@ fixed_fwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
       pl.template eval<true>(t0, G, D);
       k1 = rhs<NP>(G, D, x);
     }
-    float t_ahead = T > 1 ? __ldg(tgrid + 1) : t0;  // the grid is read one step ahead of its use
+    float t_ahead = T > 1 ? (HEADS ? tg[1] : __ldg(tgrid + 1)) : t0;  // the grid is read one step ahead of its use
 #pragma unroll 1
     for (int i = 0; i + 1 < T; ++i) {
       const float t1 = t_ahead;
-      if (i + 2 < T) t_ahead = ld_early(tgrid + i + 2);
+      if (i + 2 < T) t_ahead = HEADS ? tg[i + 2] : ld_early(tgrid + i + 2);
       const float dt = t1 - t0;
       if (METHOD == SLODE_METHOD_EULER) {
         V<NP> G, D;
@@ -1551,10 +1677,10 @@ int plan_grid(K kern, size_t smem, int64_t B, int sms, int* grid) {
   return SLODE_OK;
 }
 
-template <int H, int S, int METHOD>
+template <int H, int S, int METHOD, bool HEADS>
 int plan_fwd(const FwdArgs& a, Plan* p) {
-  p->smem = fwd_smem_bytes<H, S>(a.lat.L, a.lat.z != nullptr, a.st == S);
-  const int rc = plan_grid(fixed_fwd_kernel<H, S, METHOD>, p->smem, a.B, a.sms, &p->grid);
+  p->smem = fwd_smem_bytes<H, S>(a.lat.L, a.lat.z != nullptr, a.st == S, HEADS, a.T);
+  const int rc = plan_grid(fixed_fwd_kernel<H, S, METHOD, HEADS>, p->smem, a.B, a.sms, &p->grid);
   if (rc) return rc;
   p->ws_bytes = big_tab_bytes<H, S>() * (size_t)p->grid * kThreads;
   return SLODE_OK;
@@ -1569,10 +1695,10 @@ int plan_bwd(const BwdArgs& a, Plan* p) {
   return SLODE_OK;
 }
 
-template <int H, int S, int METHOD>
+template <int H, int S, int METHOD, bool HEADS>
 int launch_fwd(const FwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {
   Plan p;
-  const int rc = plan_fwd<H, S, METHOD>(a, &p);
+  const int rc = plan_fwd<H, S, METHOD, HEADS>(a, &p);
   if (rc) return rc;
   *ws_need = p.ws_bytes;
   if (plan_only) return SLODE_OK;
@@ -1585,8 +1711,8 @@ int launch_fwd(const FwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_onl
     set_error("fixed-grid forward: workspace must be 16-byte aligned");
     return SLODE_EINVAL;
   }
-  fixed_fwd_kernel<H, S, METHOD><<<p.grid, kThreads, p.smem, a.stream>>>(
-      a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb, w, w1t_stride, a.lat, static_cast<unsigned char*>(a.ws));
+  fixed_fwd_kernel<H, S, METHOD, HEADS><<<p.grid, kThreads, p.smem, a.stream>>>(
+      a.B, a.T, a.t, a.c, a.y0, a.sol, a.st, a.sb, w, w1t_stride, a.lat, static_cast<unsigned char*>(a.ws), a.heads);
   SLODE_CUDA_TRY(cudaGetLastError());
   return SLODE_OK;
 }
@@ -1616,10 +1742,19 @@ int launch_bwd(const BwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_onl
 
 template <int H, int S>
 int fwd_shape(const FwdArgs& a, const PackSrc& w, int w1t_stride, bool plan_only, size_t* ws_need) {
+  if (a.heads.W) {
+    switch (a.method) {
+      case SLODE_METHOD_EULER: return launch_fwd<H, S, SLODE_METHOD_EULER, true>(a, w, w1t_stride, plan_only, ws_need);
+      case SLODE_METHOD_MIDPOINT:
+        return launch_fwd<H, S, SLODE_METHOD_MIDPOINT, true>(a, w, w1t_stride, plan_only, ws_need);
+      case SLODE_METHOD_RK4: return launch_fwd<H, S, SLODE_METHOD_RK4, true>(a, w, w1t_stride, plan_only, ws_need);
+    }
+  }
   switch (a.method) {
-    case SLODE_METHOD_EULER: return launch_fwd<H, S, SLODE_METHOD_EULER>(a, w, w1t_stride, plan_only, ws_need);
-    case SLODE_METHOD_MIDPOINT: return launch_fwd<H, S, SLODE_METHOD_MIDPOINT>(a, w, w1t_stride, plan_only, ws_need);
-    case SLODE_METHOD_RK4: return launch_fwd<H, S, SLODE_METHOD_RK4>(a, w, w1t_stride, plan_only, ws_need);
+    case SLODE_METHOD_EULER: return launch_fwd<H, S, SLODE_METHOD_EULER, false>(a, w, w1t_stride, plan_only, ws_need);
+    case SLODE_METHOD_MIDPOINT:
+      return launch_fwd<H, S, SLODE_METHOD_MIDPOINT, false>(a, w, w1t_stride, plan_only, ws_need);
+    case SLODE_METHOD_RK4: return launch_fwd<H, S, SLODE_METHOD_RK4, false>(a, w, w1t_stride, plan_only, ws_need);
   }
   set_error("fixed-grid forward: unknown method %d", a.method);
   return SLODE_EINVAL;

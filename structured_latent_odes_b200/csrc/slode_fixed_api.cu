@@ -230,6 +230,44 @@ extern "C" int slode_latent_fixed_fwd(int method, int64_t B, int T, int L, int H
   return run_fwd("slode_latent_fixed_fwd", H, S, a, w, L + 1);
 }
 
+extern "C" int slode_latent_fixed_heads_fwd(int method, int64_t B, int T, int L, int H, int S, const float* t,
+                                            const float* z, const float* W1, const float* b1, const float* Wg,
+                                            const float* bg, const float* Wd, const float* bd, const float* Wa,
+                                            const float* ba, const float* Wb, const float* bb, const float* y0,
+                                            int O, int NQ, const float* head_W, float* mu, int64_t mu_row_pitch,
+                                            float* sol,
+                                            int64_t sol_stride_t, int64_t sol_stride_b, void* workspace,
+                                            int64_t workspace_bytes, void* stream_) {
+  int rc = check_sizes("slode_latent_fixed_heads_fwd", method, SLODE_BWD_DISCRETE, B, T, H, S);
+  if (rc) return rc;
+  if (B > 0) {
+    rc = check_latent("slode_latent_fixed_heads_fwd", L, z, W1, b1, Wa, ba, Wb, bb, y0);
+    if (rc) return rc;
+  }
+  if (O < 1 || O > 8 || NQ < 1 || NQ > 3 || NQ * O * S > kMaxHeadW) {
+    set_error("slode_latent_fixed_heads_fwd: obs_dim=%d (1..8), heads=%d (1..3) out of range", O, NQ);
+    return SLODE_EINVAL;
+  }
+  if (!t || !Wg || !bg || !Wd || !bd || !head_W || (B > 0 && !mu) || workspace_bytes < 0) {
+    set_error("slode_latent_fixed_heads_fwd: null pointer");
+    return SLODE_EINVAL;
+  }
+  if (mu_row_pitch < T || (reinterpret_cast<uintptr_t>(mu) & 3)) {
+    set_error("slode_latent_fixed_heads_fwd: mu_row_pitch=%lld must be >= T=%d and mu 4-byte aligned",
+              (long long)mu_row_pitch, T);
+    return SLODE_EINVAL;
+  }
+  FwdArgs a{};
+  a.method = method; a.B = B; a.T = T; a.t = t; a.y0 = y0; a.sol = sol;
+  // without sol the strides only steer the staging layout: use the (T,B,S) ones
+  a.st = sol ? sol_stride_t : B * (int64_t)S; a.sb = sol ? sol_stride_b : S;
+  a.stream = (cudaStream_t)stream_; a.lat = LatentSrc{z, L, W1, b1, Wa, ba, Wb, bb};
+  a.ws = workspace; a.ws_bytes = (size_t)workspace_bytes;
+  a.heads = HeadsSrc{head_W, mu, NQ, O, mu_row_pitch};
+  const PackSrc w{W1, Wg, bg, Wd, bd};
+  return run_fwd("slode_latent_fixed_heads_fwd", H, S, a, w, L + 1);
+}
+
 extern "C" int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H, int S, const float* t,
                                       const float* z, const float* W1, const float* b1, const float* Wg,
                                       const float* bg, const float* Wd, const float* bd, const float* Wa,

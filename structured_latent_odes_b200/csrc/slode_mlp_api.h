@@ -22,6 +22,17 @@ struct LatentSrc {
   const float *Wa, *ba, *Wb, *bb;  // latent_to_ode_net Linear(L,H) / Linear(H,S); null: y0 is given
 };
 
+// Optional fused decoder-head epilogue of the forward solve: with W given the kernel
+// writes mu_q = Linear_q(solution).permute(0,2,1) (models/decoders.py:45-47, :86) for all heads straight from the
+// states it holds in registers; sol itself then becomes optional (null: the trajectories never reach HBM).
+struct HeadsSrc {
+  const float* W;   // (NQ,O,S) stacked bias-free Linear(S -> O) weights, or null: no fused heads
+  float* mu;        // (NQ,B,O,pitch): element (q,b,o,t) at ((q B + b) O + o) pitch + t
+  int NQ, O;
+  int64_t pitch;    // row pitch in floats, >= T (a multiple of 8 keeps every row's 32-byte sectors in phase)
+};
+constexpr int kMaxHeadW = 3 * 8 * 8;  // NQ * O * S floats staged per block
+
 struct FwdArgs {
   int method;
   int64_t B;
@@ -34,6 +45,7 @@ struct FwdArgs {
   LatentSrc lat;
   void* ws;          // caller-provided scratch (slode_fixed_workspace_bytes), may be null when 0 bytes are needed
   size_t ws_bytes;
+  HeadsSrc heads;    // fused decoder heads (W null: off); with them sol may be null
 };
 
 struct BwdArgs {

@@ -9,7 +9,9 @@ keys and return tuples as the reference:
 
 The latent solve runs in the fused solver kernels (``OdeModel.solve_ODE``), stored (B,T,S)-contiguous, and all
 heads are produced by ONE pass over the trajectories in their final (B,O,T) layout (``slode_heads_fwd`` / ``_bwd``)
-instead of one tiny-K matmul + permute per head.
+instead of one tiny-K matmul + permute per head.  ``predict`` (no gradients: reconstruction, ``multiple_samples``)
+goes one step further: the heads run inside the solver kernel's epilogue (``slode_latent_fixed_heads_fwd``) and the
+trajectories are written to HBM only on request.
 """
 from __future__ import annotations
 
@@ -97,6 +99,19 @@ class Decoder(nn.Module):
         std = torch.ones_like(mu_50) * nn.functional.softplus(self.constant_std)
         return solution, mu_75, mu_50, mu_25, std
 
+    @torch.no_grad()
+    def predict(self, z, want_solution=False):
+        """``forward`` for callers that do not differentiate (``recon`` / posterior sampling): the heads are fused
+        into the solver kernel's epilogue, the same tuple comes back with ``solution`` = ``None`` unless asked for --
+        the (B,T,S) trajectories are then never written to HBM.  Bit-equal to ``forward``."""
+        mu, solution = self.ode_model.solve_ODE_heads(
+            z, (self.output_q50[0].weight, self.output_q75[0].weight, self.output_q25[0].weight), want_solution)
+        mu_50, mu_75, mu_25 = mu.unbind(0)
+        # the same values as forward's ``ones_like(mu) * softplus(constant_std)``, as a broadcast view: materialising
+        # (B,O,T) copies of an (O,T) table cost a third of the whole call at 2^20 trajectories
+        std = nn.functional.softplus(self.constant_std).expand(mu_50.shape)
+        return solution, mu_75, mu_50, mu_25, std
+
 
 class GaussianDecoder(nn.Module):
     def __init__(self, config, times, latent_dim, device):
@@ -115,6 +130,14 @@ class GaussianDecoder(nn.Module):
         solution = self.ode_model.solve_ODE(z=z)
         (mean,) = decoder_heads(solution, (self.output_mean[0].weight,))
         std = torch.ones_like(mean) * nn.functional.softplus(self.constant_std)
+        return solution, mean, std
+
+    @torch.no_grad()
+    def predict(self, z, want_solution=False):
+        """``forward`` under ``no_grad`` with the mean head fused into the solver kernel (see ``Decoder.predict``)."""
+        mu, solution = self.ode_model.solve_ODE_heads(z, (self.output_mean[0].weight,), want_solution)
+        mean = mu[0]
+        std = nn.functional.softplus(self.constant_std).expand(mean.shape)
         return solution, mean, std
 
 
@@ -159,7 +182,9 @@ def multiple_samples(decoder, z_loc, z_scale, num_samples, generator=None):
     B, L = z_loc.shape
     eps = torch.randn((num_samples, B, L), device=z_loc.device, dtype=z_loc.dtype, generator=generator)
     z = z_loc[None] + z_scale[None] * eps
-    out = decoder(z.reshape(num_samples * B, L))
+    # our decoders: heads fused into the solve, no (B,T,S) round trip through HBM; any other module: its forward
+    run = decoder.predict if hasattr(decoder, "predict") else decoder
+    out = run(z.reshape(num_samples * B, L))
     names = ("mu_75", "mu_50", "mu_25") if len(out) == 5 else ("mu_50",)
     res = {"z": z}
     for name, mu in zip(names, out[1:1 + len(names)]):

@@ -26,7 +26,7 @@ from torch import nn
 from . import _cabi
 
 __all__ = ["odeint", "odeint_adjoint", "install_as_torchdiffeq", "is_blackbox_func", "KernelTimer", "solve_latent",
-           "solve_fixed_from_c"]
+           "solve_latent_heads", "solve_fixed_from_c"]
 
 FIXED_METHODS = ("euler", "midpoint", "rk4")
 
@@ -338,9 +338,8 @@ class _LatentFixedSolve(torch.autograd.Function):
         return (grad_z, grad_y0, gW1, gb1, gWg, gbg, gWd, gbd, *gx0, None, None, None, None)
 
 
-def solve_latent(z, dynamics, x0_net, t, method, adjoint, layout="tbs"):
-    """Whole ``OdeModel.solve_ODE`` body in two kernels: returns ``(T,B,S)``.  ``x0_net`` is the reference's
-    ``latent_to_ode_net`` Sequential(Linear, ReLU, Linear, Sigmoid)."""
+def _latent_checked(z, dynamics, x0_net, t, method, who):
+    """Argument checks shared by the fused latent entry points; returns (t on the device, the ten weight tensors)."""
     if method not in FIXED_METHODS:
         raise NotImplementedError(method)
     if not z.is_cuda:
@@ -358,15 +357,65 @@ def solve_latent(z, dynamics, x0_net, t, method, adjoint, layout="tbs"):
         raise ValueError(f"z {tuple(z.shape)} does not match dynamics_hidden.in_features={hid.in_features}")
     if not z.is_floating_point():
         raise TypeError(f"z must be floating point, got {z.dtype}")
-    _check_weights(z.device, "solve_ODE", ("dynamics_hidden.weight", hid.weight), ("dynamics_hidden.bias", hid.bias),
+    _check_weights(z.device, who, ("dynamics_hidden.weight", hid.weight), ("dynamics_hidden.bias", hid.bias),
                    ("dyanamics_growth.weight", gro.weight), ("dyanamics_growth.bias", gro.bias),
                    ("dyanmics_degradation.weight", deg.weight), ("dyanmics_degradation.bias", deg.bias),
                    ("latent_to_ode_net.0.weight", la.weight), ("latent_to_ode_net.0.bias", la.bias),
                    ("latent_to_ode_net.2.weight", lb.weight), ("latent_to_ode_net.2.bias", lb.bias))
     t = t.detach().to(device=z.device, dtype=torch.float32).contiguous()
+    return t, (hid.weight, hid.bias, gro.weight, gro.bias, deg.weight, deg.bias, la.weight, la.bias, lb.weight,
+               lb.bias)
+
+
+def solve_latent(z, dynamics, x0_net, t, method, adjoint, layout="tbs"):
+    """Whole ``OdeModel.solve_ODE`` body in two kernels: returns ``(T,B,S)``.  ``x0_net`` is the reference's
+    ``latent_to_ode_net`` Sequential(Linear, ReLU, Linear, Sigmoid)."""
+    t, weights = _latent_checked(z, dynamics, x0_net, t, method, "solve_ODE")
     mode = _cabi.BWD_TDE_ADJOINT if adjoint else _cabi.BWD_DISCRETE
-    return _LatentFixedSolve.apply(z, None, hid.weight, hid.bias, gro.weight, gro.bias, deg.weight, deg.bias,
-                                   la.weight, la.bias, lb.weight, lb.bias, t, _cabi.METHODS[method], mode, layout)
+    return _LatentFixedSolve.apply(z, None, *weights, t, _cabi.METHODS[method], mode, layout)
+
+
+@torch.no_grad()
+def solve_latent_heads(z, dynamics, x0_net, t, method, head_weights, want_solution=False, layout="tbs",
+                       contiguous=False):
+    """``OdeModel.solve_ODE`` + the decoder heads (``models/decoders.py:43-47``, ``:85-86``) in ONE kernel, for callers
+    that do not differentiate (reconstruction, posterior sampling): returns ``(mu, sol)`` with ``mu`` the
+    ``(NQ,B,O,T)`` head outputs -- ``mu[q]`` is ``Linear_q(solution).permute(0,2,1)`` -- and ``sol`` the ``(T,B,S)``
+    trajectories, or ``None`` unless ``want_solution`` (they are then never written to HBM).  Bit-equal to
+    ``solve_latent`` followed by ``decoders.decoder_heads``.
+
+    ``mu`` is a ``[..., :T]`` view of a buffer whose rows are padded to a multiple of eight floats (32-byte sectors:
+    every row then has the same sector phase and the kernel's stores never diverge); ``contiguous=True`` asks for
+    the reference's exactly contiguous ``(B,O,T)`` rows instead (same values, the slower store schedule when
+    ``T % 8 != 0``)."""
+    t, weights = _latent_checked(z, dynamics, x0_net, t, method, "solve_latent_heads")
+    W = torch.stack([w.detach() for w in head_weights], dim=0)
+    _check_weights(z.device, "solve_latent_heads", ("decoder head weights", W))
+    W = W.contiguous()
+    B, L = z.shape
+    H, S = weights[0].shape[0], weights[2].shape[0]
+    NQ, O, SW = W.shape
+    if SW != S:
+        raise ValueError(f"head weights {tuple(W.shape)} do not match ode_state_dim={S}")
+    T = t.numel()
+    method_id = _cabi.METHODS[method]
+    zc = z.detach().to(torch.float32).contiguous()
+    w = [x.detach().contiguous() for x in weights]
+    pitch = T if contiguous else (T + 7) // 8 * 8
+    mu = torch.empty((NQ, B, O, pitch), device=z.device, dtype=torch.float32)
+    sol = None
+    if want_solution:
+        # always (T,B,S)-contiguous here: the fused kernel writes a state row per step, coalesced across the
+        # trajectories; ``layout`` is a storage choice of the other entry points, the values are the same
+        sol = torch.empty((T, B, S), device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device), _timed("fwd"):
+        ws = _workspace(z.device, False, method_id, _cabi.BWD_DISCRETE, B, T, L, H, S, 2, False)
+        rc = _cabi.lib().slode_latent_fixed_heads_fwd(
+            method_id, B, T, L, H, S, _ptr(t), _ptr(zc), *[_ptr(x) for x in w], None, O, NQ, _ptr(W), _ptr(mu),
+            pitch, _ptr(sol), sol.stride(0) if sol is not None else 0, sol.stride(1) if sol is not None else 0,
+            _ptr(ws), ws.numel() if ws is not None else 0, torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "slode_latent_fixed_heads_fwd")
+    return mu[..., :T], sol
 
 
 class SolverStats:

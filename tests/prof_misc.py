@@ -1,6 +1,6 @@
 """One launch each of the kernels beside the fixed-grid pair (for ncu): CVS mechanistic fwd/bwd at 2^20 x 100, the
 decoder heads fwd/bwd at 2^20 x 100, the dopri5 forward and its odeint_adjoint backward at the challenge shape.
-python tests/prof_misc.py [cvs|heads|dopri5]"""
+python tests/prof_misc.py [cvs|heads|dopri5|predict]   (predict: Decoder.predict, heads fused into the solver kernel, 2^20 x 100 rk4)"""
 import os
 import sys
 
@@ -26,6 +26,13 @@ elif what == "heads":
     W = [torch.randn(O, S, device=dev, requires_grad=True) for _ in range(3)]
     mu = slode.decoder_heads(sol, W)
     (mu[0].sum() + mu[1].sum() + mu[2].sum()).backward()
+elif what == "predict":
+    import types
+    B, T = 1 << 20, 100
+    cfg = types.SimpleNamespace(obs_dim=3, ode_state_dim=5, ode_hidden_dim=25, adjoint_solver=False, solver="rk4",
+                                constant_std=1e-2)
+    dec = slode.Decoder(cfg, torch.arange(T, dtype=torch.float32, device=dev), 15, dev).to(dev)
+    dec.predict(torch.randn(B, 15, device=dev))
 else:
     import slode_testutil as U
     o = U.make_oracle("chal", "dopri5", True)

@@ -140,3 +140,59 @@ def test_heads_vector_and_scalar_paths_against_torch(S, O, NQ, T, B):
     refs = torch.autograd.grad(sum((ref[q] * G[q]).sum() for q in used), [x] + [W[q] for q in used])
     for a, b in zip(list(mus) + list(outs), list(ref) + list(refs)):
         assert U.rel_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("shape,O,method,B", [("cvs", 3, "midpoint", 77), ("cvs", 3, "rk4", 300), ("chal", 4, "euler", 1),
+                                              ("chal", 4, "rk4", 129), ("proc", 4, "midpoint", 45),
+                                              ("h64", 3, "rk4", 40)])
+@pytest.mark.parametrize("want_solution", [False, True])
+def test_predict_fuses_the_heads_into_the_solve_bit_equal(shape, O, method, B, want_solution):
+    """f2: ``Decoder.predict`` (heads in the solver kernel's epilogue, trajectories not written unless asked for) gives
+    exactly the tuple ``forward`` gives with two kernels; T = 86 / 142 / 100 cover full and partial 16-byte row groups
+    and unaligned rows."""
+    import structured_latent_odes_b200 as slode
+    L, H, S, times = U.SHAPES[shape]
+    torch.manual_seed(B)
+    dec = slode.Decoder(_cfg(shape, method, False, O), times.cuda(), L, "cuda").cuda()
+    z = torch.randn(B, L, device="cuda")
+    with torch.no_grad():
+        sol, q75, q50, q25, std = dec(z)
+    fsol, f75, f50, f25, fstd = dec.predict(z, want_solution=want_solution)
+    assert torch.equal(f75, q75) and torch.equal(f50, q50) and torch.equal(f25, q25) and torch.equal(fstd, std)
+    if want_solution:
+        assert fsol.shape == sol.shape and torch.equal(fsol, sol)
+    else:
+        assert fsol is None
+    # predict hands out views of rows padded to whole 32-byte sectors; the reference's contiguous rows (every row at
+    # its own sector phase: the lanes of a warp store at different steps) give the same numbers
+    W3 = (dec.output_q50[0].weight, dec.output_q75[0].weight, dec.output_q25[0].weight)
+    mu_c, _ = dec.ode_model.solve_ODE_heads(z, W3, contiguous=True)
+    assert mu_c.is_contiguous() and torch.equal(mu_c[0], q50) and torch.equal(mu_c[1], q75) and torch.equal(mu_c[2], q25)
+    assert f50.stride(-2) % 8 == 0 and f50.stride(-1) == 1
+    # and against the oracle heads on the oracle solve
+    o_ode = U.make_oracle(shape, method, False)
+    o_ode.load_state_dict({k[len("ode_model."):]: v.cpu() for k, v in dec.state_dict().items()
+                           if k.startswith("ode_model.")})
+    with torch.no_grad():
+        want = (o_ode.solve_ODE(z.cpu()) @ dec.output_q50[0].weight.cpu().t()).permute(0, 2, 1)
+    assert U.rel_err(f50, want) < 1e-5
+
+
+def test_gaussian_predict_and_fused_heads_argument_checks():
+    import structured_latent_odes_b200 as slode
+    L, H, S, times = U.SHAPES["cvs"]
+    dec = slode.GaussianDecoder(_cfg("cvs", "rk4", True, 3), times.cuda(), L, "cuda").cuda()
+    z = torch.randn(50, L, device="cuda")
+    with torch.no_grad():
+        sol, mean, std = dec(z)
+    fsol, fmean, fstd = dec.predict(z)
+    assert fsol is None and torch.equal(fmean, mean) and torch.equal(fstd, std)
+    empty = dec.predict(z[:0], want_solution=True)
+    assert empty[1].shape == (0, 3, len(times)) and empty[0].shape == (0, len(times), S)
+    with pytest.raises(ValueError):
+        dec.ode_model.solve_ODE_heads(z, (torch.randn(3, S + 1, device="cuda"),))
+    with pytest.raises(RuntimeError):
+        dec.ode_model.solve_ODE_heads(z, (torch.randn(3, S),))          # head weights left on the CPU
+    dop = slode.GaussianDecoder(_cfg("cvs", "dopri5", False, 3), times.cuda(), L, "cuda").cuda()
+    with pytest.raises(NotImplementedError):
+        dop.predict(z)
