@@ -153,3 +153,53 @@ def test_no_write_outside_the_callers_buffers(shape, method, mode, B):
                                     view["sol"].data_ptr(), B * S, S, G.data_ptr(), B * S, S, view["gz"].data_ptr(), None,
                                     view["gp"].data_ptr(), view["ws_b"].data_ptr() + 4, ws_b, s)
     assert rc == 1 and b"aligned" in lib.slode_last_error()
+
+
+@pytest.mark.parametrize("shape,method,O,NQ,B,pad,shift", [("cvs", "rk4", 3, 3, 130, 0, 0), ("cvs", "midpoint", 3, 3, 33, 2, 0),
+                                                          ("chal", "euler", 4, 1, 65, 5, 3), ("proc", "midpoint", 4, 3, 40, 4, 1),
+                                                          ("small", "rk4", 8, 3, 1, 7, 5), ("h128", "rk4", 2, 2, 50, 1, 2)])
+def test_fused_heads_entry_raw_pointers_any_pitch_and_alignment(shape, method, O, NQ, B, pad, shift):
+    """slode_latent_fixed_heads_fwd on raw pointers: row pitch = T + pad (sector phases of every kind, incl. odd ones),
+    a mu base that is only 4-byte aligned (shift floats into the arena), sol skipped -- the values are those of
+    slode_latent_fixed_fwd + torch heads, the padding columns and the guard bands around mu stay untouched."""
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    Ld, H, S, times = U.SHAPES[shape]
+    T = len(times)
+    o = U.make_oracle(shape, method, False)
+    p = U.make_product(o)
+    d, n0, n2 = p.dynamics, p.latent_to_ode_net[0], p.latent_to_ode_net[2]
+    lib = _cabi.lib()
+    mid = _cabi.METHODS[method]
+    g = torch.Generator(device="cuda").manual_seed(B + pad)
+    z = torch.randn(B, Ld, device="cuda", generator=g)
+    W = torch.randn(NQ, O, S, device="cuda", generator=g)
+    with torch.no_grad():
+        sol = p.solve_ODE(z)                                           # (B,T,S)
+        want = torch.stack([(sol @ W[q].t()).permute(0, 2, 1) for q in range(NQ)], 0)   # (NQ,B,O,T)
+    P = T + pad
+    GUARD, CANARY = 256, 12345.678
+    n_mu = NQ * B * O * P
+    arena = torch.full((2 * GUARD + n_mu + 8,), CANARY, device="cuda")
+    mu = arena[GUARD + shift:GUARD + shift + n_mu]
+    ws_n = lib.slode_fixed_workspace_bytes(0, mid, 0, B, T, Ld, H, S, 2, 0)
+    ws = torch.empty(max(ws_n, 1), dtype=torch.uint8, device="cuda")
+    w = [x.detach().contiguous() for x in (d.dynamics_hidden.weight, d.dynamics_hidden.bias, d.dyanamics_growth.weight,
+                                           d.dyanamics_growth.bias, d.dyanmics_degradation.weight,
+                                           d.dyanmics_degradation.bias, n0.weight, n0.bias, n2.weight, n2.bias)]
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.slode_latent_fixed_heads_fwd(mid, B, T, Ld, H, S, p.times.data_ptr(), z.data_ptr(), *[x.data_ptr() for x in w],
+                                          None, O, NQ, W.data_ptr(), mu.data_ptr(), P, None, 0, 0,
+                                          ws.data_ptr() if ws_n else None, ws_n, s)
+    assert rc == 0, lib.slode_last_error()
+    torch.cuda.synchronize()
+    got = mu.view(NQ, B, O, P)
+    assert U.rel_err(got[..., :T], want) < 2e-6
+    if pad:
+        assert bool((got[..., T:] == CANARY).all()), "padding columns of the rows were written"
+    assert bool((arena[:GUARD + shift] == CANARY).all()) and bool((arena[GUARD + shift + n_mu:] == CANARY).all())
+    # argument checks: pitch below T, too many outputs
+    assert lib.slode_latent_fixed_heads_fwd(mid, B, T, Ld, H, S, p.times.data_ptr(), z.data_ptr(), *[x.data_ptr() for x in w],
+                                            None, O, NQ, W.data_ptr(), mu.data_ptr(), T - 1, None, 0, 0, None, 0, s) == 1
+    assert lib.slode_latent_fixed_heads_fwd(mid, B, T, Ld, H, S, p.times.data_ptr(), z.data_ptr(), *[x.data_ptr() for x in w],
+                                            None, 9, NQ, W.data_ptr(), mu.data_ptr(), P, None, 0, 0, None, 0, s) == 1
