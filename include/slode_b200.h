@@ -206,7 +206,9 @@ int slode_latent_fixed_bwd(int method, int mode, int64_t B, int T, int L, int H,
  * ONE step size for the whole batch (error ratio = RMS over all B*S elements), float64 controller time,
  * Hairer initial step, FSAL, 4th-order dense output at the requested times.  The whole adaptive loop runs in one
  * persistent cooperative kernel; the accepted-step sequence is deterministic.
- *   t            (T) strictly increasing output times (float32)
+ *   t            (T) strictly monotone output times (float32).  Decreasing times run torchdiffeq's reversed solve
+ *                (_ReverseFunc: s = -t, negated right-hand side) as the same scheme with negative steps; step_log
+ *                and replay_steps then hold the caller's t0 and dt < 0
  *   first_step   > 0 to skip the initial-step selection (torchdiffeq options["first_step"]), else <= 0
  *   max_attempts bound on attempted steps (torchdiffeq options["max_num_steps"])
  *   replay_steps optional (n_replay, 3) float64 in the step_log format: take exactly these step sizes and

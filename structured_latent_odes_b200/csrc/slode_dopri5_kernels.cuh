@@ -175,6 +175,11 @@ dopri5_fwd_kernel(Dopri5Args p) {
     c.d1 = c.h0 = 0.0f;
   }
   const double t_start = (double)__ldg(p.t);
+  // decreasing output times: torchdiffeq integrates s = -t with the negated right-hand side (_ReverseFunc), which is
+  // this same scheme with NEGATIVE steps (every product and sum below is sign-symmetric in round-to-nearest), so the
+  // controller works on dt = dirs * |dt|; the step log holds the caller's t0 and the signed dt
+  const double dirs = (p.T > 1 && (double)__ldg(p.t + p.T - 1) < t_start) ? -1.0 : 1.0;
+  const float dirf = (float)dirs;
   double sums[2] = {0.0, 0.0};   // the batch-wide sums the phase in hand consumes
   if (stepper && !p.restart) { sums[0] = p.ext_sums[0]; sums[1] = p.ext_sums[1]; }
 
@@ -272,7 +277,7 @@ dopri5_fwd_kernel(Dopri5Args p) {
         c.dt = p.n_replay > 0 ? p.replay[1] : 0.0;
         c.phase = kPhAttempt;
       } else if (p.first_step > 0.0) {
-        c.dt = p.first_step;
+        c.dt = dirs * p.first_step;
         c.phase = kPhAttempt;
       } else {
         c.phase = kPhProbe;
@@ -290,9 +295,9 @@ dopri5_fwd_kernel(Dopri5Args p) {
         Gate<H> ng[1];
         vload_rows<S>(p.ys, pi, y);
         vload_rows<S>(p.fs, pi, f);
-        const float te[1] = {__fadd_rn((float)t_start, h0)};
+        const float te[1] = {__fadd_rn((float)t_start, dirf * h0)};
         mlp_eval<H, S, 1, false, 1>(te, cload(pi), A, D, ng);
-        const Vec<S> y1 = vaxpy<S>(h0, f, y);
+        const Vec<S> y1 = vaxpy<S>(dirf * h0, f, y);
         const Vec<S> f1 = rhs<S>(A[0], D[0], y1);
         Vec<S> scale;
         const Vec<S> ay = vabs<S>(y);
@@ -310,7 +315,7 @@ dopri5_fwd_kernel(Dopri5Args p) {
       float h1;
       if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, __fmul_rn(h0, 1e-3f));
       else h1 = powf(__fdiv_rn(0.01f, fmaxf(d1, d2)), 1.0f / 5.0f);
-      c.dt = (double)fminf(__fmul_rn(100.0f, h0), h1);
+      c.dt = dirs * (double)fminf(__fmul_rn(100.0f, h0), h1);
       c.phase = kPhAttempt;
     } else if (c.phase == kPhDecide) {
       // ---- accept / reject the attempt in hand and choose the next step size (torchdiffeq _optimal_step_size) --
@@ -327,7 +332,7 @@ dopri5_fwd_kernel(Dopri5Args p) {
         c.pv_t0 = c.a_t0; c.pv_t1 = c.a_t0 + c.a_dt; c.pv_dt = c.a_dt;
         c.t_cur = c.pv_t1;
         c.emit_lo = c.out_idx;
-        while (c.out_idx < p.T && (double)__ldg(p.t + c.out_idx) <= c.pv_t1) ++c.out_idx;
+        while (c.out_idx < p.T && dirs * (double)__ldg(p.t + c.out_idx) <= dirs * c.pv_t1) ++c.out_idx;
         c.emit_hi = c.out_idx;
       } else {
         ++c.n_rej;
@@ -350,7 +355,7 @@ dopri5_fwd_kernel(Dopri5Args p) {
         else c.dt = p.replay[c.attempt * 3 + 1];
       }
       const double a_t0 = c.t_cur, a_dt = c.dt, a_t1 = a_t0 + a_dt;
-      if (!stop && !(a_t1 > a_t0)) { c.status = kDopriStatusUnderflow; stop = true; }
+      if (!stop && !(dirs * a_t1 > dirs * a_t0)) { c.status = kDopriStatusUnderflow; stop = true; }
       if (!stop && p.ckpt_y && c.n_acc >= p.ckpt_cap) { c.status = kDopriStatusCkptFull; stop = true; }
       if (stop) {
         if (c.prev_acc) {  // commit the last accepted step

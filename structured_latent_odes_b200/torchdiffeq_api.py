@@ -604,9 +604,10 @@ class _MlpDopri5Solve(torch.autograd.Function):
         acc = log[log[:, 2] != 0][:, :2].contiguous()
         tt = t.detach().double().cpu()
         emit, out_idx = [1], 1
+        sgn = -1.0 if tt.numel() > 1 and float(tt[-1]) < float(tt[0]) else 1.0   # decreasing t: steps have dt < 0
         for t0, dt in acc.tolist():
             t1 = t0 + dt
-            while out_idx < tt.numel() and float(tt[out_idx]) <= t1:
+            while out_idx < tt.numel() and sgn * float(tt[out_idx]) <= sgn * t1:
                 out_idx += 1
             emit.append(out_idx)
         ctx.save_for_backward(cc, *w, t, ckpt if ckpt is not None else sol.new_zeros(0))
@@ -729,12 +730,14 @@ def _solve_blackbox_dopri5(func, y0, t, rtol, atol, options, mode, layout):
     if gro.out_features != S or not _cabi.lib().slode_dopri5_supported(H, S):
         raise NotImplementedError(f"(ode_hidden_dim={H}, ode_state_dim={S}) has no compiled dopri5 kernel")
     _check_func_tensors(y0, z, hid, gro, deg)
-    if t.numel() > 1 and bool(t[0] > t[-1]):
-        raise NotImplementedError("dopri5 with decreasing output times (the reference always integrates forward)")
+    decreasing = t.numel() > 1 and bool(t[0] > t[-1])
     needs_grad = torch.is_grad_enabled() and (y0.requires_grad or z.requires_grad
                                               or any(p.requires_grad for p in func.parameters()))
     if needs_grad:
         if mode == _cabi.BWD_TDE_ADJOINT:
+            if decreasing:
+                raise NotImplementedError("odeint_adjoint + dopri5 with decreasing output times (the reference always "
+                                          "integrates forward); odeint (discrete gradient) takes them")
             bad = sorted(set(options or {}) & {"first_step", "shard_reducer", "global_batch"})
             if bad:
                 raise NotImplementedError(f"odeint_adjoint with dopri5: options {bad} (the reference passes none)")
