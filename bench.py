@@ -574,6 +574,7 @@ def main():
             line["epoch"] = epoch
         if not args.no_epoch:
             line["cvs_mechanistic"] = time_cvs_mechanistic(dev, B, hbm_peak)
+            line["posterior_predict"] = time_posterior_predict(dev, B, args.method)
         if not args.no_cpu_baseline and world == 1:
             reps = 3
             times, cores = time_cpu_reference(args.method, args.adjoint, args.ref_batch, reps)
@@ -621,6 +622,42 @@ def time_cvs_mechanistic(dev, B, hbm_peak):
             "fwd_hbm_frac": bytes_f / (best[0] * 1e-3) / 1e9 / hbm_peak, "bwd_hbm_frac": bytes_b / (best[1] * 1e-3) / 1e9 / hbm_peak,
             "what": f"CvsMechanistic RHS, {B} trajectories x {T} times, rk4, fp32, forward + discrete-adjoint backward "
                     "(gradients to y0, the treatments and the ten shared constants)"}
+
+
+def time_posterior_predict(dev, B, method):
+    """Reconstruction / posterior sampling at the headline size (SURVEY f2 + f3; the reference's recon loops,
+    training_challenge.py:174-195): Decoder.forward under no_grad (solver kernel + heads kernel, trajectories written
+    and read back) against Decoder.predict (three quantile heads fused into the solver kernel, trajectories never in
+    HBM).  Forward only; rank 0's GPU."""
+    import types
+    import structured_latent_odes_b200 as slode
+    cfg = types.SimpleNamespace(obs_dim=3, ode_state_dim=S, ode_hidden_dim=H, adjoint_solver=False, solver=method,
+                                constant_std=1e-2)
+    torch.manual_seed(12)
+    dec = slode.Decoder(cfg, torch.arange(0.0, T, 1.0, device=dev), L, dev).to(dev)
+    z = torch.randn(B, L, device=dev, generator=torch.Generator(device=dev).manual_seed(12))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def best_of(fn, n=5):
+        best = 1e30
+        for r in range(n + 2):
+            torch.cuda.synchronize()
+            ev[0].record()
+            out = fn()
+            ev[1].record()
+            torch.cuda.synchronize()
+            del out
+            if r >= 2:
+                best = min(best, ev[0].elapsed_time(ev[1]))
+        return best
+
+    with torch.no_grad():
+        two = best_of(lambda: dec(z))
+    fused = best_of(lambda: dec.predict(z))
+    return {"fused_ms": fused, "two_kernels_ms": two, "value": B * (T - 1) / (fused * 1e-3), "unit": UNIT,
+            "what": f"Decoder.predict, {B} trajectories x {T} times, {method}, 3 quantile heads x obs_dim 3 written as "
+                    "(B,O,T) by the solver kernel itself (slode_latent_fixed_heads_fwd), forward only; two_kernels_ms = "
+                    "Decoder.forward under no_grad (slode_latent_fixed_fwd + slode_heads_fwd)"}
 
 
 def time_cvs_epoch(dev, rank, world, sync_all):
