@@ -196,3 +196,19 @@ def test_gaussian_predict_and_fused_heads_argument_checks():
     dop = slode.GaussianDecoder(_cfg("cvs", "dopri5", False, 3), times.cuda(), L, "cuda").cuda()
     with pytest.raises(NotImplementedError):
         dop.predict(z)
+
+
+def test_predict_on_a_grid_longer_than_the_staged_one():
+    """Grids above 1024 points are read from global memory by the fused kernel (shorter ones are staged in shared
+    memory): same bits as the two-kernel path either way; T = 1100 also ends on a partial sector."""
+    import structured_latent_odes_b200 as slode
+    L, H, S, _ = U.SHAPES["cvs"]
+    for T in (1100, 1024):
+        times = torch.linspace(0.0, 30.0, T)
+        torch.manual_seed(T)
+        dec = slode.Decoder(_cfg("cvs", "euler", False, 3), times.cuda(), L, "cuda").cuda()
+        z = torch.randn(70, L, device="cuda")
+        with torch.no_grad():
+            sol, q75, q50, q25, _ = dec(z)
+        fsol, f75, f50, f25, _ = dec.predict(z, want_solution=True)
+        assert torch.equal(f50, q50) and torch.equal(f75, q75) and torch.equal(f25, q25) and torch.equal(fsol, sol)
