@@ -31,6 +31,9 @@
 #include "slode_common.cuh"
 #include "slode_mlp_api.h"
 
+#ifndef SLODE_FX_ROW_AHEAD
+#define SLODE_FX_ROW_AHEAD 2   // reverse sweep: intervals the state / cotangent rows are fetched ahead (1 or 2)
+#endif
 #ifndef SLODE_FX_FWD_MINB
 #define SLODE_FX_FWD_MINB 5
 #endif
@@ -1087,7 +1090,7 @@ __host__ __device__ constexpr size_t bwd_smem_bytes(int L, bool lat) {
   else n += (size_t)kThreads * SH::PQS;              // the warps' exchange buffers
   if (!SH::BIG) n += (size_t)(GradLayout<H, S>::total(L, lat, lat) + 3) / 4 * 4;  // block accumulators
   if (lat) n += LatSmem<H, S>::floats(L) + (size_t)kThreads * ((L + 3) / 4 * 4);  // staged nets + the warps' z rows
-  n += (size_t)2 * S * kThreads;  // the threads' state / cotangent rows of the interval in flight (cp.async targets)
+  n += (size_t)2 * SLODE_FX_ROW_AHEAD * S * kThreads;  // the threads' state / cotangent rows of the intervals in flight (cp.async targets)
   return n * sizeof(float);
 }
 
@@ -1133,8 +1136,10 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     zT = p_ + LatSmem<H, S>::floats(L) + (size_t)warp * 32 * LQ;
     p_ += LatSmem<H, S>::floats(L) + (size_t)kThreads * LQ;
   }
-  float* const rowx = p_ + tid;                 // this thread's state row of the interval in flight
-  float* const rowg = p_ + S * kThreads + tid;  // ... and its upstream-gradient row
+  constexpr int kAhead = SLODE_FX_ROW_AHEAD;
+  static_assert(kAhead == 1 || kAhead == 2, "row slots are addressed with i & (kAhead - 1)");
+  float* const rowx = p_ + tid;                          // this thread's state rows of the intervals in flight: slot i % kAhead
+  float* const rowg = p_ + kAhead * S * kThreads + tid;  // ... and its upstream-gradient rows
   stage_weights<H, S>(wt, w.w1t, w1t_stride, w.Wg, w.bg, w.Wd, w.bd);
   for (int i = tid; i < n_acc; i += kThreads) acc[i] = 0.0f;
   __syncthreads();
@@ -1194,16 +1199,25 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
     // the point of use they cost a full L2 round trip per interval (12 % of the sweep's stall samples;
     // prefetch.global.L1 does not help the read-only path), forced early into registers they occupy 12 registers
     // for a whole interval and make the evaluator's shared-memory waits wait for them too (shared scoreboards).
-    // Groups are committed in the order state(i), cotangent(i), state(i-1), ...: each read waits for all but the
-    // newest group.
+    // One interval ahead still left waits behind where an interval is shorter than an HBM round trip, so the rows are
+    // fetched TWO intervals ahead into two slots (i & 1): euler 2.19 -> 2.04 ms, midpoint odeint_adjoint 2.35 -> 2.28,
+    // midpoint discrete 2.69 -> 2.64, rk4 unchanged (3.61) at 2^20 x 100 (SLODE_FX_ROW_AHEAD=1 builds the old schedule).
+    // Groups are committed in the order state(i), cotangent(i), state(i-1), cotangent(i-1), ...: each read waits for
+    // all but the three newest groups.
     constexpr int kStateAhead = (MODE == SLODE_BWD_DISCRETE) ? 0 : 1;
     const float* px = xs + (int64_t)(T - 2 + kStateAhead) * st;   // running pointers: no 64-bit multiplies in the loop
     const float* pg = gs + (int64_t)(T - 2) * gst;
+    constexpr int kSlot = S * kThreads;   // floats between the two slots of a row
     if (T > 1) {
-      row_fetch<S>(rowx, px);
-      cp_commit();
-      row_fetch<S, true>(rowg, pg, ok);
-      cp_commit();
+#pragma unroll
+      for (int a = 0; a < kAhead; ++a) {   // intervals T-2, (T-3): groups state, cotangent, (state, cotangent)
+        if (T - 2 - a >= 0) row_fetch<S>(rowx + ((T - 2 - a) & (kAhead - 1)) * kSlot, px);
+        cp_commit();
+        if (T - 2 - a >= 0) row_fetch<S, true>(rowg + ((T - 2 - a) & (kAhead - 1)) * kSlot, pg, ok);
+        cp_commit();
+        px -= st;   // px / pg end up at the rows of the interval kAhead behind the one in hand
+        pg -= gst;
+      }
     }
     V<NP> G0, D0, G1, D1, G2, D2;   // rk4: the three evaluations of the interval in hand
     int pa = 0, pb = 0;             // rk4: walk positions after the first two seeks of the interval
@@ -1216,11 +1230,12 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
       // written inside the seek trips themselves and the separate pass over the flipped keys (another divergent trip
       // per flip) is not needed there
       auto rec_now = [&](int j) { sw.record(rec, tab, j); };
-      auto state_row = [&]() {  // the interval's state row; its slot is refilled for the next interval at once
-        cp_wait<1>();
-        const V<NP> r = row_read<S>(rowx);
+      auto state_row = [&]() {  // the interval's state row; its slot is refilled for interval i - 2 at once
+        float* const slot = rowx + (i & (kAhead - 1)) * kSlot;
+        cp_wait<2 * kAhead - 1>();
+        const V<NP> r = row_read<S>(slot);
+        if (i >= kAhead) row_fetch<S>(slot, px);
         px -= st;
-        if (i > 0) row_fetch<S>(rowx, px);
         cp_commit();
         return r;
       };
@@ -1378,11 +1393,14 @@ fixed_bwd_kernel(int64_t B, int T, const float* __restrict__ tgrid, const float*
           Dc = D2;
         }
       }
-      cp_wait<1>();
-      lam = vadd<NP>(lam, row_read<S>(rowg));   // a masked-off thread's row was zero-filled
-      pg -= gst;
-      if (i > 0) row_fetch<S, true>(rowg, pg, ok);
-      cp_commit();
+      {
+        float* const slot = rowg + (i & (kAhead - 1)) * kSlot;
+        cp_wait<2 * kAhead - 1>();
+        lam = vadd<NP>(lam, row_read<S>(slot));   // a masked-off thread's row was zero-filled
+        if (i >= kAhead) row_fetch<S, true>(slot, pg, ok);
+        pg -= gst;
+        cp_commit();
+      }
       t1 = t0;
     }
 
